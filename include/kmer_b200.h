@@ -1,0 +1,242 @@
+/*
+ * kmer_b200.h — C ABI of the B200-native k-mer counting engine (libkmerb200.so).
+ *
+ * This is the drop-in boundary for the k-mer COUNTING path of
+ * axlwild/dna-kmeres-parallel.  The reference has no FFI of its own (it is a
+ * monolithic main()); each entry point below replaces one host entry point or
+ * data contract that the reference's main() uses around the count step, and
+ * cites it as  <file>:<line>  into the reference tree.
+ *
+ * Conventions
+ *   - plain C, pointers + sizes, no torch / C++ types in any signature;
+ *   - every call returns KC_OK (0) or a negative kc_status; the message is
+ *     available from kc_last_error(ctx) (ctx may be NULL for ctx-less calls);
+ *   - library code never calls exit() (the reference does: main.cu:224-227);
+ *   - "d_" arguments are device pointers on the ctx's GPU, "h_" are host;
+ *   - plain calls are synchronous (the reference synchronises after every
+ *     launch, main.cu:291); *_async variants enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream) and
+ *     return immediately;
+ *   - one ctx is not thread-safe; distinct ctxs are.
+ *   - there is NO CPU fallback: every counting call runs sm_100a kernels.
+ *
+ * K-mer semantics (bit-exact with the reference):
+ *   window = k consecutive bytes of ONE sequence; counted iff all k bytes are
+ *   upper-case A/C/G/T (main.cu:641-644, kernels.h:133-140); forward strand
+ *   only; table index is little-endian in the string,
+ *   idx = sum_p code(s[p]) * 4^p, A=0 C=1 G=2 T=3 (utils.h:30-47).
+ */
+#ifndef KMER_B200_H
+#define KMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KC_API __attribute__((visibility("default")))
+#else
+#define KC_API
+#endif
+
+typedef enum kc_status {
+    KC_OK = 0,
+    KC_ERR_INVALID = -1,     /* bad argument (k out of range, NULL pointer, ...) */
+    KC_ERR_CUDA = -2,        /* CUDA runtime error, text in kc_last_error */
+    KC_ERR_IO = -3,          /* file could not be opened / written */
+    KC_ERR_NOMEM = -4,       /* host or device allocation failed */
+    KC_ERR_TABLE_FULL = -5,  /* sparse table capacity exhausted (caller may retry larger) */
+    KC_ERR_UNSUPPORTED = -6  /* not an sm_100 device, dense k too large, ... */
+} kc_status;
+
+typedef struct kc_ctx kc_ctx;         /* device, streams, scratch */
+typedef struct kc_seqset kc_seqset;   /* loaded FASTA records */
+typedef struct kc_sparse kc_sparse;   /* sorted (code,count) result of a sparse count */
+
+/* ------------------------------------------------------------------ */
+/* Context + errors.  Replaces the reference's implicit "device 0,     */
+/* default stream, printf+exit" conventions (main.cu:150-158,224-227). */
+/* ------------------------------------------------------------------ */
+KC_API int kc_version(void);
+KC_API int kc_ctx_create(int device, kc_ctx** out);
+KC_API void kc_ctx_destroy(kc_ctx* ctx);
+KC_API const char* kc_last_error(const kc_ctx* ctx);
+KC_API int kc_ctx_device(const kc_ctx* ctx);
+KC_API int kc_ctx_sm_count(const kc_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench "gpu_launches") */
+KC_API uint64_t kc_ctx_launch_count(const kc_ctx* ctx);
+/* block until everything enqueued through this ctx has finished */
+KC_API int kc_ctx_synchronize(kc_ctx* ctx);
+
+/* Device / pinned-host memory helpers so a C caller needs no CUDA headers.
+ * (Replaces cudaMallocManaged at main.cu:223,235,251,460,532.)            */
+KC_API int kc_device_alloc(kc_ctx* ctx, size_t nbytes, void** d_out);
+KC_API int kc_device_free(kc_ctx* ctx, void* d_ptr);
+KC_API int kc_host_alloc_pinned(kc_ctx* ctx, size_t nbytes, void** h_out);
+KC_API int kc_host_free_pinned(kc_ctx* ctx, void* h_ptr);
+KC_API int kc_memcpy_h2d(kc_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);
+KC_API int kc_memcpy_d2h(kc_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes);
+KC_API int kc_memset_d(kc_ctx* ctx, void* d_dst, int byte, size_t nbytes);
+
+/* ------------------------------------------------------------------ */
+/* k selection / k-mer enumeration.                                    */
+/* Replaces compile-time K, PERMS_KMERES (kernels.h:11-19), the        */
+/* permutation() odometer (utils.h:21-50), permutationsMap             */
+/* (main.cu:134-135) and the c_perms upload (main.cu:151-158).         */
+/* ------------------------------------------------------------------ */
+#define KC_MAX_K 31          /* uint64 codes */
+#define KC_MAX_DENSE_K 16    /* uint32 codes; table = 4^k uint32 must fit in HBM */
+
+/* 4^k, or 0 when k is outside 1..KC_MAX_K */
+KC_API uint64_t kc_num_kmers(int k);
+/* Same contract as utils.h:21 `permutation(alphabet, length, permutations)`:
+ * caller supplies |alphabet|^k buffers of >= k+1 bytes; filled in the
+ * reference's little-endian odometer order (entry 1 of "ACGT",3 is "CAA").
+ * Unlike the reference the strings ARE NUL-terminated.                     */
+KC_API int kc_permutation(const char* alphabet, int k, char** permutations);
+/* LE index of a k-mer string (KC_ERR_INVALID if a byte is not in ACGT)     */
+KC_API int kc_kmer_index(const char* kmer, int k, uint64_t* idx_out);
+/* inverse; `out` needs k+1 bytes                                          */
+KC_API int kc_kmer_string(uint64_t idx, int k, char* out);
+
+/* ------------------------------------------------------------------ */
+/* Sequence load.  Replaces importSeqs (main.cu:474-545, mode 0) and   */
+/* importSeqsNoNL (main.cu:401-473, mode 1) and their globals          */
+/* ids / seqs / indexes_aux / data / numberOfSequenses / size_all_seqs */
+/* (main.cu:34-35,65-70).  Differences, all deliberate: */
+/* terminal offset always emitted; 64-bit offsets; max_seqs<=0 means   */
+/* unlimited (reference: MAX_SEQS 100, main.cu:30).                    */
+/* ------------------------------------------------------------------ */
+#define KC_IMPORT_BLANKLINE 0   /* importSeqs: records end at a blank / CR line */
+#define KC_IMPORT_NONL 1        /* importSeqsNoNL: ... or at the next '>' line   */
+
+KC_API int kc_import_seqs(const char* path, int mode, long max_seqs, kc_seqset** out);
+/* same parser over an in-memory FASTA image */
+KC_API int kc_import_seqs_mem(const char* fasta, size_t nbytes, int mode, long max_seqs,
+                              kc_seqset** out);
+KC_API void kc_seqset_free(kc_seqset* s);
+KC_API uint32_t kc_seqset_num_seqs(const kc_seqset* s);
+KC_API uint32_t kc_seqset_num_ids(const kc_seqset* s);
+/* total bytes of `data` = sum(L_i + 1)  (reference size_all_seqs, main.cu:530) */
+KC_API uint64_t kc_seqset_nbytes(const kc_seqset* s);
+/* host image of the reference's `data`: sequences back to back, each followed
+ * by one '\0' (main.cu:537-543)                                             */
+KC_API const char* kc_seqset_data(const kc_seqset* s);
+/* num_seqs+1 start offsets into data, last = nbytes (reference `indexes`)     */
+KC_API const int64_t* kc_seqset_offsets(const kc_seqset* s);
+/* header line i (with its leading '>'), as stored in the reference's `ids`    */
+KC_API const char* kc_seqset_id(const kc_seqset* s, uint32_t i);
+/* copy data + offsets to the ctx's GPU (idempotent); pointers stay owned by s */
+KC_API int kc_seqset_to_device(kc_ctx* ctx, kc_seqset* s, const char** d_data,
+                               const int64_t** d_offsets);
+
+/* ------------------------------------------------------------------ */
+/* Counting — the hot path.                                            */
+/* ------------------------------------------------------------------ */
+
+/* Reference-shaped per-sequence table.  Replaces the kernel
+ *   sumKmereCoincidencesGlobalMemory(char* data,int* indices,unsigned num_seqs,int* sum)
+ * (kernels.h:113-144, launched main.cu:290): same `data` layout (each sequence
+ * followed by one separator byte), same kmer-major result
+ *   d_sums[entry + num_seqs * kmer]   (kernels.h:142),
+ * but any 1 <= k <= KC_MAX_DENSE_K and 64-bit offsets.  d_sums is overwritten
+ * (the reference pre-zeroes it on the host, main.cu:240-242).               */
+KC_API int kc_count_per_seq(kc_ctx* ctx, const char* d_data, const int64_t* d_offsets,
+                            uint32_t num_seqs, int k, int32_t* d_sums);
+KC_API int kc_count_per_seq_async(kc_ctx* ctx, const char* d_data, const int64_t* d_offsets,
+                                  uint32_t num_seqs, int k, int32_t* d_sums, void* stream);
+
+/* Aggregate dense table over a byte stream: d_table[idx] = number of valid
+ * windows with LE index idx among windows starting in [0, nbytes-k].  Any byte
+ * outside ACGT (separator '\0', '\n', 'N', lower case...) resets the window,
+ * so separators need no offsets.  Equals the row sums of kc_count_per_seq.
+ * d_table (uint32[4^k]) is overwritten.  Counters wrap modulo 2^32.         */
+KC_API int kc_count_dense(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k,
+                          uint32_t* d_table);
+KC_API int kc_count_dense_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k,
+                                uint32_t* d_table, void* stream);
+/* Shard form used by the multi-GPU path: ADDS (no zeroing) the windows that
+ * START in [win_begin, win_end) of a buffer whose bytes [0, nbytes) are
+ * readable (so the caller passes its shard plus a (k-1)-byte halo).         */
+#define KC_DENSE_AUTO 0      /* engine picks by k and size                    */
+#define KC_DENSE_DIRECT 1    /* smem-privatised (small k) / global-atomic bins */
+#define KC_DENSE_PARTITION 2 /* two-pass radix partition + smem sub-tables     */
+KC_API int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
+                                      uint64_t win_begin, uint64_t win_end, int k,
+                                      uint32_t* d_table, int algo, void* stream);
+/* End to end from HOST memory: chunked H2D (pinned staging, double buffered)
+ * overlapped with counting, table copied back to h_table.                   */
+KC_API int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k,
+                               uint32_t* h_table);
+
+/* Sparse counting for k <= 31 (uint64 LE codes).  Result: distinct k-mers
+ * sorted by code with their uint32 counts.                                  */
+#define KC_SPARSE_HASH 0   /* open-addressing hash table (CAS key, RED count) */
+#define KC_SPARSE_SORT 1   /* radix sort of codes + run-length reduce          */
+KC_API int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int algo,
+                           uint64_t capacity_hint, kc_sparse** out);
+KC_API void kc_sparse_free(kc_sparse* s);
+KC_API uint64_t kc_sparse_size(const kc_sparse* s);
+KC_API const uint64_t* kc_sparse_d_keys(const kc_sparse* s);    /* device, sorted */
+KC_API const uint32_t* kc_sparse_d_counts(const kc_sparse* s);  /* device */
+KC_API int kc_sparse_copy_to_host(kc_ctx* ctx, const kc_sparse* s, uint64_t* h_keys,
+                                  uint32_t* h_counts);
+/* Building blocks of the hash-sharded multi-GPU path (owner = mix64(code) % G):
+ * split a (keys,counts) list into G owner buckets (stable within a bucket),   */
+KC_API int kc_sparse_bucket_by_owner(kc_ctx* ctx, const uint64_t* d_keys,
+                                     const uint32_t* d_counts, uint64_t n, uint32_t num_owners,
+                                     uint64_t* d_keys_out, uint32_t* d_counts_out,
+                                     uint64_t* h_bucket_sizes /* [num_owners] */);
+/* merge an unsorted (keys,counts) list with duplicates into a kc_sparse       */
+KC_API int kc_sparse_merge(kc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_counts,
+                           uint64_t n, kc_sparse** out);
+/* owner hash, exported so host-side sharding logic and tests agree with the GPU */
+KC_API uint64_t kc_mix64(uint64_t code);
+
+/* ------------------------------------------------------------------ */
+/* Count table dump.  Byte-identical to the (commented-out) dump at    */
+/* main.cu:301-309: "Sums:\n", per k-mer row "%d: " then "%d,\t" per   */
+/* sequence then "\n", and a final "\n".  h_sums is a HOST table       */
+/* [4^k][num_seqs].  path == NULL writes to stdout.                    */
+/* ------------------------------------------------------------------ */
+KC_API int kc_dump_counts(const char* path, const int32_t* h_sums, int k, uint32_t num_seqs);
+
+/* ------------------------------------------------------------------ */
+/* "Next" row f1: k-mer distance step.  Replaces the num_seqs          */
+/* synchronous launches of minKmeres2 (kernels.h:85-109, main.cu:327-  */
+/* 335) with one fused all-pairs kernel.  d_dist is the reference's    */
+/* packed strict upper triangle (kernels.h:46-48), float32,            */
+/* n(n-1)/2 entries: d = 1 - sum_kmer min(c_i,c_j)/(min(L_i,L_j)-k+1). */
+/* ------------------------------------------------------------------ */
+KC_API int kc_kmer_distance(kc_ctx* ctx, const int32_t* d_sums, const int64_t* d_offsets,
+                            uint32_t num_seqs, int k, float* d_dist);
+KC_API int64_t kc_triangular_index(int64_t i, int64_t j, int64_t n); /* kernels.h:46-48 */
+/* one "%f\n" per pair (main.cu:355-358); path == NULL writes to stdout */
+KC_API int kc_dump_distances(const char* path, const float* h_dist, uint64_t n_pairs);
+
+/* ------------------------------------------------------------------ */
+/* Deterministic synthetic inputs, generated directly in  */
+/* HBM so 3.1-30 Gbp configs never cross PCIe.  The oracle has the     */
+/* same generators on the CPU (oracle/kmer_oracle.c).                  */
+/* ------------------------------------------------------------------ */
+/* base(i) = "ACGT"[splitmix64(seed + pos0 + i) >> 62], i in [0,n)            */
+KC_API int kc_gen_bases(kc_ctx* ctx, uint64_t seed, uint64_t pos0, uint64_t n, char* d_out,
+                        void* stream);
+/* config-3 style genome slice [pos0,pos0+n) of a total_len sequence: random
+ * bases with `long_runs` long N runs and `short_runs` short ones overlaid    */
+KC_API int kc_gen_genome(kc_ctx* ctx, uint64_t seed, uint64_t total_len, uint32_t long_runs,
+                         uint32_t short_runs, int k, uint64_t pos0, uint64_t n, char* d_out,
+                         void* stream);
+/* config-4/5 style reads [read0, read0+nreads): read_len bases sampled from a
+ * genome_len random genome with 1/err_den substitutions, each followed by '\n' */
+KC_API int kc_gen_reads(kc_ctx* ctx, uint64_t seed, uint64_t genome_len, uint32_t read_len,
+                        uint32_t err_den, uint64_t read0, uint64_t nreads, char* d_out,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMER_B200_H */
