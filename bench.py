@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the k-mer counting hot path.
+
+Workload (BASELINE.json configs[2], the configuration the north_star target is
+quoted on): a 3.1 Gbp human-genome-sized synthetic sequence with N runs, k = 12,
+dense 16.7M-bin histogram; STRONG scaling over --gpus N (the sequence is cut into
+N window ranges with a (k-1)-byte halo, tables merged with an NCCL reduce).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3            (our arm)
+  python bench.py --impl reference --steps 3 --warmup 1     (CPU reference arm)
+
+One JSON line on stdout (rank 0).  `value` = bases/s with the input resident in
+HBM; `e2e` = the same through the C-ABI host entry point with host buffers (H2D
+and D2H inside the timed region); `roofline` = dominant kernel vs the measured
+HBM peak; `cpu_baseline` = the oracle (a port of the reference's CPU loop) timed
+on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "dna-kmeres-parallel_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (total bases, k, long N runs, short N runs, seed)
+    "config3": dict(L=3_100_000_000, k=12, long_runs=1000, short_runs=10000, seed=0xB2000003,
+                    desc="3.1 Gbp synthetic genome with N runs, k=12 dense 16.7M-bin histogram (BASELINE configs[2])"),
+    "config2": dict(L=100_000_000, k=8, long_runs=0, short_runs=0, seed=0xB2000002,
+                    desc="100 Mbp synthetic ACGT, k=8 dense 65,536-bin histogram (BASELINE configs[1])"),
+    "config1": dict(L=1_000_000, k=3, long_runs=0, short_runs=0, seed=0xB2000001,
+                    desc="1 Mbp synthetic ACGT, k=3 (BASELINE configs[0])"),
+}
+METRIC = "bases/sec"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons while the timed region runs (NVML, 5 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's counting loop (main.cu:636-646),
+    all host threads, on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle as O
+    w = WORKLOADS[args.workload]
+    k = w["k"]
+    cores = min(os.cpu_count() or 1, 64)
+    sample = min(w["L"], args.ref_sample)
+    # generate the sample slice [0, sample) of the workload on the CPU, threaded
+    buf = np.empty(sample, dtype=np.uint8)
+    cuts = [sample * i // cores for i in range(cores + 1)]
+
+    def gen(i):
+        buf[cuts[i]:cuts[i + 1]] = O.gen_genome(w["seed"], w["L"], w["long_runs"], w["short_runs"], k, cuts[i],
+                                                cuts[i + 1] - cuts[i])
+    th = [threading.Thread(target=gen, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for _ in range(args.warmup):
+        O.count_dense(buf, k, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        table, inv = O.count_dense(buf, k, threads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    what = "first %d bases of the %s sequence per step, oracle port, %d threads" % (sample, args.workload, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": w["desc"], "k": k, "bases_per_step": sample, "kmers_per_sec": (sample - k + 1) / dt},
+        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port", "sample": what},
+        "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition")
+    ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="bases of the CPU-baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=1 << 30, help="bases per step of the reference arm")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import kmerb200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = dict(WORKLOADS[args.workload])
+    if args.length:
+        w["L"] = args.length
+    L, k = w["L"], w["k"]
+    ctx = kmerb200.Context(local)
+    nk = kmerb200.num_kmers(k)
+
+    # ---- this rank's shard: window starts [b, e), bytes [bb, be) incl. halo ----
+    b, e, bb, be = kmerb200.shard_windows(L, k, rank, world)
+    nb = be - bb
+    data = ctx.gen_genome(w["seed"], L, w["long_runs"], w["short_runs"], k, bb, nb)
+    table = torch.zeros(nk, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        table.zero_()
+        ctx.count_dense_range(data, nb, 0, e - b, k, table, algo=args.algo)
+        if world > 1:
+            dist.reduce(table, dst=0, op=dist.ReduceOp.SUM)  # int32 add == uint32 add mod 2^32
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kmerb200.lib().kc_ctx_set_timing(ctx._h, 0)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0 + args.steps  # + table.zero_() fill kernel per step
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = L / (ms_step * 1e-3)
+    checksum = int(table.to(torch.int64).sum().item()) if rank == 0 else 0
+
+    # ---- per-kernel times for the roofline (events on the launching stream) ----
+    kmerb200.lib().kc_ctx_set_timing(ctx._h, 1)
+    passes = []
+    for _ in range(min(args.steps, 10)):
+        table.zero_()
+        ctx.count_dense_range(data, nb, 0, e - b, k, table, algo=args.algo)
+        torch.cuda.synchronize()
+        a, c = kmerb200.pass_times(ctx)
+        passes.append((a, c))
+    kmerb200.lib().kc_ctx_set_timing(ctx._h, 0)
+    barrier()
+    peak, peak_src = hbm_peak()
+    p1 = float(np.mean([p[0] for p in passes]))
+    p2 = float(np.mean([p[1] for p in passes]))
+    bases_launch = e - b + k - 1
+    if p2 > 0:  # two-pass partition path
+        kernels = {"part_scatter_kernel": (p1, bases_launch), "part_count_kernel": (p2, 4 * nk)}
+    else:
+        kernels = {"dense_direct_kernel": (p1, bases_launch + 4 * nk)}
+    dom = max(kernels, key=lambda n: kernels[n][0])
+    dms, dbytes = kernels[dom]
+    achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+    step_bytes = (L + 4 * nk)
+    step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": {n: v[0] for n, v in kernels.items()},
+                "algorithmic_bytes_per_launch": dbytes,
+                "step": {"achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8000": step_gbs / 8000.0,
+                         "algorithmic_bytes": step_bytes}}
+
+    # ---- end to end through the host entry point ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        host.copy_(data)
+        h_table = torch.empty(nk, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        n_e2e = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            if world == 1:
+                ctx.count_dense_host(host, k, h_table)  # chunked H2D overlapped with counting, D2H of the table
+            else:
+                d = data.copy_(host, non_blocking=True)
+                table.zero_()
+                ctx.count_dense_range(d, nb, 0, e - b, k, table, algo=args.algo)
+                dist.reduce(table, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    h_table.copy_(table, non_blocking=True)
+                torch.cuda.synchronize()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": L / float(dt.item()), "unit": "bases/s", "h2d_bytes_per_step": int(nb) * world,
+               "d2h_bytes_per_step": 4 * nk, "ms_per_step": float(dt.item()) * 1e3, "steps": n_e2e,
+               "api": "kc_count_dense_host" if world == 1 else "H2D + kc_count_dense_range_async + NCCL reduce + D2H"}
+        if rank == 0 and world == 1:
+            assert int(h_table.to(torch.int64).sum().item()) == checksum, "e2e table differs from resident-input table"
+        del host
+
+    # ---- CPU baseline: the oracle port, 1 thread, bounded sample ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle as O
+        sample = min(nb, args.cpu_sample)
+        h = data[:sample].cpu().numpy()
+        t0 = time.perf_counter()
+        want, inv = O.count_dense(h, k, threads=1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "bases/s", "cores": 1, "kind": "port",
+               "sample": "first %d bases of the same sequence, oracle/kmer_oracle.c or_count_dense, 1 thread, %.1f s"
+                         % (sample, dt)}
+        # the sample doubles as a parity spot check of the shipped path
+        chk = torch.zeros(nk, dtype=torch.int32, device=dev)
+        ctx.count_dense_range(data, sample, 0, sample, k, chk, algo=args.algo)
+        torch.cuda.synchronize()
+        assert (chk.cpu().numpy().view(np.uint32) == want).all(), "GPU table differs from the oracle on the CPU sample"
+        cpu["parity_on_sample"] = "bit-exact"
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": w["desc"], "k": k, "bases": L, "kmers_per_sec": (L - k + 1) / (ms_step * 1e-3),
+                       "algo": {0: "auto", 1: "direct", 2: "partition"}[args.algo],
+                       "l2": "input %.1f GB per GPU exceeds the 126 MB L2 (no flush needed)" % (nb / 1e9)
+                       if nb > 512e6 else "input smaller than L2: table+scratch writes of each step evict it only partly",
+                       "sharding": "window ranges + %d-byte halo, ncclReduce of uint32[4^k]" % (k - 1) if world > 1 else "single GPU",
+                       "table_checksum": checksum},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,440 @@
+// api.cu — context, memory helpers, k-mer enumeration, FASTA loader, text dumps.
+// Host-side pieces of the C ABI (include/kmer_b200.h); no kernels here.
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+static int reserve(kc_ctx* ctx, void** p, size_t* have, size_t nbytes) {
+    if (*have >= nbytes) return KC_OK;
+    DeviceGuard dg(ctx->device);
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    // grow geometrically to keep reallocations rare, but never past what is needed by >25 %
+    size_t want = nbytes + nbytes / 4;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = nbytes;
+        e = cudaMalloc(p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return kc_set_error(ctx, KC_ERR_NOMEM, "device scratch allocation of %zu bytes failed: %s", nbytes,
+                            cudaGetErrorString(e));
+    }
+    *have = want;
+    return KC_OK;
+}
+int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes) { return reserve(ctx, &ctx->scratch, &ctx->scratch_bytes, nbytes); }
+int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes) { return reserve(ctx, &ctx->scratch2, &ctx->scratch2_bytes, nbytes); }
+
+extern "C" {
+
+int kc_version(void) { return 100; }
+
+int kc_ctx_create(int device, kc_ctx** out) {
+    if (!out) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return kc_set_error(nullptr, KC_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return kc_set_error(nullptr, KC_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return kc_set_error(nullptr, KC_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return kc_set_error(nullptr, KC_ERR_UNSUPPORTED,
+                            "device %d is sm_%d%d; libkmerb200 ships sm_100a code only (no fallback arch)", device,
+                            prop.major, prop.minor);
+    kc_ctx* ctx = new kc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    DeviceGuard dg(device);
+    // blocking streams: ordered after work the caller queued on the legacy default
+    // stream (what a torch caller uses), but independent of each other
+    if ((e = cudaStreamCreate(&ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamCreate(&ctx->copy_stream)) != cudaSuccess) {
+        delete ctx;
+        return kc_set_error(nullptr, KC_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return KC_OK;
+}
+
+void kc_ctx_destroy(kc_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard dg(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& ev : ctx->tev)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char* kc_last_error(const kc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+int kc_ctx_device(const kc_ctx* ctx) { return ctx ? ctx->device : -1; }
+int kc_ctx_sm_count(const kc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t kc_ctx_launch_count(const kc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int kc_ctx_synchronize(kc_ctx* ctx) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return KC_OK;
+}
+
+int kc_ctx_set_timing(kc_ctx* ctx, int enabled) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    if (enabled)
+        for (auto& ev : ctx->tev)
+            if (!ev) KC_CUDA(ctx, cudaEventCreate(&ev));
+    ctx->timing = enabled != 0;
+    ctx->timed_kernels = 0;
+    return KC_OK;
+}
+
+int kc_ctx_pass_times(kc_ctx* ctx, float* first_ms, float* second_ms) {
+    if (!ctx || !first_ms || !second_ms) return KC_ERR_INVALID;
+    *first_ms = *second_ms = 0.f;
+    if (!ctx->timing || ctx->timed_kernels == 0) return KC_OK;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaEventSynchronize(ctx->tev[ctx->timed_kernels]));
+    KC_CUDA(ctx, cudaEventElapsedTime(first_ms, ctx->tev[0], ctx->tev[1]));
+    if (ctx->timed_kernels == 2) KC_CUDA(ctx, cudaEventElapsedTime(second_ms, ctx->tev[1], ctx->tev[2]));
+    return KC_OK;
+}
+
+int kc_device_alloc(kc_ctx* ctx, size_t nbytes, void** d_out) {
+    if (!ctx || !d_out) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    cudaError_t e = cudaMalloc(d_out, nbytes ? nbytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *d_out = nullptr;
+        return kc_set_error(ctx, KC_ERR_NOMEM, "cudaMalloc(%zu): %s", nbytes, cudaGetErrorString(e));
+    }
+    return KC_OK;
+}
+int kc_device_free(kc_ctx* ctx, void* d_ptr) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaFree(d_ptr));
+    return KC_OK;
+}
+int kc_host_alloc_pinned(kc_ctx* ctx, size_t nbytes, void** h_out) {
+    if (!ctx || !h_out) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    cudaError_t e = cudaHostAlloc(h_out, nbytes ? nbytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *h_out = nullptr;
+        return kc_set_error(ctx, KC_ERR_NOMEM, "cudaHostAlloc(%zu): %s", nbytes, cudaGetErrorString(e));
+    }
+    return KC_OK;
+}
+int kc_host_free_pinned(kc_ctx* ctx, void* h_ptr) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaFreeHost(h_ptr));
+    return KC_OK;
+}
+int kc_memcpy_h2d(kc_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KC_OK;
+}
+int kc_memcpy_d2h(kc_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KC_OK;
+}
+int kc_memset_d(kc_ctx* ctx, void* d_dst, int byte, size_t nbytes) {
+    if (!ctx) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    KC_CUDA(ctx, cudaMemsetAsync(d_dst, byte, nbytes, ctx->stream));
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k selection / enumeration (utils.h:21-50, main.cu:122-135)
+// ---------------------------------------------------------------------------
+uint64_t kc_num_kmers(int k) { return (k < 1 || k > KC_MAX_K) ? 0 : (1ull << (2 * k)); }
+
+static inline int base_code(unsigned char c) {
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+}
+
+int kc_permutation(const char* alphabet, int k, char** permutations) {
+    if (!alphabet || !permutations || k < 1) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_permutation: bad argument");
+    const size_t na = strlen(alphabet);
+    if (na < 1) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_permutation: empty alphabet");
+    // |alphabet|^k entries; entry i spells the base-|alphabet| digits of i with
+    // string position 0 as the LEAST significant digit (the reference's odometer
+    // increments letterIdx[0] first, utils.h:36-46).
+    uint64_t total = 1;
+    for (int i = 0; i < k; i++) {
+        if (total > (1ull << 40) / na) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_permutation: %zu^%d too large", na, k);
+        total *= na;
+    }
+    std::vector<uint32_t> digit(k, 0);
+    for (uint64_t i = 0; i < total; i++) {
+        char* dst = permutations[i];
+        for (int p = 0; p < k; p++) dst[p] = alphabet[digit[p]];
+        dst[k] = '\0';
+        for (int p = 0; p < k; p++) {
+            if (++digit[p] < na) break;
+            digit[p] = 0;
+        }
+    }
+    return KC_OK;
+}
+
+int kc_kmer_index(const char* kmer, int k, uint64_t* idx_out) {
+    if (!kmer || !idx_out || k < 1 || k > KC_MAX_K) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_kmer_index: bad argument");
+    uint64_t v = 0;
+    for (int p = 0; p < k; p++) {
+        const int c = base_code((unsigned char)kmer[p]);
+        if (c < 0) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_kmer_index: byte 0x%02x at %d is not in ACGT", (unsigned char)kmer[p], p);
+        v |= (uint64_t)c << (2 * p);
+    }
+    *idx_out = v;
+    return KC_OK;
+}
+
+int kc_kmer_string(uint64_t idx, int k, char* out) {
+    if (!out || k < 1 || k > KC_MAX_K || (k < 32 && (idx >> (2 * k)) != 0))
+        return kc_set_error(nullptr, KC_ERR_INVALID, "kc_kmer_string: bad argument");
+    for (int p = 0; p < k; p++) out[p] = "ACGT"[(idx >> (2 * p)) & 3];
+    out[k] = '\0';
+    return KC_OK;
+}
+
+uint64_t kc_mix64(uint64_t code) { return kc_mix64_hd(code); }
+
+int64_t kc_triangular_index(int64_t i, int64_t j, int64_t n) {
+    // kernels.h:46-48 — i is 1-based, j is the gap to the later sequence
+    return (n * (i - 1) - (((i - 2) * (i - 1)) / 2)) + (j - i);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// FASTA loader (importSeqs main.cu:474-545, importSeqsNoNL main.cu:401-473)
+// ---------------------------------------------------------------------------
+struct kc_seqset {
+    std::vector<std::string> ids;
+    std::string data;               // sequences, each followed by '\0'
+    std::vector<int64_t> offsets;   // num_seqs + 1
+    uint32_t num_seqs = 0;
+    // device copies
+    kc_ctx* owner = nullptr;
+    char* d_data = nullptr;
+    int64_t* d_offsets = nullptr;
+};
+
+namespace {
+// std::getline over a memory image: yields every '\n'-terminated line plus a
+// final unterminated one, like the ifstream loop at main.cu:487.
+struct LineReader {
+    const char* p;
+    const char* end;
+    bool next(const char*& line, size_t& len) {
+        if (p >= end) return false;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        line = p;
+        if (nl) {
+            len = (size_t)(nl - p);
+            p = nl + 1;
+        } else {
+            len = (size_t)(end - p);
+            p = end;
+        }
+        return true;
+    }
+};
+
+void close_record(kc_seqset* s, std::string& acc) {
+    s->offsets.push_back((int64_t)s->data.size());
+    for (char& ch : acc)
+        if (ch == '|') ch = '\0';  // main.cu:538-541 turns every '|' of globalAcc into NUL
+    s->data.append(acc);
+    s->data.push_back('\0');       // the record's own '|' separator (main.cu:505,517)
+    s->num_seqs++;
+    acc.clear();
+}
+
+int parse_fasta(const char* img, size_t n, int mode, long max_seqs, kc_seqset* s) {
+    LineReader rd{img, img + n};
+    const char* line;
+    size_t len;
+    bool armed = false, stop = false;
+    std::string acc;
+    while (!stop && rd.next(line, len)) {
+        if (len == 0) continue;  // blank line between records
+        if (line[0] == '>') {
+            s->ids.emplace_back(line, len);
+            armed = true;
+            continue;
+        }
+        if (!armed) continue;  // sequence text without a header is dropped
+        armed = false;
+        acc.assign(line, len);
+        bool closed = false;
+        while (rd.next(line, len)) {
+            const bool header = (mode == KC_IMPORT_NONL && len > 0 && line[0] == '>');
+            if (header) armed = true;  // NoNL: the header ends the record but is not kept
+            if (len == 0 || line[0] == '\r' || header) {
+                close_record(s, acc);
+                closed = true;
+                break;
+            }
+            acc.append(line, len);
+            if (max_seqs > 0 && (long)s->num_seqs >= max_seqs) break;
+        }
+        if (!closed && !acc.empty()) {
+            close_record(s, acc);
+            if (max_seqs > 0 && (long)s->num_seqs >= max_seqs) stop = true;
+        }
+    }
+    s->offsets.push_back((int64_t)s->data.size());  // terminal offset, always
+    return KC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int kc_import_seqs_mem(const char* fasta, size_t nbytes, int mode, long max_seqs, kc_seqset** out) {
+    if (!out || (!fasta && nbytes)) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs_mem: null pointer");
+    if (mode != KC_IMPORT_BLANKLINE && mode != KC_IMPORT_NONL)
+        return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs: unknown mode %d", mode);
+    kc_seqset* s = new kc_seqset();
+    parse_fasta(fasta, nbytes, mode, max_seqs, s);
+    *out = s;
+    return KC_OK;
+}
+
+int kc_import_seqs(const char* path, int mode, long max_seqs, kc_seqset** out) {
+    if (!path || !out) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs: null pointer");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    // the reference prints "Error opening" and exit(0)s here (main.cu:477-480)
+    if (!f) return kc_set_error(nullptr, KC_ERR_IO, "Error opening: %s . Check your file or path.", path);
+    std::string img;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0) img.append(buf, got);
+    fclose(f);
+    return kc_import_seqs_mem(img.data(), img.size(), mode, max_seqs, out);
+}
+
+void kc_seqset_free(kc_seqset* s) {
+    if (!s) return;
+    if (s->owner) {
+        DeviceGuard dg(s->owner->device);
+        if (s->d_data) cudaFree(s->d_data);
+        if (s->d_offsets) cudaFree(s->d_offsets);
+    }
+    delete s;
+}
+uint32_t kc_seqset_num_seqs(const kc_seqset* s) { return s ? s->num_seqs : 0; }
+uint32_t kc_seqset_num_ids(const kc_seqset* s) { return s ? (uint32_t)s->ids.size() : 0; }
+uint64_t kc_seqset_nbytes(const kc_seqset* s) { return s ? s->data.size() : 0; }
+const char* kc_seqset_data(const kc_seqset* s) { return s ? s->data.data() : nullptr; }
+const int64_t* kc_seqset_offsets(const kc_seqset* s) { return s ? s->offsets.data() : nullptr; }
+const char* kc_seqset_id(const kc_seqset* s, uint32_t i) {
+    return (s && i < s->ids.size()) ? s->ids[i].c_str() : nullptr;
+}
+
+int kc_seqset_to_device(kc_ctx* ctx, kc_seqset* s, const char** d_data, const int64_t** d_offsets) {
+    if (!ctx || !s) return KC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    if (!s->d_data) {
+        s->owner = ctx;
+        KC_CUDA(ctx, cudaMalloc(&s->d_data, s->data.size() ? s->data.size() : 1));
+        KC_CUDA(ctx, cudaMalloc(&s->d_offsets, s->offsets.size() * sizeof(int64_t)));
+        KC_CUDA(ctx, cudaMemcpyAsync(s->d_data, s->data.data(), s->data.size(), cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(ctx, cudaMemcpyAsync(s->d_offsets, s->offsets.data(), s->offsets.size() * sizeof(int64_t),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (d_data) *d_data = s->d_data;
+    if (d_offsets) *d_offsets = s->d_offsets;
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// text dumps (main.cu:301-309 and main.cu:355-358)
+// ---------------------------------------------------------------------------
+int kc_dump_counts(const char* path, const int32_t* h_sums, int k, uint32_t num_seqs) {
+    if (!h_sums || k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_dump_counts: bad argument");
+    FILE* f = path ? fopen(path, "w") : stdout;
+    if (!f) return kc_set_error(nullptr, KC_ERR_IO, "kc_dump_counts: cannot open %s", path);
+    const uint64_t nk = 1ull << (2 * k);
+    fprintf(f, "Sums:\n");
+    uint64_t idx = 0;
+    for (uint64_t j = 0; j < nk; j++) {
+        fprintf(f, "%d: ", (int)j);
+        for (uint32_t i = 0; i < num_seqs; i++) fprintf(f, "%d,\t", h_sums[idx++]);
+        fprintf(f, "\n");
+    }
+    fprintf(f, "\n");
+    if (path)
+        fclose(f);
+    else
+        fflush(f);
+    return KC_OK;
+}
+
+int kc_dump_distances(const char* path, const float* h_dist, uint64_t n_pairs) {
+    if (!h_dist && n_pairs) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_dump_distances: null pointer");
+    FILE* f = path ? fopen(path, "w") : stdout;
+    if (!f) return kc_set_error(nullptr, KC_ERR_IO, "kc_dump_distances: cannot open %s", path);
+    for (uint64_t i = 0; i < n_pairs; i++) fprintf(f, "%f\n", h_dist[i]);
+    if (path)
+        fclose(f);
+    else
+        fflush(f);
+    return KC_OK;
+}
+
+}  // extern "C"

@@ -70,6 +70,12 @@ KC_API int kc_ctx_sm_count(const kc_ctx* ctx);
 KC_API uint64_t kc_ctx_launch_count(const kc_ctx* ctx);
 /* block until everything enqueued through this ctx has finished */
 KC_API int kc_ctx_synchronize(kc_ctx* ctx);
+/* Measurement aid: when enabled, the dense entry points bracket their kernels
+ * with CUDA events on the launching stream; after the stream is synchronised
+ * kc_ctx_pass_times returns the device time of the last call's kernels in ms
+ * (direct path: *first = kernel, *second = 0; partition path: scatter, count). */
+KC_API int kc_ctx_set_timing(kc_ctx* ctx, int enabled);
+KC_API int kc_ctx_pass_times(kc_ctx* ctx, float* first_ms, float* second_ms);
 
 /* Device / pinned-host memory helpers so a C caller needs no CUDA headers.
  * (Replaces cudaMallocManaged at main.cu:223,235,251,460,532.)            */
