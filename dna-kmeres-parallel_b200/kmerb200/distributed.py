@@ -1,0 +1,116 @@
+"""Multi-GPU host logic: one process per GPU, torch.distributed for the plumbing
+(NCCL over NVLink on the GPU box, gloo in the CPU tests).  SURVEY.md §8e.
+
+dense   : the sequence is cut into window ranges; each rank reads its bytes plus
+          a (k-1)-byte halo and counts only windows STARTING in its range, so no
+          carry is exchanged; the uint32[4^k] tables are summed with one reduce
+          (int32 views: two's-complement add == uint32 add mod 2^32).
+sparse  : reads are cut by read index; each rank counts locally, buckets its
+          (code, count) pairs by owner = mix64(code) % world, exchanges buckets
+          with one all-to-all, and the owner merges what it received: every rank
+          ends with a disjoint, sorted key range of the global result.
+
+The functions take the local "engine" as callables so the same code runs on the
+GPU (kmerb200.Context) and in the gloo tests (the oracle stands in on the CPU).
+"""
+import numpy as np
+
+from . import shard_reads, shard_windows  # noqa: F401  (re-exported)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def reduce_table(table, dst=0):
+    """Sum uint32 tables (held as int32 torch tensors) onto rank `dst`."""
+    dist = _dist()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(table, dst=dst, op=dist.ReduceOp.SUM)
+    return table
+
+
+def all_reduce_table(table):
+    dist = _dist()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(table, op=dist.ReduceOp.SUM)
+    return table
+
+
+def exchange_by_owner(keys, counts, sizes):
+    """keys (int64) / counts (int32) torch tensors laid out owner by owner with
+    `sizes[o]` entries for owner o.  Returns what this rank owns: (keys, counts)
+    concatenated over senders."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size()
+    dev = keys.device
+    send = torch.tensor([int(s) for s in sizes], dtype=torch.int64, device=dev)
+    recv = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send)
+    in_splits = [int(x) for x in send.cpu().tolist()]
+    out_splits = [int(x) for x in recv.cpu().tolist()]
+    rkeys = torch.empty(sum(out_splits), dtype=keys.dtype, device=dev)
+    rcounts = torch.empty(sum(out_splits), dtype=counts.dtype, device=dev)
+    dist.all_to_all_single(rkeys, keys[: sum(in_splits)].contiguous(), out_splits, in_splits)
+    dist.all_to_all_single(rcounts, counts[: sum(in_splits)].contiguous(), out_splits, in_splits)
+    return rkeys, rcounts
+
+
+def count_dense_sharded(count_range, make_shard, nbytes, k, table, rank, world, dst=0):
+    """count_range(shard, shard_nbytes, win_begin, win_end, table) adds into `table`;
+    make_shard(byte_begin, byte_end) returns this rank's bytes.  The reduced table
+    lands on rank `dst`."""
+    b, e, bb, be = shard_windows(nbytes, k, rank, world)
+    if e > b:
+        shard = make_shard(bb, be)
+        count_range(shard, be - bb, 0, e - b, table)
+    return reduce_table(table, dst)
+
+
+def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):
+    """GPU path of the hash-sharded all-to-all: `d_reads` holds THIS rank's reads.
+    Returns a kmerb200.Sparse with the keys this rank owns."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    local = ctx.count_sparse(d_reads, nbytes, k, algo)
+    if world == 1:
+        return local
+    n = len(local)
+    dev = "cuda:%d" % ctx.device
+    ok = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    oc = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    sizes = ctx.sparse_bucket_by_owner(local.d_keys, local.d_counts, n, world, ok, oc)
+    local.close()
+    rk, rc = exchange_by_owner(ok, oc, sizes)
+    torch.cuda.synchronize()
+    return ctx.sparse_merge(rk, rc, rk.numel())
+
+
+# ---- numpy stand-ins used by the CPU (gloo) tests ---------------------------
+def mix64_np(x):
+    x = np.asarray(x, dtype=np.uint64).copy()
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xFF51AFD7ED558CCD)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xC4CEB9FE1A85EC53)
+    x ^= x >> np.uint64(33)
+    return x
+
+
+def bucket_by_owner_np(keys, counts, world):
+    owner = (mix64_np(keys) % np.uint64(world)).astype(np.int64)
+    order = np.argsort(owner, kind="stable")
+    sizes = np.bincount(owner, minlength=world)
+    return keys[order], counts[order], sizes
+
+
+def merge_np(keys, counts):
+    if keys.size == 0:
+        return keys, counts
+    order = np.argsort(keys, kind="stable")
+    k, c = keys[order], counts[order].astype(np.uint64)
+    uniq, start = np.unique(k, return_index=True)
+    return uniq, np.add.reduceat(c, start).astype(np.uint32)

@@ -1,0 +1,39 @@
+"""The N>1 host path (shards, halo, reduce, owner all-to-all) at world_size 2 on the
+CPU with gloo; the oracle stands in for the per-rank GPU engine."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_world2_gloo():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29653", os.path.join(ROOT, "tests", "_gloo_worker.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "GLOO_WORKER_OK world=2" in r.stdout
+
+
+def test_mix64_np_matches_engine(kmerlib, oracle):
+    from kmerb200 import distributed as D
+    xs = np.array([0, 1, 0xDEADBEEF, (1 << 62) - 1, 12345678901234567], dtype=np.uint64)
+    got = D.mix64_np(xs)
+    assert [int(g) for g in got] == [kmerlib.mix64(int(x)) for x in xs] == [oracle.mix64(int(x)) for x in xs]
+
+
+def test_merge_and_bucket_np():
+    from kmerb200 import distributed as D
+    keys = np.array([5, 9, 5, 1, 9, 9], dtype=np.uint64)
+    counts = np.array([1, 2, 3, 4, 5, 6], dtype=np.uint32)
+    k, c = D.merge_np(keys, counts)
+    assert k.tolist() == [1, 5, 9] and c.tolist() == [4, 4, 13]
+    bk, bc, sizes = D.bucket_by_owner_np(keys, counts, 3)
+    assert sizes.sum() == 6 and sorted(bk.tolist()) == sorted(keys.tolist())
+    start = 0
+    for o in range(3):
+        assert ((D.mix64_np(bk[start:start + sizes[o]]) % np.uint64(3)) == o).all()
+        start += sizes[o]
