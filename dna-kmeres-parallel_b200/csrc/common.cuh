@@ -212,6 +212,29 @@ __device__ __forceinline__ Decoded16 kc_load_block(const ScanGeom& g, uint64_t b
     return d;
 }
 
+// Split form for software pipelining: issue the 128-bit load early, decode when
+// the data is needed (keeps two loads per lane in flight).
+__device__ __forceinline__ uint4 kc_issue_block(const ScanGeom& g, uint64_t b) {
+    const uint64_t a0 = b << 4;
+    if (a0 + 16 <= g.lo || a0 >= g.hi) return make_uint4(0, 0, 0, 0);
+    return kc_ldg_stream(g.abase + b);
+}
+__device__ __forceinline__ Decoded16 kc_finish_block(const ScanGeom& g, uint64_t b, uint4 raw) {
+    const uint64_t a0 = b << 4;
+    Decoded16 d = kc_decode16(raw);  // an all-zero block decodes to 16 bad bases
+    if (a0 < g.lo || a0 + 16 > g.hi) {
+        if (a0 + 16 <= g.lo || a0 >= g.hi) {
+            d.bad = 0xFFFFu;
+        } else {
+            const int l = a0 < g.lo ? (int)(g.lo - a0) : 0;
+            const int h = a0 + 16 > g.hi ? (int)(g.hi - a0) : 16;
+            const uint32_t keep = ((1u << h) - 1u) & ~((1u << l) - 1u);
+            d.bad |= ~keep & 0xFFFFu;
+        }
+    }
+    return d;
+}
+
 // One lane's view of a 512-byte group: 16 own bases + up to 32 halo bases.
 template <int HALO>
 struct LaneWindow {

@@ -15,6 +15,8 @@
 //       atomics, then adds them to the global table in 128-byte runs.
 //       Random scatter to a 64 MiB table moves from L2 (<= 1 sector/clk/SM) into
 //       shared memory (32 banks/clk/SM).  See DESIGN.md §3.3.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -84,142 +86,238 @@ __device__ __forceinline__ uint32_t part_code(uint32_t rec, int r) {
     return (rec >> (2 * r)) & ((C::K == 16) ? 0xFFFFFFFFu : ((1u << (2 * C::K)) - 1u));
 }
 
+// plain RED (inline PTX: no compiler warp-aggregation wrapper around it)
+__device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <typename C>
 __device__ __forceinline__ void part_fallback(uint32_t rec, uint32_t okbits, uint32_t* table) {
 #pragma unroll
     for (int r = 0; r < C::A; r++)
-        if (okbits & (1u << r)) atomicAdd(&table[part_code<C>(rec, r)], 1u);
+        if (okbits & (1u << r)) global_red_add(table + part_code<C>(rec, r), 1u);
+}
+
+// ---- shared-memory primitives as inline PTX (32-bit shared addresses): keeps
+// ptxas from wrapping atomicAdd in its warp-aggregation sequence and pins the
+// program order the staging protocol below relies on.
+__device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_ld(uint32_t saddr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+    return r;
 }
 
 // Pass 1.  1024 threads, one CTA per SM, each warp owns a contiguous run of
-// 512-byte groups.  Shared memory: cnt[P], gbase[P], buf[P][CAP].
-template <typename C, int FLUSH_EVERY>
+// 512-byte groups and never waits for another warp: there is no CTA barrier and
+// no global atomic in the main loop.
+//
+// Shared memory per CTA: state[P] (low 16 bits = slots reserved, high 16 bits =
+// slots written), cur[P] (records already flushed to this CTA's private region of
+// partition p), buf[P][CAP] (staged records; CAP = 24 = one 96-byte chunk of
+// three full 32-byte sectors).
+//
+// Staging protocol (all shared-memory, CTA scope):
+//   writer : slot = atom.add(state[p], 1) & 0xFFFF;
+//            slot <  CAP : buf[p][slot] = rec; w = atom.add(state[p], 1<<16) >> 16;
+//                          the writer that makes w == CAP-1 has seen every slot
+//                          written and its warp flushes the bin;
+//            slot >= CAP : the bin is full and its flush is in flight (a window of
+//                          a few dozen cycles) -> count the record's windows with
+//                          global REDs instead (~1 % of records).
+//   flusher: the whole warp reads buf[p][0..CAP) into registers, lane 0 resets
+//            state[p] = 0 (one store clears both halves, so a new generation can
+//            start immediately) and advances cur[p]; then CAP lanes write one
+//            aligned chunk to the CTA's private global region.
+// Shared-memory requests of a warp are performed in program order, so a writer's
+// store precedes its "written" increment and the flusher's loads precede its
+// reset; any record a later generation stores therefore lands after the loads.
+// Every record is consumed exactly once: by a chunk, by the final flush, or by
+// the RED fallback.  Parity against the oracle at 3.1 G windows checks this.
+//
+// Global layout: slabs[cta][p][region_cap] — a CTA writes into one contiguous
+// area, the (cta, p) regions need no global cursor, counts[p][cta] is published
+// at the end.
+template <typename C>
 __global__ void __launch_bounds__(1024, 1)
 part_scatter_kernel(ScanGeom g, uint32_t* __restrict__ table, uint32_t* __restrict__ slabs,
-                    uint32_t* __restrict__ gcursor, uint32_t slab_cap) {
+                    uint32_t* __restrict__ counts, uint32_t region_cap) {
     extern __shared__ uint32_t smem[];
-    uint32_t* cnt = smem;
-    uint32_t* gbase = smem + C::P;
-    uint32_t* buf = smem + 2 * C::P;
+    const uint32_t s_state = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t s_cur = s_state + C::P * 4;
+    const uint32_t s_buf = s_state + 2 * C::P * 4;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    for (int b = tid; b < C::P; b += 1024) cnt[b] = 0;
+    // cur[p] holds the absolute word offset (inside this CTA's slab area) of the next chunk
+    for (int b = tid; b < C::P; b += 1024) {
+        smem[b] = 0;
+        smem[C::P + b] = b * region_cap;
+    }
     __syncthreads();
 
-    // every warp of the CTA runs the same number of steps so the CTA-wide
-    // flush barriers line up; warps past the end scan empty ranges.
     const uint64_t ngroups = g.g_end - g.g_begin;
     const uint64_t nwarps = (uint64_t)gridDim.x * 32;
     const uint64_t gpw = (ngroups + nwarps - 1) / nwarps;
     const uint64_t w = (uint64_t)blockIdx.x * 32 + (tid >> 5);
     const uint64_t gb = g.g_begin + min(w * gpw, ngroups);
     const uint64_t ge = g.g_begin + min((w + 1) * gpw, ngroups);
+    uint32_t* const my_slabs = slabs + (uint64_t)blockIdx.x * C::P * region_cap;  // < 2^32 words per CTA
+    const uint32_t lane_slot = (uint32_t)min(lane, C::CAP - 1) * 4;
 
-    auto flush = [&]() {
-        __syncthreads();
-        for (int b = tid; b < C::P; b += 1024) {
-            const uint32_t c = min(cnt[b], (uint32_t)C::CAP);
-            gbase[b] = c ? atomicAdd(&gcursor[b], c) : 0u;
+    auto flush_bin = [&](uint32_t b) {  // whole warp, converged
+        const uint32_t r = smem_ld(s_buf + b * (C::CAP * 4) + lane_slot);
+        __syncwarp();
+        uint32_t pos = 0;
+        if (lane == 0) {
+            smem_st(s_state + b * 4, 0u);
+            pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
         }
-        __syncthreads();
-        const int hw = tid >> 4, l16 = tid & 15;
-        for (int b = hw; b < C::P; b += 64) {
-            const uint32_t c = min(cnt[b], (uint32_t)C::CAP);
-            const uint32_t gbs = gbase[b];
-            for (uint32_t s = l16; s < c; s += 16) {
-                const uint32_t rec = buf[b * C::CAP + s];
-                const uint32_t gi = gbs + s;
-                if (gi < slab_cap)
-                    slabs[(uint64_t)b * slab_cap + gi] = rec;
-                else
-                    part_fallback<C>(rec, C::AMASK, table);
-            }
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (lane < C::CAP) {
+            if (pos + C::CAP <= (b + 1) * region_cap)
+                my_slabs[pos + lane] = r;
+            else
+                part_fallback<C>(r, C::AMASK, table);
         }
-        __syncthreads();
-        for (int b = tid; b < C::P; b += 1024) cnt[b] = 0;
-        __syncthreads();
     };
 
-    Decoded16 cur = kc_load_block(g, gb * 32 + lane);
-    for (uint64_t step = 0; step < gpw; step++) {
-        const uint64_t grp = gb + step;
-        if (grp < ge) {  // warp-uniform
+    // one record: reserve, store, publish; returns true when this lane completed the bin
+    auto emit = [&](uint32_t rec, uint32_t& pid) -> bool {
+        pid = (rec >> C::KB0) & (C::P - 1);
+        const uint32_t slot = smem_atom_add(s_state + pid * 4, 1u) & 0xFFFFu;
+        if (slot < (uint32_t)C::CAP) {
+            smem_st(s_buf + pid * (C::CAP * 4) + slot * 4, rec);
+            return (smem_atom_add(s_state + pid * 4, 0x10000u) >> 16) == (uint32_t)C::CAP - 1;
+        }
+        part_fallback<C>(rec, C::AMASK, table);
+        return false;
+    };
+
+    if (gb < ge) {
+        const uint32_t nsteps = (uint32_t)(ge - gb);
+        // steps [i_lo, i_hi) lie fully inside the buffer and the window range, together
+        // with the 2 groups of look-ahead the loads need and the 20 positions a record needs
+        const uint64_t safe_lo = (max(g.lo, g.wlo) + 511) >> 9;
+        const uint64_t lim = min(g.hi, g.whi);
+        const uint64_t safe_hi = lim >= 2048 ? ((lim - 32) >> 9) - 3 : 0;  // last interior group + 1
+        const uint32_t i_lo = safe_lo > gb ? (uint32_t)min((uint64_t)nsteps, safe_lo - gb) : 0u;
+        const uint32_t i_hi = safe_hi > gb ? (uint32_t)min((uint64_t)nsteps, safe_hi - gb) : 0u;
+        // (a0 - wlo) mod A for this lane, advanced by 512 mod A per group
+        const int64_t delta0 = (int64_t)(((gb * 32 + lane) << 4)) - (int64_t)g.wlo;
+        int d = (int)(((delta0 % C::A) + C::A) % C::A);
+        const uint4* ptr = g.abase + gb * 32 + lane;  // block of this lane in the current group
+        uint4 raw1 = kc_issue_block(g, (gb + 1) * 32 + lane);
+        Decoded16 cur16 = kc_finish_block(g, gb * 32 + lane, kc_issue_block(g, gb * 32 + lane));
+        for (uint32_t i = 0; i < nsteps; i++, ptr += 32) {
+            const bool interior = i >= i_lo && i < i_hi;  // warp-uniform
+            uint4 raw2;
             Decoded16 nxt;
-            if (grp + 1 < ge || lane < 1) {
-                nxt = kc_load_block(g, (grp + 1) * 32 + lane);
+            if (interior) {
+                raw2 = kc_ldg_stream(ptr + 64);
+                nxt = kc_decode16(raw1);
             } else {
-                nxt.packed = 0;
-                nxt.bad = 0xFFFFu;
+                const uint64_t grp = gb + i;
+                raw2 = kc_issue_block(g, (grp + 2) * 32 + lane);
+                nxt = kc_finish_block(g, (grp + 1) * 32 + lane, raw1);
             }
-            uint32_t p1 = __shfl_down_sync(0xffffffffu, cur.packed, 1);
-            uint32_t b1 = __shfl_down_sync(0xffffffffu, cur.bad, 1);
+            uint32_t p1 = __shfl_down_sync(0xffffffffu, cur16.packed, 1);
+            uint32_t b1 = __shfl_down_sync(0xffffffffu, cur16.bad, 1);
             const uint32_t n0p = __shfl_sync(0xffffffffu, nxt.packed, 0);
             const uint32_t n0b = __shfl_sync(0xffffffffu, nxt.bad, 0);
             if (lane == 31) {
                 p1 = n0p;
                 b1 = n0b;
             }
-            const uint32_t p0 = cur.packed;
-            const uint64_t B = (uint64_t)cur.bad | ((uint64_t)b1 << 16) | (0xFFFFull << 32);
-            const uint64_t a0 = (grp * 32 + lane) << 4;
-            uint32_t ok = ~(uint32_t)kc_window_bad(B, C::K);  // 32 window starts
-            if ((grp << 9) < g.wlo || ((grp + 1) << 9) + 16 > g.whi) {
+            const uint32_t p0 = cur16.packed;
+            const uint32_t B32 = cur16.bad | (b1 << 16);
+            uint32_t ok = (1u << (33 - C::K)) - 1u;  // the windows that fit the 32 known bases
+            if (B32) ok = ~(uint32_t)kc_window_bad((uint64_t)B32 | (0xFFFFull << 32), C::K);
+            int j0 = d ? C::A - d : 0;  // first record start among this lane's 16 positions, 0..A-1
+            if (!interior) {
+                const uint64_t a0 = (gb + i) * 512 + (uint64_t)lane * 16;
                 const int l = a0 < g.wlo ? (int)min((uint64_t)32, g.wlo - a0) : 0;
                 const int h = a0 + 32 > g.whi ? (int)(g.whi > a0 ? g.whi - a0 : 0) : 32;
                 const uint32_t hm = h >= 32 ? 0xFFFFFFFFu : ((1u << h) - 1u);
                 const uint32_t lm = l >= 32 ? 0xFFFFFFFFu : ((1u << l) - 1u);
                 ok &= hm & ~lm;
-            }
-            // records start at aligned coordinates wlo + A*m
-            int j0;
-            if (a0 >= g.wlo) {
-                const uint32_t d = (uint32_t)((a0 - g.wlo) % (uint64_t)C::A);
-                j0 = d ? C::A - (int)d : 0;
-            } else {
-                j0 = (int)min((uint64_t)64, g.wlo - a0);
-            }
-#pragma unroll
-            for (int t = 0; t < (16 + C::A - 1) / C::A; t++) {
-                const int j = j0 + t * C::A;
-                if (j < 16) {
-                    const uint32_t okr = (ok >> j) & C::AMASK;
-                    if (okr) {
-                        const uint32_t rec = __funnelshift_r(p0, p1, 2 * j);
-                        if (okr == C::AMASK) {
-                            const uint32_t pid = (rec >> C::KB0) & (C::P - 1);
-                            const uint32_t slot = atomicAdd(&cnt[pid], 1u);
-                            if (slot < (uint32_t)C::CAP) {
-                                buf[pid * C::CAP + slot] = rec;
-                            } else {
-                                const uint32_t gi = atomicAdd(&gcursor[pid], 1u);
-                                if (gi < slab_cap)
-                                    slabs[(uint64_t)pid * slab_cap + gi] = rec;
-                                else
-                                    part_fallback<C>(rec, C::AMASK, table);
-                            }
-                        } else {
-                            part_fallback<C>(rec, okr, table);
-                        }
+                if (a0 < g.wlo) {  // the first record starts at wlo itself
+                    if (g.wlo - a0 < 16) {
+                        j0 = (int)(g.wlo - a0);
+                    } else {
+                        j0 = 0;
+                        ok = 0;
                     }
                 }
             }
-            cur = nxt;
+            // records at j = j0, j0+A, ... while j < 16 (sh = 2j < 32)
+            constexpr int NSLOT = (16 + C::A - 1) / C::A;
+            uint32_t sh = 2 * (uint32_t)j0;
+            uint32_t okj = ok >> j0;
+#pragma unroll
+            for (int t = 0; t < NSLOT; t++) {
+                bool full = false;
+                uint32_t pid = 0;
+                const uint32_t okr = okj & C::AMASK;
+                if (sh < 32 && okr) {
+                    const uint32_t rec = __funnelshift_r(p0, p1, sh);
+                    if (okr == C::AMASK)
+                        full = emit(rec, pid);
+                    else
+                        part_fallback<C>(rec, okr, table);
+                }
+                uint32_t fm = __ballot_sync(0xffffffffu, full);
+                while (fm) {
+                    const int src = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    flush_bin(__shfl_sync(0xffffffffu, pid, src));
+                }
+                sh += 2 * C::A;
+                okj >>= C::A;
+            }
+            cur16 = nxt;
+            raw1 = raw2;
+            d += 512 % C::A;
+            if (d >= C::A) d -= C::A;
         }
-        if ((step % FLUSH_EVERY) == FLUSH_EVERY - 1) flush();
     }
-    flush();
+    // final flush of the partially filled bins, then publish the region lengths
+    __syncthreads();
+    for (int b = tid >> 5; b < C::P; b += 32) {
+        const uint32_t c = smem[b] & 0xFFFFu;  // < CAP: a full bin was flushed by its last writer
+        const uint32_t base = b * region_cap;
+        const uint32_t pos = smem[C::P + b] - base;
+        uint32_t stored = pos < region_cap ? pos : region_cap;  // chunks are a prefix
+        if ((uint32_t)lane < c) {
+            const uint32_t r = smem[2 * C::P + b * C::CAP + lane];
+            if (pos + C::CAP <= region_cap)
+                my_slabs[base + pos + lane] = r;
+            else
+                part_fallback<C>(r, C::AMASK, table);
+        }
+        if (pos + C::CAP <= region_cap) stored = pos + c;
+        if (lane == 0) counts[(uint64_t)b * gridDim.x + blockIdx.x] = stored;
+    }
 }
 
-// Pass 2.  One partition at a time per CTA (dynamic queue); NBINS uint32 bins
-// in shared memory.
+// Pass 2.  One partition at a time per CTA (dynamic queue); NBINS uint32 bins in
+// shared memory; the partition's records lie in `nregions` private regions (one
+// per pass-1 CTA) which the 32 warps take round-robin.
 template <typename C>
 __global__ void __launch_bounds__(1024, 1)
 part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slabs,
-                  const uint32_t* __restrict__ gcursor, uint32_t slab_cap,
+                  const uint32_t* __restrict__ counts, uint32_t region_cap, uint32_t nregions,
                   uint32_t* __restrict__ work_counter) {
     extern __shared__ uint32_t bins[];
     __shared__ uint32_t s_part;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t SUBMASK = C::SUB - 1;
     for (;;) {
         if (tid == 0) s_part = atomicAdd(work_counter, 1u);
@@ -230,24 +328,39 @@ part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sla
         __syncthreads();
         const uint32_t part = s_part;
         if (part >= (uint32_t)C::P) break;
-        const uint32_t n = min(gcursor[part], slab_cap);
-        const uint32_t* src = slabs + (uint64_t)part * slab_cap;  // slab_cap % 4 == 0 -> 16 B aligned
         auto count_rec = [&](uint32_t rec) {
             // Y = record with the key bits removed; window r's bin = Y bits [2r, 2r+KB0)
             const uint32_t Y = (rec & SUBMASK) | ((rec >> (2 * C::K)) << C::KB0);
 #pragma unroll
             for (int r = 0; r < C::A; r++) atomicAdd(&bins[r * C::SUB + ((Y >> (2 * r)) & SUBMASK)], 1u);
         };
-        const uint32_t n4 = n >> 2;
-        const uint4* src4 = reinterpret_cast<const uint4*>(src);
-        for (uint32_t i = tid; i < n4; i += 1024) {
-            const uint4 v = kc_ldg_stream(src4 + i);
-            count_rec(v.x);
-            count_rec(v.y);
-            count_rec(v.z);
-            count_rec(v.w);
+        for (uint32_t reg = warp; reg < nregions; reg += 32) {
+            const uint32_t n = counts[(uint64_t)part * nregions + reg];
+            const uint32_t* src = slabs + ((uint64_t)reg * C::P + part) * region_cap;  // chunk aligned
+            const uint4* src4 = reinterpret_cast<const uint4*>(src);
+            const uint32_t n4 = n >> 2;
+            uint32_t i = lane;
+            for (; i + 32 < n4; i += 64) {  // two loads in flight per lane
+                const uint4 v0 = kc_ldg_stream(src4 + i);
+                const uint4 v1 = kc_ldg_stream(src4 + i + 32);
+                count_rec(v0.x);
+                count_rec(v0.y);
+                count_rec(v0.z);
+                count_rec(v0.w);
+                count_rec(v1.x);
+                count_rec(v1.y);
+                count_rec(v1.z);
+                count_rec(v1.w);
+            }
+            for (; i < n4; i += 32) {
+                const uint4 v = kc_ldg_stream(src4 + i);
+                count_rec(v.x);
+                count_rec(v.y);
+                count_rec(v.z);
+                count_rec(v.w);
+            }
+            for (uint32_t t = (n4 << 2) + lane; t < n; t += 32) count_rec(src[t]);
         }
-        for (uint32_t i = (n4 << 2) + tid; i < n; i += 1024) count_rec(src[i]);
         __syncthreads();
         // add the sub-tables to the global table: for alignment r the bin is
         //   low (KB0-2r bits) | key << (KB0-2r) | high (2r bits) << (2K-2r)
@@ -268,7 +381,6 @@ part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sla
 }
 
 using Part12 = PartCfg<12, 5, 11, 24>;
-constexpr int kPart12Flush = 6;
 
 // ---------------------------------------------------------------------------
 // host side
@@ -300,40 +412,42 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
     return KC_OK;
 }
 
-template <typename C, int FLUSH>
+template <typename C>
 static int dense_partition(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaStream_t st) {
     const uint64_t ngroups = g.g_end - g.g_begin;
     if (ngroups == 0) return KC_OK;
     const uint64_t nwin = g.whi - g.wlo;
     const uint64_t nrec = (nwin + C::A - 1) / C::A;
-    // slab capacity: mean + 12.5 % + slack, multiple of 4 records (16 B)
-    uint64_t cap = nrec / C::P;
-    cap = cap + cap / 8 + 4096;
-    cap = (cap + 3) & ~3ull;
-    if (cap > 0xFFFFFFF0ull) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "partition slab too large");
-    const size_t slab_bytes = (size_t)cap * C::P * sizeof(uint32_t);
-    const size_t ctl_bytes = (C::P + 64) * sizeof(uint32_t);
-    int rc = kc_scratch_reserve(ctx, slab_bytes + ctl_bytes);
+    const uint64_t want = (ngroups + 31) / 32;
+    const int grid1 = (int)(want > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want);
+    // private region of every (partition, pass-1 CTA): mean + 12.5 % + 3 chunks, a
+    // whole number of chunks and of 128-byte lines.  Overflow falls back to global REDs.
+    uint64_t cap = nrec / ((uint64_t)C::P * grid1);
+    cap = cap + cap / 8 + 3 * C::CAP;
+    constexpr uint64_t kUnit = (C::CAP % 32 == 0) ? C::CAP : (C::CAP % 16 == 0 ? 2 * C::CAP : 4 * C::CAP);
+    cap = (cap + kUnit - 1) / kUnit * kUnit;
+    if ((uint64_t)C::P * cap >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "partition region too large");
+    const size_t nregions = (size_t)C::P * grid1;
+    const size_t ctl_bytes = (nregions + 64) * sizeof(uint32_t);  // counts[P][grid1] + work counter
+    const size_t ctl_pad = (ctl_bytes + 255) & ~(size_t)255;
+    const size_t slab_bytes = nregions * cap * sizeof(uint32_t);
+    int rc = kc_scratch_reserve(ctx, ctl_pad + slab_bytes);
     if (rc) return rc;
-    uint32_t* gcursor = (uint32_t*)ctx->scratch;
-    uint32_t* work = gcursor + C::P;
-    uint32_t* slabs = gcursor + C::P + 64;
-    KC_CUDA(ctx, cudaMemsetAsync(gcursor, 0, ctl_bytes, st));
+    uint32_t* counts = (uint32_t*)ctx->scratch;
+    uint32_t* work = counts + nregions;
+    uint32_t* slabs = (uint32_t*)((char*)ctx->scratch + ctl_pad);
+    KC_CUDA(ctx, cudaMemsetAsync(work, 0, 64 * sizeof(uint32_t), st));
 
     const size_t smem1 = (size_t)(2 * C::P + C::P * C::CAP) * sizeof(uint32_t);
     const size_t smem2 = (size_t)C::NBINS * sizeof(uint32_t);
-    KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter_kernel<C, FLUSH>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem2));
-    uint64_t want = (ngroups + 31) / 32;
-    int grid1 = (int)(want > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want);
+    KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
-    part_scatter_kernel<C, FLUSH><<<grid1, 1024, smem1, st>>>(g, d_table, slabs, gcursor, (uint32_t)cap);
+    part_scatter_kernel<C><<<grid1, 1024, smem1, st>>>(g, d_table, slabs, counts, (uint32_t)cap);
     KC_LAUNCH_CHECK(ctx, "part_scatter_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
     int grid2 = ctx->sm_count < C::P ? ctx->sm_count : C::P;
-    part_count_kernel<C><<<grid2, 1024, smem2, st>>>(d_table, slabs, gcursor, (uint32_t)cap, work);
+    part_count_kernel<C><<<grid2, 1024, smem2, st>>>(d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
     KC_LAUNCH_CHECK(ctx, "part_count_kernel");
     if (ctx->timing) {
         KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
@@ -342,7 +456,7 @@ static int dense_partition(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cu
     return KC_OK;
 }
 
-static uint64_t g_partition_min_windows = 1ull << 24;  // below this the direct path wins
+static uint64_t g_partition_min_windows = 1ull << 26;  // below this the direct path wins
 
 extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
                                           uint64_t win_begin, uint64_t win_end, int k,
@@ -365,7 +479,7 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     const bool use_part =
         can_part && (algo == KC_DENSE_PARTITION ||
                      (algo == KC_DENSE_AUTO && (win_end - win_begin) >= g_partition_min_windows));
-    if (use_part) return dense_partition<Part12, kPart12Flush>(ctx, g, d_table, st);
+    if (use_part) return dense_partition<Part12>(ctx, g, d_table, st);
     return dense_direct(ctx, g, d_table, st);
 }
 

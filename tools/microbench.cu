@@ -8,7 +8,8 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
-__device__ __forceinline__ uint32_t xs(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+// LCG: one IMAD per draw, high bits are the good ones
+__device__ __forceinline__ uint32_t xs(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 12; }
 
 __global__ void __launch_bounds__(1024, 1) k_stream(const uint4* __restrict__ p, uint64_t n16, uint32_t* out) {
     uint32_t acc = 0;
