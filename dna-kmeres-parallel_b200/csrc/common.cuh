@@ -144,6 +144,17 @@ __device__ __forceinline__ uint4 kc_ldg_stream(const uint4* p) {
     return r;
 }
 
+// Same load, but INTO the registers of `r` ("+r": the asm formally reads them, so the
+// register allocator must reuse them and cannot hoist the load above the last use of
+// the old value).  This is what makes a register prefetch ring rotate without MOVs:
+// with a plain "=r" load ptxas hoists the LDG, has to pick a spare destination and
+// copies it back at the loop edge — a copy that waits for the load.
+__device__ __forceinline__ void kc_ldg_stream_into(uint4& r, const uint4* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
+                 : "l"(p));
+}
+
 // bit j of result set <=> any of bad bits j .. j+k-1 set (k in 1..32)
 __device__ __forceinline__ uint64_t kc_window_bad(uint64_t B, int k) {
     uint64_t W = 0, span = B;  // span = OR of B>>0 .. B>>(2^bit - 1)

@@ -91,11 +91,25 @@ __device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Slow path, deliberately NOT inlined: it is taken by ~1 % of the records (bin full
+// while its flush is in flight, records next to an N run) and inlining its five
+// predicated REDs at every call site quadrupled the size of the scatter kernel.
 template <typename C>
-__device__ __forceinline__ void part_fallback(uint32_t rec, uint32_t okbits, uint32_t* table) {
+__device__ __noinline__ void part_fallback(uint32_t rec, uint32_t okbits, uint32_t* table) {
 #pragma unroll
     for (int r = 0; r < C::A; r++)
         if (okbits & (1u << r)) global_red_add(table + part_code<C>(rec, r), 1u);
+}
+
+// A bin whose chunk does not fit its global region any more (skewed input): count
+// its records directly.  Reads the staged records back from shared memory.
+template <typename C>
+__device__ __noinline__ void part_overflow_bin(uint32_t s_bin, uint32_t* table) {
+    for (int q = 0; q < C::CAP; q++) {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(s_bin + 4 * q) : "memory");
+        part_fallback<C>(r, C::AMASK, table);
+    }
 }
 
 // ---- shared-memory primitives as inline PTX (32-bit shared addresses): keeps
@@ -115,189 +129,197 @@ __device__ __forceinline__ uint32_t smem_ld(uint32_t saddr) {
     return r;
 }
 
-// Pass 1.  1024 threads, one CTA per SM, each warp owns a contiguous run of
-// 512-byte groups and never waits for another warp: there is no CTA barrier and
-// no global atomic in the main loop.
+__device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+
+// Pass 1.  Each warp owns a contiguous run of 512-byte groups and never waits for
+// another warp: no CTA barrier and no global atomic in the main loop.  The kernel
+// only sees INTERIOR groups: every block it touches (including DEPTH+1 groups of
+// prefetch past its last group) is readable and every window it can emit lies in
+// the requested range, so the hot loop has no bounds checks, no range masks and a
+// single code path; the host sends the few windows before/after the interior to
+// dense_direct_kernel.
+//
+// Loads: every iteration of the DEPTH-times unrolled loop first issues the DEPTH
+// 128-bit loads the NEXT iteration will decode and copies them into the ring at its
+// end, so DEPTH loads per lane are in flight for DEPTH steps — the bare scan runs
+// at the HBM peak this way (tools/microbench2.cu).  (ptxas turns any "load into the
+// ring slot in place" formulation into load-to-spare-register + MOV right behind
+// it, and the MOV waits for the load: measured 3x slower.)
 //
 // Shared memory per CTA: state[P] (low 16 bits = slots reserved, high 16 bits =
-// slots written), cur[P] (records already flushed to this CTA's private region of
-// partition p), buf[P][CAP] (staged records; CAP = 24 = one 96-byte chunk of
-// three full 32-byte sectors).
+// slots written), cur[P] (absolute word offset of the next chunk in this CTA's
+// private global region of partition p), buf[P][CAP] (staged records; CAP = 24 =
+// one 96-byte chunk of three full 32-byte sectors).
 //
 // Staging protocol (all shared-memory, CTA scope):
 //   writer : slot = atom.add(state[p], 1) & 0xFFFF;
 //            slot <  CAP : buf[p][slot] = rec; w = atom.add(state[p], 1<<16) >> 16;
 //                          the writer that makes w == CAP-1 has seen every slot
-//                          written and its warp flushes the bin;
+//                          written: that LANE flushes the bin by itself;
 //            slot >= CAP : the bin is full and its flush is in flight (a window of
 //                          a few dozen cycles) -> count the record's windows with
-//                          global REDs instead (~1 % of records).
-//   flusher: the whole warp reads buf[p][0..CAP) into registers, lane 0 resets
+//                          global REDs instead (well under 1 % of records).
+//   flusher: one lane reads buf[p][0..CAP) with 128-bit shared loads, resets
 //            state[p] = 0 (one store clears both halves, so a new generation can
-//            start immediately) and advances cur[p]; then CAP lanes write one
-//            aligned chunk to the CTA's private global region.
-// Shared-memory requests of a warp are performed in program order, so a writer's
+//            start immediately), advances cur[p] and writes the chunk with 128-bit
+//            global stores.  Several lanes of a warp flush different bins in the
+//            same divergent region, so the cost per step does not grow with their
+//            number (the warp-cooperative flush of an earlier version did).
+// Shared-memory requests of a thread are performed in program order, so a writer's
 // store precedes its "written" increment and the flusher's loads precede its
 // reset; any record a later generation stores therefore lands after the loads.
 // Every record is consumed exactly once: by a chunk, by the final flush, or by
 // the RED fallback.  Parity against the oracle at 3.1 G windows checks this.
 //
 // Global layout: slabs[cta][p][region_cap] — a CTA writes into one contiguous
-// area, the (cta, p) regions need no global cursor, counts[p][cta] is published
+// area, the (cta, p) regions need no global cursor; counts[p][cta] is published
 // at the end.
-template <typename C>
-__global__ void __launch_bounds__(1024, 1)
-part_scatter_kernel(ScanGeom g, uint32_t* __restrict__ table, uint32_t* __restrict__ slabs,
-                    uint32_t* __restrict__ counts, uint32_t region_cap) {
+template <typename C, int THREADS, int MINB, int DEPTH, int ABLATE = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
+part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* __restrict__ table,
+                    uint32_t* __restrict__ slabs, uint32_t* __restrict__ counts, uint32_t region_cap) {
+    static_assert(C::CAP % 8 == 0, "chunks are moved 128 bits at a time, in two halves");
+    constexpr int NW = THREADS / 32;
     extern __shared__ uint32_t smem[];
     const uint32_t s_state = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t s_cur = s_state + C::P * 4;
     const uint32_t s_buf = s_state + 2 * C::P * 4;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    // cur[p] holds the absolute word offset (inside this CTA's slab area) of the next chunk
-    for (int b = tid; b < C::P; b += 1024) {
+    for (int b = tid; b < C::P; b += THREADS) {
         smem[b] = 0;
         smem[C::P + b] = b * region_cap;
     }
     __syncthreads();
 
-    const uint64_t ngroups = g.g_end - g.g_begin;
-    const uint64_t nwarps = (uint64_t)gridDim.x * 32;
-    const uint64_t gpw = (ngroups + nwarps - 1) / nwarps;
-    const uint64_t w = (uint64_t)blockIdx.x * 32 + (tid >> 5);
-    const uint64_t gb = g.g_begin + min(w * gpw, ngroups);
-    const uint64_t ge = g.g_begin + min((w + 1) * gpw, ngroups);
+    // ngroups is a multiple of DEPTH (host) and so is every warp's share: the
+    // unrolled loop below then needs no per-step guard.  (A guard makes the ring
+    // registers conditionally assigned; ptxas then loads into a spare register and
+    // inserts a MOV at the join that waits for the load — no overlap at all.)
+    const uint64_t nwarps = (uint64_t)gridDim.x * NW;
+    const uint64_t units = ngroups / DEPTH;
+    const uint64_t upw = (units + nwarps - 1) / nwarps;
+    const uint64_t w = (uint64_t)blockIdx.x * NW + (tid >> 5);
+    const uint64_t gb = min(w * upw, units) * DEPTH;
+    const uint32_t nsteps = (uint32_t)(min((w + 1) * upw, units) * DEPTH - gb);
     uint32_t* const my_slabs = slabs + (uint64_t)blockIdx.x * C::P * region_cap;  // < 2^32 words per CTA
-    const uint32_t lane_slot = (uint32_t)min(lane, C::CAP - 1) * 4;
 
-    auto flush_bin = [&](uint32_t b) {  // whole warp, converged
-        const uint32_t r = smem_ld(s_buf + b * (C::CAP * 4) + lane_slot);
-        __syncwarp();
-        uint32_t pos = 0;
-        if (lane == 0) {
+    // flush bin b (this lane completed it): two halves to keep registers low
+    auto flush_bin = [&](uint32_t b) {
+        constexpr int H = C::CAP / 8;  // 128-bit pieces per half
+        const uint32_t src = s_buf + b * (C::CAP * 4);
+        const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
+        if (pos + C::CAP > (b + 1) * region_cap) {  // region full (skewed input): rare, slow, exact
+            part_overflow_bin<C>(src, table);
             smem_st(s_state + b * 4, 0u);
-            pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
+            return;
         }
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (lane < C::CAP) {
-            if (pos + C::CAP <= (b + 1) * region_cap)
-                my_slabs[pos + lane] = r;
-            else
-                part_fallback<C>(r, C::AMASK, table);
-        }
-    };
-
-    // one record: reserve, store, publish; returns true when this lane completed the bin
-    auto emit = [&](uint32_t rec, uint32_t& pid) -> bool {
-        pid = (rec >> C::KB0) & (C::P - 1);
-        const uint32_t slot = smem_atom_add(s_state + pid * 4, 1u) & 0xFFFFu;
-        if (slot < (uint32_t)C::CAP) {
-            smem_st(s_buf + pid * (C::CAP * 4) + slot * 4, rec);
-            return (smem_atom_add(s_state + pid * 4, 0x10000u) >> 16) == (uint32_t)C::CAP - 1;
-        }
-        part_fallback<C>(rec, C::AMASK, table);
-        return false;
-    };
-
-    if (gb < ge) {
-        const uint32_t nsteps = (uint32_t)(ge - gb);
-        // steps [i_lo, i_hi) lie fully inside the buffer and the window range, together
-        // with the 2 groups of look-ahead the loads need and the 20 positions a record needs
-        const uint64_t safe_lo = (max(g.lo, g.wlo) + 511) >> 9;
-        const uint64_t lim = min(g.hi, g.whi);
-        const uint64_t safe_hi = lim >= 2048 ? ((lim - 32) >> 9) - 3 : 0;  // last interior group + 1
-        const uint32_t i_lo = safe_lo > gb ? (uint32_t)min((uint64_t)nsteps, safe_lo - gb) : 0u;
-        const uint32_t i_hi = safe_hi > gb ? (uint32_t)min((uint64_t)nsteps, safe_hi - gb) : 0u;
-        // (a0 - wlo) mod A for this lane, advanced by 512 mod A per group
-        const int64_t delta0 = (int64_t)(((gb * 32 + lane) << 4)) - (int64_t)g.wlo;
-        int d = (int)(((delta0 % C::A) + C::A) % C::A);
-        const uint4* ptr = g.abase + gb * 32 + lane;  // block of this lane in the current group
-        uint4 raw1 = kc_issue_block(g, (gb + 1) * 32 + lane);
-        Decoded16 cur16 = kc_finish_block(g, gb * 32 + lane, kc_issue_block(g, gb * 32 + lane));
-        for (uint32_t i = 0; i < nsteps; i++, ptr += 32) {
-            const bool interior = i >= i_lo && i < i_hi;  // warp-uniform
-            uint4 raw2;
-            Decoded16 nxt;
-            if (interior) {
-                raw2 = kc_ldg_stream(ptr + 64);
-                nxt = kc_decode16(raw1);
-            } else {
-                const uint64_t grp = gb + i;
-                raw2 = kc_issue_block(g, (grp + 2) * 32 + lane);
-                nxt = kc_finish_block(g, (grp + 1) * 32 + lane, raw1);
-            }
-            uint32_t p1 = __shfl_down_sync(0xffffffffu, cur16.packed, 1);
-            uint32_t b1 = __shfl_down_sync(0xffffffffu, cur16.bad, 1);
-            const uint32_t n0p = __shfl_sync(0xffffffffu, nxt.packed, 0);
-            const uint32_t n0b = __shfl_sync(0xffffffffu, nxt.bad, 0);
-            if (lane == 31) {
-                p1 = n0p;
-                b1 = n0b;
-            }
-            const uint32_t p0 = cur16.packed;
-            const uint32_t B32 = cur16.bad | (b1 << 16);
-            uint32_t ok = (1u << (33 - C::K)) - 1u;  // the windows that fit the 32 known bases
-            if (B32) ok = ~(uint32_t)kc_window_bad((uint64_t)B32 | (0xFFFFull << 32), C::K);
-            int j0 = d ? C::A - d : 0;  // first record start among this lane's 16 positions, 0..A-1
-            if (!interior) {
-                const uint64_t a0 = (gb + i) * 512 + (uint64_t)lane * 16;
-                const int l = a0 < g.wlo ? (int)min((uint64_t)32, g.wlo - a0) : 0;
-                const int h = a0 + 32 > g.whi ? (int)(g.whi > a0 ? g.whi - a0 : 0) : 32;
-                const uint32_t hm = h >= 32 ? 0xFFFFFFFFu : ((1u << h) - 1u);
-                const uint32_t lm = l >= 32 ? 0xFFFFFFFFu : ((1u << l) - 1u);
-                ok &= hm & ~lm;
-                if (a0 < g.wlo) {  // the first record starts at wlo itself
-                    if (g.wlo - a0 < 16) {
-                        j0 = (int)(g.wlo - a0);
-                    } else {
-                        j0 = 0;
-                        ok = 0;
-                    }
-                }
-            }
-            // records at j = j0, j0+A, ... while j < 16 (sh = 2j < 32)
-            constexpr int NSLOT = (16 + C::A - 1) / C::A;
-            uint32_t sh = 2 * (uint32_t)j0;
-            uint32_t okj = ok >> j0;
+        uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
+        uint4 v[H];
 #pragma unroll
-            for (int t = 0; t < NSLOT; t++) {
-                bool full = false;
-                uint32_t pid = 0;
-                const uint32_t okr = okj & C::AMASK;
-                if (sh < 32 && okr) {
-                    const uint32_t rec = __funnelshift_r(p0, p1, sh);
-                    if (okr == C::AMASK)
-                        full = emit(rec, pid);
-                    else
-                        part_fallback<C>(rec, okr, table);
+        for (int q = 0; q < H; q++) v[q] = smem_ld128(src + 16 * q);
+#pragma unroll
+        for (int q = 0; q < H; q++) dst[q] = v[q];
+#pragma unroll
+        for (int q = 0; q < H; q++) v[q] = smem_ld128(src + 16 * (H + q));
+        smem_st(s_state + b * 4, 0u);  // every slot has been read: the bin is free again
+#pragma unroll
+        for (int q = 0; q < H; q++) dst[H + q] = v[q];
+    };
+
+    if (nsteps) {
+        // record starts are the positions = 0 mod A counted from the first interior byte
+        int d = (int)(((gb % C::A) * (512 % C::A) + (uint32_t)lane * (16 % C::A)) % C::A);
+        const uint4* ptr = base + gb * 32 + lane;
+        uint4 raw[DEPTH];
+        Decoded16 cur16 = kc_decode16(kc_ldg_stream(ptr));
+#pragma unroll
+        for (int q = 0; q < DEPTH; q++) raw[q] = kc_ldg_stream(ptr + 32 * (q + 1));
+
+        for (uint32_t i = 0; i < nsteps; i += DEPTH) {
+            // issue the loads of the NEXT iteration's groups first (i+DEPTH+1 ...): they
+            // have this whole iteration (DEPTH steps) to land before the copy at its end
+            uint4 fresh[DEPTH];
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) fresh[q] = kc_ldg_stream(ptr + 32 * (DEPTH + 1 + q));
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) {
+                {
+                    const Decoded16 nxt = kc_decode16(raw[q]);  // group i+q+1, loaded one iteration ago
+                    uint32_t p1 = __shfl_down_sync(0xffffffffu, cur16.packed, 1);
+                    uint32_t b1 = __shfl_down_sync(0xffffffffu, cur16.bad, 1);
+                    const uint32_t n0p = __shfl_sync(0xffffffffu, nxt.packed, 0);
+                    const uint32_t n0b = __shfl_sync(0xffffffffu, nxt.bad, 0);
+                    if (lane == 31) {
+                        p1 = n0p;
+                        b1 = n0b;
+                    }
+                    const uint32_t p0 = cur16.packed;
+                    const uint32_t B32 = cur16.bad | (b1 << 16);
+                    uint32_t ok = (1u << (33 - C::K)) - 1u;  // the windows that fit the 32 known bases
+                    if (B32) ok = ~(uint32_t)kc_window_bad((uint64_t)B32 | (0xFFFFull << 32), C::K);
+                    const int j0 = d ? C::A - d : 0;  // first record start among this lane's 16 positions
+                    // records at j = j0, j0+A, ... while j < 16 (sh = 2j < 32)
+                    constexpr int NSLOT = (16 + C::A - 1) / C::A;
+#pragma unroll
+                    for (int t = 0; t < NSLOT; t++) {
+                        const uint32_t sh = 2 * (uint32_t)j0 + 2 * C::A * t;
+                        const uint32_t okr = (ok >> (j0 + C::A * t)) & C::AMASK;
+                        if (sh < 32 && okr) {
+                            const uint32_t rec = __funnelshift_r(p0, p1, sh);
+                            if (okr != C::AMASK) {
+                                part_fallback<C>(rec, okr, table);  // rare: next to an N run
+                            } else if (ABLATE == 2) {
+                                if (rec == 0x12345678u && j0 == 77) table[rec] = okr;  // measurement only
+                            } else {
+                                const uint32_t pid = (rec >> C::KB0) & (C::P - 1);
+                                const uint32_t slot = smem_atom_add(s_state + pid * 4, 1u) & 0xFFFFu;
+                                if (slot < (uint32_t)C::CAP) {
+                                    smem_st(s_buf + (pid * C::CAP + slot) * 4, rec);
+                                    const uint32_t wr = smem_atom_add(s_state + pid * 4, 0x10000u) >> 16;
+                                    if (wr == (uint32_t)C::CAP - 1) flush_bin(pid);
+                                } else {
+                                    part_fallback<C>(rec, C::AMASK, table);
+                                }
+                            }
+                        }
+                    }
+                    cur16 = nxt;
+                    d += 512 % C::A;
+                    if (d >= C::A) d -= C::A;
                 }
-                uint32_t fm = __ballot_sync(0xffffffffu, full);
-                while (fm) {
-                    const int src = __ffs(fm) - 1;
-                    fm &= fm - 1;
-                    flush_bin(__shfl_sync(0xffffffffu, pid, src));
-                }
-                sh += 2 * C::A;
-                okj >>= C::A;
             }
-            cur16 = nxt;
-            raw1 = raw2;
-            d += 512 % C::A;
-            if (d >= C::A) d -= C::A;
+            // Copy into the ring at the END of the iteration.  ptxas would hoist plain
+            // copies to just behind the last read of raw[q] (and stall there on the
+            // load); OR-ing in a zero it cannot see through, produced after the last
+            // shared-memory operation of the iteration, pins them here.
+            uint32_t zero;
+            asm volatile("shr.u32 %0, %1, 31;" : "=r"(zero) : "r"(d) : "memory");  // d in [0, A)
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) {
+                raw[q].x = fresh[q].x | zero;
+                raw[q].y = fresh[q].y | zero;
+                raw[q].z = fresh[q].z | zero;
+                raw[q].w = fresh[q].w | zero;
+            }
+            ptr += 32 * DEPTH;
         }
     }
     // final flush of the partially filled bins, then publish the region lengths
     __syncthreads();
-    for (int b = tid >> 5; b < C::P; b += 32) {
+    for (int b = tid >> 5; b < C::P; b += NW) {
         const uint32_t c = smem[b] & 0xFFFFu;  // < CAP: a full bin was flushed by its last writer
-        const uint32_t base = b * region_cap;
-        const uint32_t pos = smem[C::P + b] - base;
+        const uint32_t base_off = b * region_cap;
+        const uint32_t pos = smem[C::P + b] - base_off;
         uint32_t stored = pos < region_cap ? pos : region_cap;  // chunks are a prefix
         if ((uint32_t)lane < c) {
             const uint32_t r = smem[2 * C::P + b * C::CAP + lane];
             if (pos + C::CAP <= region_cap)
-                my_slabs[base + pos + lane] = r;
+                my_slabs[base_off + pos + lane] = r;
             else
                 part_fallback<C>(r, C::AMASK, table);
         }
@@ -310,7 +332,7 @@ part_scatter_kernel(ScanGeom g, uint32_t* __restrict__ table, uint32_t* __restri
 // shared memory; the partition's records lie in `nregions` private regions (one
 // per pass-1 CTA) which the 32 warps take round-robin.
 template <typename C>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(1024, (C::NBINS * 4 <= 100 * 1024) ? 2 : 1)
 part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slabs,
                   const uint32_t* __restrict__ counts, uint32_t region_cap, uint32_t nregions,
                   uint32_t* __restrict__ work_counter) {
@@ -380,7 +402,7 @@ part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sla
     }
 }
 
-using Part12 = PartCfg<12, 5, 11, 24>;
+using Part12 = PartCfg<12, 5, 11, 16>;
 
 // ---------------------------------------------------------------------------
 // host side
@@ -412,20 +434,43 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
     return KC_OK;
 }
 
-template <typename C>
-static int dense_partition(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaStream_t st) {
-    const uint64_t ngroups = g.g_end - g.g_begin;
-    if (ngroups == 0) return KC_OK;
-    const uint64_t nwin = g.whi - g.wlo;
-    const uint64_t nrec = (nwin + C::A - 1) / C::A;
-    const uint64_t want = (ngroups + 31) / 32;
-    const int grid1 = (int)(want > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want);
-    // private region of every (partition, pass-1 CTA): mean + 12.5 % + 3 chunks, a
-    // whole number of chunks and of 128-byte lines.  Overflow falls back to global REDs.
+// launch shape of pass 1
+template <typename C, int THREADS_, int MINB_, int DEPTH_>
+struct ScatterShape {
+    using Cfg = C;
+    static constexpr int THREADS = THREADS_, MINB = MINB_, DEPTH = DEPTH_;
+};
+
+static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaStream_t st);
+
+template <typename S>
+static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
+                           uint32_t* d_table, cudaStream_t st) {
+    using C = typename S::Cfg;
+    const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, C::K);
+    // interior groups [G0, G1): fully readable, all their windows requested, and
+    // DEPTH+1 groups of prefetch past G1 still readable
+    const uint64_t G0 = (max(g.lo, g.wlo) + 511) >> 9;
+    const uint64_t lim = min(g.hi, g.whi);
+    const uint64_t Gl = lim >> 9;
+    const uint64_t G1 = Gl > (uint64_t)(2 * S::DEPTH + 2) ? Gl - (2 * S::DEPTH + 2) : 0;
+    if (G1 <= G0 + 64) return dense_direct(ctx, g, d_table, st);
+    const uint64_t ngroups = (G1 - G0) / S::DEPTH * S::DEPTH;  // every warp runs whole unrolled iterations
+    const uint64_t nrec = (ngroups * 512 + C::A - 1) / C::A;  // records start at (G0<<9) + A*m
+    const uint64_t shift = g.lo;                              // aligned coordinate of byte 0
+    const uint64_t head_end = (G0 << 9) - shift;              // first window the interior kernel owns
+    const uint64_t tail_begin = (G0 << 9) + nrec * C::A - shift;
+
+    constexpr int NW = S::THREADS / 32;
+    const uint64_t want = (ngroups + NW - 1) / NW;
+    const uint64_t maxg = (uint64_t)ctx->sm_count * S::MINB;
+    const int grid1 = (int)(want > maxg ? maxg : want);
+    // private region of every (partition, pass-1 CTA): mean + 12.5 % + slack, a whole
+    // number of 128-byte lines.  Overflow falls back to global REDs.
     uint64_t cap = nrec / ((uint64_t)C::P * grid1);
-    cap = cap + cap / 8 + 3 * C::CAP;
+    cap = cap + cap / 8 + 4 * C::CAP;
     constexpr uint64_t kUnit = (C::CAP % 32 == 0) ? C::CAP : (C::CAP % 16 == 0 ? 2 * C::CAP : 4 * C::CAP);
-    cap = (cap + kUnit - 1) / kUnit * kUnit;
+    cap = (cap + kUnit - 1) / kUnit * kUnit;  // whole chunks and whole 128-byte lines
     if ((uint64_t)C::P * cap >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "partition region too large");
     const size_t nregions = (size_t)C::P * grid1;
     const size_t ctl_bytes = (nregions + 64) * sizeof(uint32_t);  // counts[P][grid1] + work counter
@@ -440,20 +485,39 @@ static int dense_partition(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cu
 
     const size_t smem1 = (size_t)(2 * C::P + C::P * C::CAP) * sizeof(uint32_t);
     const size_t smem2 = (size_t)C::NBINS * sizeof(uint32_t);
-    KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const uint4* base = g.abase + (G0 << 5);
+    static const int ablate = getenv("KC_PART_ABLATE") ? atoi(getenv("KC_PART_ABLATE")) : 0;  // measurement aid
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
-    part_scatter_kernel<C><<<grid1, 1024, smem1, st>>>(g, d_table, slabs, counts, (uint32_t)cap);
+#define KC_LAUNCH_SCATTER(ABL)                                                                              \
+    do {                                                                                                    \
+        auto kern = part_scatter_kernel<C, S::THREADS, S::MINB, S::DEPTH, ABL>;                   \
+        KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));  \
+        kern<<<grid1, S::THREADS, smem1, st>>>(base, ngroups, d_table, slabs, counts, (uint32_t)cap);       \
+    } while (0)
+    if (ablate == 1)
+        KC_LAUNCH_SCATTER(1);
+    else if (ablate == 2)
+        KC_LAUNCH_SCATTER(2);
+    else
+        KC_LAUNCH_SCATTER(0);
+#undef KC_LAUNCH_SCATTER
     KC_LAUNCH_CHECK(ctx, "part_scatter_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
-    int grid2 = ctx->sm_count < C::P ? ctx->sm_count : C::P;
+    KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const int ctas2 = (smem2 + 1024) * 2 <= ctx->smem_optin + 1024 && smem2 <= 100 * 1024 ? 2 : 1;
+    int grid2 = ctx->sm_count * ctas2 < C::P ? ctx->sm_count * ctas2 : C::P;
     part_count_kernel<C><<<grid2, 1024, smem2, st>>>(d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
     KC_LAUNCH_CHECK(ctx, "part_count_kernel");
-    if (ctx->timing) {
-        KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
-        ctx->timed_kernels = 2;
-    }
-    return KC_OK;
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
+    // the windows before and after the interior
+    const bool timing = ctx->timing;
+    ctx->timing = false;
+    rc = KC_OK;
+    if (head_end > win_begin) rc = dense_direct(ctx, kc_make_geom(d_data, nbytes, win_begin, head_end, C::K), d_table, st);
+    if (!rc && tail_begin < win_end) rc = dense_direct(ctx, kc_make_geom(d_data, nbytes, tail_begin, win_end, C::K), d_table, st);
+    ctx->timing = timing;
+    if (timing) ctx->timed_kernels = 2;
+    return rc;
 }
 
 static uint64_t g_partition_min_windows = 1ull << 26;  // below this the direct path wins
@@ -479,7 +543,12 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     const bool use_part =
         can_part && (algo == KC_DENSE_PARTITION ||
                      (algo == KC_DENSE_AUTO && (win_end - win_begin) >= g_partition_min_windows));
-    if (use_part) return dense_partition<Part12>(ctx, g, d_table, st);
+    if (use_part) {
+        // measured on B200 (profiles/r01_scatter_shapes.txt): CAP 16 / depth 3 is the fastest shape
+        static const int shape = getenv("KC_PART_SHAPE") ? atoi(getenv("KC_PART_SHAPE")) : 0;  // tuning aid
+        if (shape == 1) return dense_partition<ScatterShape<PartCfg<12, 5, 11, 24>, 1024, 1, 2>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+        return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+    }
     return dense_direct(ctx, g, d_table, st);
 }
 
