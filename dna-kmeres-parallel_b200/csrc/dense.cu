@@ -101,17 +101,6 @@ __device__ __noinline__ void part_fallback(uint32_t rec, uint32_t okbits, uint32
         if (okbits & (1u << r)) global_red_add(table + part_code<C>(rec, r), 1u);
 }
 
-// A bin whose chunk does not fit its global region any more (skewed input): count
-// its records directly.  Reads the staged records back from shared memory.
-template <typename C>
-__device__ __noinline__ void part_overflow_bin(uint32_t s_bin, uint32_t* table) {
-    for (int q = 0; q < C::CAP; q++) {
-        uint32_t r;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(s_bin + 4 * q) : "memory");
-        part_fallback<C>(r, C::AMASK, table);
-    }
-}
-
 // ---- shared-memory primitives as inline PTX (32-bit shared addresses): keeps
 // ptxas from wrapping atomicAdd in its warp-aggregation sequence and pins the
 // program order the staging protocol below relies on.
@@ -123,12 +112,6 @@ __device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
 __device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t smem_ld(uint32_t saddr) {
-    uint32_t r;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
-    return r;
-}
-
 __device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
@@ -208,27 +191,31 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
     const uint32_t nsteps = (uint32_t)(min((w + 1) * upw, units) * DEPTH - gb);
     uint32_t* const my_slabs = slabs + (uint64_t)blockIdx.x * C::P * region_cap;  // < 2^32 words per CTA
 
-    // flush bin b (this lane completed it): two halves to keep registers low
+    // flush bin b (this lane completed it).  All shared loads are issued first and the
+    // bin is reopened right behind them, before the global side starts: the window in
+    // which other warps find the bin full (and fall back to REDs) is a handful of issue
+    // slots instead of an atomic round trip plus a store burst.
     auto flush_bin = [&](uint32_t b) {
-        constexpr int H = C::CAP / 8;  // 128-bit pieces per half
+        constexpr int Q = C::CAP / 4;  // 128-bit pieces
         const uint32_t src = s_buf + b * (C::CAP * 4);
-        const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
-        if (pos + C::CAP > (b + 1) * region_cap) {  // region full (skewed input): rare, slow, exact
-            part_overflow_bin<C>(src, table);
-            smem_st(s_state + b * 4, 0u);
-            return;
-        }
-        uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
-        uint4 v[H];
+        uint4 v[Q];
 #pragma unroll
-        for (int q = 0; q < H; q++) v[q] = smem_ld128(src + 16 * q);
-#pragma unroll
-        for (int q = 0; q < H; q++) dst[q] = v[q];
-#pragma unroll
-        for (int q = 0; q < H; q++) v[q] = smem_ld128(src + 16 * (H + q));
+        for (int q = 0; q < Q; q++) v[q] = smem_ld128(src + 16 * q);
         smem_st(s_state + b * 4, 0u);  // every slot has been read: the bin is free again
+        const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
+        if (pos + C::CAP <= (b + 1) * region_cap) {
+            uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
 #pragma unroll
-        for (int q = 0; q < H; q++) dst[H + q] = v[q];
+            for (int q = 0; q < Q; q++) dst[q] = v[q];
+        } else {  // region full (skewed input): rare, slow, exact (static indices: v stays in registers)
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                part_fallback<C>(v[q].x, C::AMASK, table);
+                part_fallback<C>(v[q].y, C::AMASK, table);
+                part_fallback<C>(v[q].z, C::AMASK, table);
+                part_fallback<C>(v[q].w, C::AMASK, table);
+            }
+        }
     };
 
     if (nsteps) {
