@@ -38,6 +38,13 @@ WORKLOADS = {
     "config1": dict(L=1_000_000, k=3, long_runs=0, short_runs=0, seed=0xB2000001,
                     desc="1 Mbp synthetic ACGT, k=3 (BASELINE configs[0])"),
 }
+SPARSE_WORKLOADS = {
+    # name: (reads at full scale, read length, genome length, k, seed) — SURVEY §8d configs 4 and 5
+    "config4": dict(reads=100_000_000, read_len=150, genome=500_000_000, k=21, err_den=200, seed=0xB2000004,
+                    desc="150 bp reads with 0.5 % substitutions from a 500 Mbp genome, k=21 sparse (BASELINE configs[3])"),
+    "config5": dict(reads=200_000_000, read_len=150, genome=1_000_000_000, k=31, err_den=200, seed=0xB2000005,
+                    desc="150 bp reads with 0.5 % substitutions from a 1 Gbp genome, k=31 sparse (BASELINE configs[4])"),
+}
 METRIC = "bases/sec"
 FALLBACK_HBM_GBS = 6650.0
 
@@ -144,13 +151,96 @@ def run_reference(args):
     return 0
 
 
+def run_sparse(args):
+    """configs 4/5 (not the default bench line): sparse counting of reads, hash or sort,
+    hash-sharded all-to-all when world > 1.  --reads scales the number of reads."""
+    import torch
+    import torch.distributed as dist
+    import kmerb200
+    from kmerb200 import distributed as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = SPARSE_WORKLOADS[args.workload]
+    nreads = args.reads or w["reads"]
+    k, rl = w["k"], w["read_len"]
+    ctx = kmerb200.Context(local)
+    r0, r1 = kmerb200.shard_reads(nreads, rank, world)
+    data = ctx.gen_reads(w["seed"], w["genome"], rl, w["err_den"], r0, r1 - r0)
+    nb = (r1 - r0) * (rl + 1)
+    torch.cuda.synchronize()
+    algo = {"hash": kmerb200.SPARSE_HASH, "sort": kmerb200.SPARSE_SORT}[args.sparse_algo]
+    hint = args.capacity_hint
+
+    def step():
+        if world == 1:
+            sp = ctx.count_sparse(data, nb, k, algo, hint)
+        else:
+            sp = D.count_sparse_sharded_gpu(ctx, data, nb, k, algo)
+        return len(sp), sp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        n, sp = step()
+        sp.close()
+    barrier()
+    launches0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n, sp = step()
+        if _ + 1 < args.steps:
+            sp.close()
+    barrier()
+    dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    nd = torch.tensor([n], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nd, op=dist.ReduceOp.SUM)
+    sec = float(dt.item())
+    bases = nreads * rl
+    peak, peak_src = hbm_peak()
+    alg_bytes = nreads * (rl + 1) + 12 * int(nd.item())
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": bases / sec, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": w["desc"], "k": k, "reads": nreads, "bases": bases, "algo": args.sparse_algo,
+                       "distinct_kmers": int(nd.item()), "kmers_per_sec": nreads * (rl - k + 1) / sec,
+                       "timing": "wall clock around the synchronous C-ABI call (sorted result included)",
+                       "sharding": "reads by index, owner = mix64(code) % G, all-to-all" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "kernel": "whole call", "achieved": alg_bytes / sec / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(ctx.launch_count - launches0),
+        }
+        print(json.dumps(line))
+    sp.close()
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(SPARSE_WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="sparse workloads: number of reads (0 = full scale)")
+    ap.add_argument("--sparse-algo", default="hash", choices=["hash", "sort"])
+    ap.add_argument("--capacity-hint", type=int, default=0, help="sparse hash: expected distinct k-mers")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition")
     ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="bases of the CPU-baseline sample")
@@ -160,6 +250,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.workload in SPARSE_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "sparse workloads are measured on the GPU arm only"}))
+            return 0
+        return run_sparse(args)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -264,20 +264,18 @@ struct LaneWindow {
 
 // Drives a warp over groups [gb, ge) of the geometry; calls body(lw, a0) once
 // per group per lane, a0 = aligned coordinate of the lane's first base.
+// Pipeline: the block of group g+2 is requested at the top of the step for group
+// g and decoded at its end, so one 128-bit load per lane is in flight during the
+// whole body; groups g and g+1 are held decoded (g+1 feeds the halo of the last
+// lanes).
 template <int HALO, typename Body>
 __device__ __forceinline__ void kc_warp_scan(const ScanGeom& g, uint64_t gb, uint64_t ge, Body body) {
     const int lane = threadIdx.x & 31;
     if (gb >= ge) return;
     Decoded16 cur = kc_load_block(g, gb * 32 + lane);
+    Decoded16 nxt = kc_load_block(g, (gb + 1) * 32 + lane);
     for (uint64_t grp = gb; grp < ge; grp++) {
-        // next group: fully needed if it will be processed, else only lanes < HALO
-        Decoded16 nxt;
-        if (grp + 1 < ge || lane < HALO) {
-            nxt = kc_load_block(g, (grp + 1) * 32 + lane);
-        } else {
-            nxt.packed = 0;
-            nxt.bad = 0xFFFFu;
-        }
+        const uint4 raw = kc_issue_block(g, (grp + 2) * 32 + lane);
         LaneWindow<HALO> lw;
         lw.p0 = cur.packed;
         uint32_t p1 = __shfl_down_sync(0xffffffffu, cur.packed, 1);
@@ -319,6 +317,7 @@ __device__ __forceinline__ void kc_warp_scan(const ScanGeom& g, uint64_t gb, uin
         lw.ok = ok;
         body(lw, a0);
         cur = nxt;
+        nxt = kc_finish_block(g, (grp + 2) * 32 + lane, raw);
     }
 }
 #endif  // __CUDACC__

@@ -367,3 +367,20 @@ def test_config3_full_size(ctx, kmerlib, oracle):
     want, inv = oracle.count_dense(host, k, threads=threads)
     assert total + inv == L - k + 1
     assert (t_part.cpu().numpy().view(np.uint32) == want).all()
+
+
+def test_all_256_byte_values(ctx, kmerlib, oracle):
+    """Only the four upper-case letters may pass the SIMD validity test of the decoder."""
+    rng = np.random.default_rng(256)
+    every = np.arange(256, dtype=np.uint8)
+    s = np.concatenate([every, rng.permutation(every), np.repeat(every, 3), rng.integers(0, 256, 100000).astype(np.uint8)])
+    for k in (1, 2, 3):
+        want, _ = oracle.count_dense(s, k)
+        assert (dense_gpu(ctx, kmerlib, to_dev(s), s.size, k) == want).all()
+    want1, _ = oracle.count_dense(every, 1)
+    assert want1.tolist() == [1, 1, 1, 1]
+    # the same bytes through the k=12 partition path, embedded in valid sequence
+    base = oracle.gen_bases(3, 0, 1 << 22)
+    base[1000:1000 + s.size:97] = s[: len(base[1000:1000 + s.size:97])]
+    want, _ = oracle.count_dense(base, 12)
+    assert (dense_gpu(ctx, kmerlib, to_dev(base), base.size, 12, algo=kmerlib.DENSE_PARTITION) == want).all()
