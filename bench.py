@@ -147,7 +147,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -223,12 +223,31 @@ def run_sparse(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(ctx.launch_count - launches0),
         }
-        print(json.dumps(line))
+        emit(line)
     sp.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) must not share stdout with the ONE
+    JSON line: route fd 1 to stderr for the run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -250,9 +269,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    _quiet_stdout()
     if args.workload in SPARSE_WORKLOADS:
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "sparse workloads are measured on the GPU arm only"}))
+            emit({"impl": "reference", "unavailable": "sparse workloads are measured on the GPU arm only"})
             return 0
         return run_sparse(args)
     if args.impl == "reference":
@@ -416,7 +436,7 @@ def main():
                        "table_checksum": checksum},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

@@ -4,8 +4,8 @@
 // constant memory; the kernel hard-codes 3, kernels.h:133-138).  These kernels
 // extend the same window semantics (main.cu:636-646) to 64-bit codes:
 //
-//   KC_SPARSE_HASH  open-addressing table in HBM: uint64 keys (CAS on the key,
-//                   linear probing from mix64(code)), uint32 counts (RED.ADD),
+//   KC_SPARSE_HASH  open-addressing table in HBM: 16-byte slots {uint64 key, uint32 count}
+//                   (CAS on the key, linear probing from mix64(code), RED.ADD on the count),
 //                   filled straight from the WarpScanner — codes never touch
 //                   memory; then non-empty slots are compacted and sorted.
 //   KC_SPARSE_SORT  codes written per window chunk, radix-sorted (CUB, a
@@ -29,9 +29,17 @@ static constexpr uint64_t KEY_EMPTY = ~0ull;
 // ---------------------------------------------------------------------------
 // hash table
 // ---------------------------------------------------------------------------
+// One slot = 16 bytes {key, count, pad}: the key probe and the count update touch
+// the same 32-byte sector, i.e. one random DRAM access (and one TLB miss) per insert
+// instead of two with split key/count arrays.
+struct __align__(16) HashSlot {
+    unsigned long long key;
+    uint32_t count;
+    uint32_t pad;
+};
+
 struct HashTable {
-    unsigned long long* keys;
-    uint32_t* counts;
+    HashSlot* slots;
     uint64_t mask;          // capacity - 1 (capacity is a power of two)
     unsigned long long* distinct;  // number of occupied slots
     uint32_t* full;         // set when a probe sequence wrapped the whole table / load limit
@@ -41,9 +49,9 @@ struct HashTable {
 __device__ __forceinline__ void hash_add(const HashTable& t, uint64_t code, uint32_t add) {
     uint64_t h = kc_mix64_hd(code) & t.mask;
     for (uint64_t probes = 0; probes <= t.mask; probes++) {
-        unsigned long long cur = *((volatile unsigned long long*)&t.keys[h]);
+        unsigned long long cur = *((volatile unsigned long long*)&t.slots[h].key);
         if (cur == KEY_EMPTY) {
-            cur = atomicCAS(&t.keys[h], (unsigned long long)KEY_EMPTY, (unsigned long long)code);
+            cur = atomicCAS(&t.slots[h].key, (unsigned long long)KEY_EMPTY, (unsigned long long)code);
             if (cur == KEY_EMPTY) {
                 const unsigned long long d = atomicAdd(t.distinct, 1ull);
                 if (d + 1 > t.max_distinct) *t.full = 1u;
@@ -51,7 +59,7 @@ __device__ __forceinline__ void hash_add(const HashTable& t, uint64_t code, uint
             }
         }
         if (cur == code) {
-            atomicAdd(&t.counts[h], add);
+            atomicAdd(&t.slots[h].count, add);
             return;
         }
         h = (h + 1) & t.mask;
@@ -85,31 +93,50 @@ __global__ void hash_add_pairs_kernel(const uint64_t* __restrict__ keys, const u
         hash_add(t, keys[i], counts[i]);
 }
 
-__global__ void hash_init_kernel(unsigned long long* keys, uint32_t* counts, uint64_t cap) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        keys[i] = KEY_EMPTY;
-        counts[i] = 0;
-    }
+__global__ void hash_init_kernel(HashSlot* slots, uint64_t cap) {
+    const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    uint4* p = reinterpret_cast<uint4*>(slots);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = empty;
 }
 
-__global__ void hash_compact_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counts,
-                                    uint64_t cap, uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts,
-                                    unsigned long long* cursor) {
-    const int lane = threadIdx.x & 31;
+// Compaction: per CTA iteration one global atomic reserves room for every occupied
+// slot the CTA saw (warp ballots -> shared counter -> one atomicAdd), instead of one
+// same-address global atomic per warp.
+__global__ void __launch_bounds__(256) hash_compact_kernel(const HashSlot* __restrict__ slots, uint64_t cap,
+                                                           uint64_t* __restrict__ out_keys,
+                                                           uint32_t* __restrict__ out_counts,
+                                                           unsigned long long* cursor) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t cap32 = (cap + 31) & ~31ull;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap32; i += stride) {
-        const bool has = i < cap && keys[i] != KEY_EMPTY;
+    const uint64_t capr = (cap + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const uint4* p = reinterpret_cast<const uint4*>(slots);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capr; i += stride) {
+        uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        if (i < cap) v = kc_ldg_stream(p + i);
+        const bool has = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
         const uint32_t m = __ballot_sync(0xffffffffu, has);
-        if (m == 0) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (has) {
-            const uint64_t o = base + __popc(m & ((1u << lane) - 1u));
-            out_keys[o] = keys[i];
-            out_counts[o] = counts[i];
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t c = s_warp[w];
+                s_warp[w] = tot;
+                tot += c;
+            }
+            s_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
         }
+        __syncthreads();
+        if (has) {
+            const uint64_t o = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+            out_keys[o] = ((uint64_t)v.y << 32) | v.x;
+            out_counts[o] = v.z;
+        }
+        __syncthreads();
     }
 }
 
@@ -120,6 +147,7 @@ template <int HALO>
 __global__ void __launch_bounds__(256) sparse_codes_kernel(ScanGeom g, uint64_t* __restrict__ out) {
     const int k = g.k;
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;
+    const uint64_t invalid = 1ull << (2 * k);  // sorts behind every code within 2k+1 key bits
     const uint64_t ngroups = g.g_end - g.g_begin;
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     const uint64_t gpw = (ngroups + nwarps - 1) / nwarps;
@@ -130,16 +158,16 @@ __global__ void __launch_bounds__(256) sparse_codes_kernel(ScanGeom g, uint64_t*
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const uint64_t a = a0 + j;
-            if (a >= g.wlo && a < g.whi) out[a - g.wlo] = (lw.ok & (1u << j)) ? lw.code64(j, kmask) : KEY_EMPTY;
+            if (a >= g.wlo && a < g.whi) out[a - g.wlo] = (lw.ok & (1u << j)) ? lw.code64(j, kmask) : invalid;
         }
     });
 }
 
 // trims the EMPTY run at the end of a sorted unique list
 __global__ void count_valid_runs_kernel(const uint64_t* __restrict__ uniq, const unsigned long long* nruns,
-                                        unsigned long long* nvalid) {
+                                        unsigned long long* nvalid, uint64_t invalid) {
     const unsigned long long n = *nruns;
-    *nvalid = (n > 0 && uniq[n - 1] == KEY_EMPTY) ? n - 1 : n;
+    *nvalid = (n > 0 && uniq[n - 1] == invalid) ? n - 1 : n;
 }
 
 __global__ void owner_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t owners,
@@ -235,18 +263,17 @@ template <int HALO>
 int run_hash(kc_ctx* ctx, const ScanGeom& g, uint64_t capacity, DevBuf& okeys, DevBuf& ocounts, uint64_t* ndistinct,
              bool* full) {
     cudaStream_t st = ctx->stream;
-    DevBuf keys, counts, ctl;
-    if (keys.alloc(capacity * 8) || counts.alloc(capacity * 4) || ctl.alloc(64)) {
+    DevBuf slots, ctl;
+    if (slots.alloc(capacity * sizeof(HashSlot)) || ctl.alloc(64)) {
         cudaGetLastError();
         return kc_set_error(ctx, KC_ERR_NOMEM, "hash table of %llu slots does not fit in device memory",
                             (unsigned long long)capacity);
     }
     KC_CUDA(ctx, cudaMemsetAsync(ctl.p, 0, 64, st));
-    hash_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(keys.as<unsigned long long>(), counts.as<uint32_t>(), capacity);
+    hash_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(slots.as<HashSlot>(), capacity);
     KC_LAUNCH_CHECK(ctx, "hash_init_kernel");
     HashTable t;
-    t.keys = keys.as<unsigned long long>();
-    t.counts = counts.as<uint32_t>();
+    t.slots = slots.as<HashSlot>();
     t.mask = capacity - 1;
     t.distinct = ctl.as<unsigned long long>();
     t.full = (uint32_t*)(ctl.as<unsigned long long>() + 1);
@@ -267,7 +294,7 @@ int run_hash(kc_ctx* ctx, const ScanGeom& g, uint64_t capacity, DevBuf& okeys, D
         return kc_set_error(ctx, KC_ERR_NOMEM, "out of device memory compacting %llu k-mers", h[0]);
     }
     unsigned long long* cursor = ctl.as<unsigned long long>() + 2;
-    hash_compact_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(t.keys, t.counts, capacity, okeys.as<uint64_t>(),
+    hash_compact_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(t.slots, capacity, okeys.as<uint64_t>(),
                                                            ocounts.as<uint32_t>(), cursor);
     KC_LAUNCH_CHECK(ctx, "hash_compact_kernel");
     KC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -305,7 +332,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         size_t free_b = 0, total_b = 0;
         KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
         uint64_t cap = next_pow2(want + want / 2 + 1024);
-        while (cap * 12 > free_b * 6 / 10 && cap > 1024) cap >>= 1;  // keep room for the compacted copy
+        while (cap * 16 > free_b * 6 / 10 && cap > 1024) cap >>= 1;  // keep room for the compacted copy
         for (;;) {
             DevBuf ok, oc;
             uint64_t nd = 0;
@@ -316,7 +343,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
                 rc = sort_reduce_pairs(ctx, ok.as<uint64_t>(), oc.as<uint32_t>(), nd, 2 * k, out);
                 return rc;
             }
-            if (cap * 2 * 12 > free_b * 8 / 10)
+            if (cap * 2 * 16 > free_b * 8 / 10)
                 return kc_set_error(ctx, KC_ERR_TABLE_FULL, "hash table with %llu slots overflowed and a larger one does not fit",
                                     (unsigned long long)cap);
             cap *= 2;
@@ -343,7 +370,8 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
             sparse_codes_kernel<2><<<grid_for(ctx, ngroups), 256, 0, st>>>(g, codes.as<uint64_t>());
         KC_LAUNCH_CHECK(ctx, "sparse_codes_kernel");
         size_t t1 = 0, t2 = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, t1, codes.as<uint64_t>(), sorted.as<uint64_t>(), (int)m, 0, 64, st);
+        const int sort_bits = 2 * k + 1;  // codes + the invalid marker at bit 2k
+        cub::DeviceRadixSort::SortKeys(nullptr, t1, codes.as<uint64_t>(), sorted.as<uint64_t>(), (int)m, 0, sort_bits, st);
         cub::DeviceRunLengthEncode::Encode(nullptr, t2, sorted.as<uint64_t>(), uniq.as<uint64_t>(), cnts.as<uint32_t>(),
                                            ctl.as<unsigned long long>(), (int)m, st);
         size_t tb = t1 > t2 ? t1 : t2;
@@ -351,13 +379,12 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
             cudaGetLastError();
             return kc_set_error(ctx, KC_ERR_NOMEM, "sort path: out of device memory for sort scratch");
         }
-        // the EMPTY sentinel has bits above 2k set, so sort all 64 bits: it lands last
-        KC_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, tb, codes.as<uint64_t>(), sorted.as<uint64_t>(), (int)m, 0, 64, st));
+        KC_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, tb, codes.as<uint64_t>(), sorted.as<uint64_t>(), (int)m, 0, sort_bits, st));
         tb = t1 > t2 ? t1 : t2;
         KC_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(tmp.p, tb, sorted.as<uint64_t>(), uniq.as<uint64_t>(), cnts.as<uint32_t>(),
                                                         ctl.as<unsigned long long>(), (int)m, st));
         ctx->launches += 8;
-        count_valid_runs_kernel<<<1, 1, 0, st>>>(uniq.as<uint64_t>(), ctl.as<unsigned long long>(), ctl.as<unsigned long long>() + 1);
+        count_valid_runs_kernel<<<1, 1, 0, st>>>(uniq.as<uint64_t>(), ctl.as<unsigned long long>(), ctl.as<unsigned long long>() + 1, 1ull << (2 * k));
         KC_LAUNCH_CHECK(ctx, "count_valid_runs_kernel");
         unsigned long long h[2];
         KC_CUDA(ctx, cudaMemcpyAsync(h, ctl.p, 16, cudaMemcpyDeviceToHost, st));
