@@ -352,7 +352,9 @@ def main():
     p1 = float(np.mean([p[0] for p in passes]))
     p2 = float(np.mean([p[1] for p in passes]))
     bases_launch = e - b + k - 1
-    if p2 > 0:  # two-pass partition path
+    if p2 > 0 and k == 8:  # shared-memory 16-bit bins + reduce of the per-CTA partials
+        kernels = {"dense_smem16_kernel": (p1, bases_launch), "smem16_reduce_kernel": (p2, 4 * nk)}
+    elif p2 > 0:  # two-pass partition path
         kernels = {"part_scatter_kernel": (p1, bases_launch), "part_count_kernel": (p2, 4 * nk)}
     else:
         kernels = {"dense_direct_kernel": (p1, bases_launch + 4 * nk)}

@@ -61,6 +61,130 @@ __global__ void __launch_bounds__(256) dense_direct_kernel(ScanGeom g, uint32_t*
     }
 }
 
+__device__ __forceinline__ void global_red_add_early(uint32_t* p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// k = 8: shared-memory-privatised bins with 16-bit counters
+// ---------------------------------------------------------------------------
+// 4^8 uint32 bins are 256 KB — more than one CTA can hold — so each CTA keeps the
+// 65536 bins as 16-bit fields, two per 32-bit word (bin c lives in word c & 0x7FFF,
+// half c >> 15): 128 KB.  A field must never wrap into its neighbour:
+//   * the thread whose add makes a field reach a multiple of 0x4000 moves 0x4000 of
+//     it to the global table (shared atomic add of -0x4000 on the field, one global
+//     RED of +0x4000);
+//   * the CTA meets at a barrier every 2 steps = 32768 adds.
+// Invariant: every pending move was triggered at a value >= 0x4000 * (moves pending),
+// so a field never goes negative; at a barrier nothing is pending and each field is
+// < 0x4000 (every up-crossing of a multiple of 0x4000 is paired with one move down);
+// between two barriers at most 32768 adds happen in the whole CTA, so a field stays
+// below 0x4000 + 0x8000 = 0xC000 < 0x10000 whatever the scheduling.
+// At the end every CTA writes its 32768 words to partials[cta][] and
+// smem16_reduce_kernel adds them, unpacked, into the table.
+__device__ __forceinline__ uint32_t smem_atom_add_k8(uint32_t saddr, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
+    return r;
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(1024, 1)
+dense_smem16_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* __restrict__ table,
+                    uint32_t* __restrict__ partials) {
+    static_assert(DEPTH == 2, "the barrier period (2 steps = 32768 adds) is the unroll factor");
+    extern __shared__ uint32_t words[];  // 32768
+    const uint32_t s_words = (uint32_t)__cvta_generic_to_shared(words);
+    const int tid = threadIdx.x, lane = tid & 31;
+    {
+        uint4* w4 = reinterpret_cast<uint4*>(words);
+        for (int i = tid; i < 32768 / 4; i += 1024) w4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const uint64_t nwarps = (uint64_t)gridDim.x * 32;
+    const uint64_t units = ngroups / DEPTH;
+    const uint64_t upw = (units + nwarps - 1) / nwarps;  // unrolled iterations of every warp (uniform)
+    const uint64_t w = (uint64_t)blockIdx.x * 32 + (tid >> 5);
+    const uint64_t gb = min(w * upw, units) * DEPTH;
+    const uint32_t nsteps = (uint32_t)(min((w + 1) * upw, units) * DEPTH - gb);
+    const uint4* ptr = base + gb * 32 + lane;
+    uint4 raw[DEPTH];
+    Decoded16 cur16;
+    cur16.packed = 0;
+    cur16.bad = 0xFFFFu;
+    if (nsteps) {
+        cur16 = kc_decode16(kc_ldg_stream(ptr));
+#pragma unroll
+        for (int q = 0; q < DEPTH; q++) raw[q] = kc_ldg_stream(ptr + 32 * (q + 1));
+    }
+    for (uint32_t i = 0; i < (uint32_t)upw * DEPTH; i += DEPTH) {
+        if (i < nsteps) {  // warp-uniform; nsteps is a multiple of DEPTH
+            uint4 fresh[DEPTH];
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) fresh[q] = kc_ldg_stream(ptr + 32 * (DEPTH + 1 + q));
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) {
+                const Decoded16 nxt = kc_decode16(raw[q]);
+                uint32_t p1 = __shfl_down_sync(0xffffffffu, cur16.packed, 1);
+                uint32_t b1 = __shfl_down_sync(0xffffffffu, cur16.bad, 1);
+                const uint32_t n0p = __shfl_sync(0xffffffffu, nxt.packed, 0);
+                const uint32_t n0b = __shfl_sync(0xffffffffu, nxt.bad, 0);
+                if (lane == 31) {
+                    p1 = n0p;
+                    b1 = n0b;
+                }
+                const uint32_t p0 = cur16.packed;
+                const uint32_t B32 = cur16.bad | (b1 << 16);
+                uint32_t ok = 0xFFFFu;
+                if (B32) ok = ~(uint32_t)kc_window_bad((uint64_t)B32 | (0xFFFFull << 32), 8) & 0xFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (ok & (1u << j)) {
+                        const uint32_t code = __funnelshift_r(p0, p1, 2 * j) & 0xFFFFu;
+                        const uint32_t inc = (code >> 15) * 0xFFFFu + 1u;  // 1 or 0x10000
+                        const uint32_t addr = s_words + (code & 0x7FFFu) * 4;
+                        const uint32_t old = smem_atom_add_k8(addr, inc);
+                        if (((old + inc) & (inc * 0x3FFFu)) == 0) {  // the field reached 0x4000 or 0x8000
+                            smem_atom_add_k8(addr, 0u - inc * 0x4000u);
+                            global_red_add_early(table + code, 0x4000u);
+                        }
+                    }
+                }
+                cur16 = nxt;
+            }
+            uint32_t zero;
+            asm volatile("shr.u32 %0, %1, 31;" : "=r"(zero) : "r"(cur16.bad) : "memory");  // bad < 2^16: pins the copies here
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) {
+                raw[q].x = fresh[q].x | zero;
+                raw[q].y = fresh[q].y | zero;
+                raw[q].z = fresh[q].z | zero;
+                raw[q].w = fresh[q].w | zero;
+            }
+            ptr += 32 * DEPTH;
+        }
+        __syncthreads();  // at most 32768 adds per CTA between two barriers
+    }
+    {
+        const uint4* w4 = reinterpret_cast<const uint4*>(words);
+        uint4* out = reinterpret_cast<uint4*>(partials + (uint64_t)blockIdx.x * 32768);
+        for (int i = tid; i < 32768 / 4; i += 1024) out[i] = w4[i];
+    }
+}
+
+__global__ void smem16_reduce_kernel(const uint32_t* __restrict__ partials, int nparts, uint32_t* __restrict__ table) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 32768) return;
+    uint32_t lo = 0, hi = 0;
+    for (int p = 0; p < nparts; p++) {
+        const uint32_t v = partials[(uint64_t)p * 32768 + w];
+        lo += v & 0xFFFFu;
+        hi += v >> 16;
+    }
+    table[w] += lo;
+    table[w + 32768] += hi;
+}
+
 // ---------------------------------------------------------------------------
 // partition path
 // ---------------------------------------------------------------------------
@@ -507,6 +631,44 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     return rc;
 }
 
+// k = 8 path: interior groups through dense_smem16_kernel, the rest through dense_direct
+static int dense_smem16(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
+                        uint32_t* d_table, cudaStream_t st) {
+    constexpr int DEPTH = 2;
+    const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, 8);
+    const uint64_t G0 = (max(g.lo, g.wlo) + 511) >> 9;
+    const uint64_t lim = min(g.hi, g.whi);
+    const uint64_t Gl = lim >> 9;
+    const uint64_t G1 = Gl > (uint64_t)(2 * DEPTH + 2) ? Gl - (2 * DEPTH + 2) : 0;
+    if (G1 <= G0 + 64) return dense_direct(ctx, g, d_table, st);
+    const uint64_t ngroups = (G1 - G0) / DEPTH * DEPTH;
+    const uint64_t shift = g.lo;
+    const uint64_t head_end = (G0 << 9) - shift;
+    const uint64_t tail_begin = ((G0 + ngroups) << 9) - shift;  // every window start of the interior groups is counted
+    const uint64_t want = (ngroups / DEPTH + 31) / 32;
+    const int grid = (int)(want > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want);
+    int rc = kc_scratch_reserve(ctx, (size_t)grid * 32768 * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t* partials = (uint32_t*)ctx->scratch;
+    const size_t smem = 32768 * sizeof(uint32_t);
+    KC_CUDA(ctx, cudaFuncSetAttribute(dense_smem16_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
+    dense_smem16_kernel<DEPTH><<<grid, 1024, smem, st>>>(g.abase + (G0 << 5), ngroups, d_table, partials);
+    KC_LAUNCH_CHECK(ctx, "dense_smem16_kernel");
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
+    smem16_reduce_kernel<<<32768 / 256, 256, 0, st>>>(partials, grid, d_table);
+    KC_LAUNCH_CHECK(ctx, "smem16_reduce_kernel");
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
+    const bool timing = ctx->timing;
+    ctx->timing = false;
+    rc = KC_OK;
+    if (head_end > win_begin) rc = dense_direct(ctx, kc_make_geom(d_data, nbytes, win_begin, head_end, 8), d_table, st);
+    if (!rc && tail_begin < win_end) rc = dense_direct(ctx, kc_make_geom(d_data, nbytes, tail_begin, win_end, 8), d_table, st);
+    ctx->timing = timing;
+    if (timing) ctx->timed_kernels = 2;
+    return rc;
+}
+
 static uint64_t g_partition_min_windows = 1ull << 26;  // below this the direct path wins
 
 extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
@@ -530,6 +692,8 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     const bool use_part =
         can_part && (algo == KC_DENSE_PARTITION ||
                      (algo == KC_DENSE_AUTO && (win_end - win_begin) >= g_partition_min_windows));
+    if (k == 8 && algo == KC_DENSE_AUTO && (win_end - win_begin) >= (1ull << 22))
+        return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
     if (use_part) {
         // measured on B200 (profiles/r01_scatter_shapes.txt): CAP 16 / depth 3 is the fastest shape
         static const int shape = getenv("KC_PART_SHAPE") ? atoi(getenv("KC_PART_SHAPE")) : 0;  // tuning aid

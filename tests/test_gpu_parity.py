@@ -384,3 +384,22 @@ def test_all_256_byte_values(ctx, kmerlib, oracle):
     base[1000:1000 + s.size:97] = s[: len(base[1000:1000 + s.size:97])]
     want, _ = oracle.count_dense(base, 12)
     assert (dense_gpu(ctx, kmerlib, to_dev(base), base.size, 12, algo=kmerlib.DENSE_PARTITION) == want).all()
+
+
+def test_dense_k8_smem16(ctx, kmerlib, oracle):
+    """k=8 shared-memory path (16-bit fields with bounded spill): random, dirty and
+    maximally skewed inputs, unaligned pointer, range split."""
+    n = 9_000_001
+    for s in (dirty(oracle, n, seed=88), np.full(n, ord("A"), np.uint8), np.frombuffer(b"ACGTTGCAAC" * (n // 10), np.uint8)):
+        m = s.size
+        want, _ = oracle.count_dense(s, 8)
+        d = to_dev(s)
+        assert (dense_gpu(ctx, kmerlib, d, m, 8) == want).all()
+        assert (dense_gpu(ctx, kmerlib, d, m, 8, algo=kmerlib.DENSE_DIRECT) == want).all()
+    s = dirty(oracle, n, seed=89)
+    want, _ = oracle.count_dense(s, 8)
+    d = _torch().zeros(n + 128, dtype=_torch().uint8, device="cuda:0")
+    d[5: 5 + n] = _torch().from_numpy(s)
+    assert (dense_gpu(ctx, kmerlib, d, n, 8, offset=5) == want).all()
+    nwin = n - 7
+    assert (dense_gpu(ctx, kmerlib, to_dev(s), n, 8, ranges=[(0, 4_500_003), (4_500_003, nwin)]) == want).all()
