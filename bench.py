@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--reduce-slices", type=int, default=1,
                     help="N>1: count the shard in S slices and overlap each slice's NCCL reduce with the next count "
                          "(measured slower than S=1 at N=2: 2.24 / 2.57 / 3.35 ms for S=1/2/4)")
+    ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of a replayed CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -335,18 +336,41 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    l0 = ctx.launch_count
+    step()
+    launches_per_step = ctx.launch_count - l0 + S  # + one zero-fill kernel per slice table
+    barrier()
+    # One step = zero-fill + ~8 launches (+ the NCCL reduce): captured once in a CUDA
+    # graph and replayed, so the timed region is not paced by Python/ctypes launches.
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            graph.replay()
+            barrier()
+        except Exception as ex:  # fall back to plain launches
+            sys.stderr.write("bench: CUDA graph capture failed (%s); timing plain launches\n" % ex)
+            graph = None
+            torch.cuda.synchronize()
+    run_step = graph.replay if graph is not None else step
     sampler = ClockSampler(local)
-    launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     ev0.record()
     for _ in range(args.steps):
-        step()
+        run_step()
     ev1.record()
     barrier()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count - launches0 + args.steps * S  # + one zero-fill kernel per slice table
+    launches = launches_per_step * args.steps
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -449,6 +473,7 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "bases": L, "kmers_per_sec": (L - k + 1) / (ms_step * 1e-3),
                        "algo": {0: "auto", 1: "direct", 2: "partition"}[args.algo],
+                       "launch": "CUDA graph replay" if graph is not None else "plain launches",
                        "l2": "input %.1f GB per GPU exceeds the 126 MB L2 (no flush needed)" % (nb / 1e9)
                        if nb > 512e6 else "input smaller than L2: table+scratch writes of each step evict it only partly",
                        "sharding": ("window ranges + %d-byte halo; ncclReduce of uint32[4^k] in %d slices overlapped with counting"

@@ -497,16 +497,19 @@ part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sla
         __syncthreads();
         // add the sub-tables to the global table: for alignment r the bin is
         //   low (KB0-2r bits) | key << (KB0-2r) | high (2r bits) << (2K-2r)
-        for (int idx = tid; idx < C::NBINS; idx += 1024) {
-            const uint32_t v = bins[idx];
-            if (v) {
-                const int r = idx / C::SUB;
-                const uint32_t f = idx & SUBMASK;
-                const int lowbits = C::KB0 - 2 * r;
-                const uint32_t low = f & ((1u << lowbits) - 1u);
-                const uint32_t high = f >> lowbits;
-                const uint32_t code = low | (part << lowbits) | (high << (2 * C::K - 2 * r));
-                atomicAdd(&table[code], v);
+#pragma unroll
+        for (int r = 0; r < C::A; r++) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int lowbits = C::KB0 - 2 * r;
+            const uint32_t keypart = part << lowbits;
+            for (int f = tid; f < C::SUB; f += 1024) {
+                const uint32_t v = bins[r * C::SUB + f];
+                if (v) {
+                    const uint32_t low = (uint32_t)f & ((1u << lowbits) - 1u);
+                    const uint32_t high = (uint32_t)f >> lowbits;
+                    global_red_add(table + (low | keypart | (high << (2 * C::K - 2 * r))), v);
+                }
             }
         }
         __syncthreads();
