@@ -37,6 +37,12 @@ WORKLOADS = {
                     desc="100 Mbp synthetic ACGT, k=8 dense 65,536-bin histogram (BASELINE configs[1])"),
     "config1": dict(L=1_000_000, k=3, long_runs=0, short_runs=0, seed=0xB2000001,
                     desc="1 Mbp synthetic ACGT, k=3 (BASELINE configs[0])"),
+    # not BASELINE configs: the same 3.1 Gbp genome at the other partition-path k
+    "genome_k9": dict(L=3_100_000_000, k=9, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=9"),
+    "genome_k10": dict(L=3_100_000_000, k=10, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=10"),
+    "genome_k11": dict(L=3_100_000_000, k=11, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=11"),
+    "genome_k8": dict(L=3_100_000_000, k=8, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=8"),
+    "genome_k6": dict(L=3_100_000_000, k=6, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=6"),
 }
 SPARSE_WORKLOADS = {
     # name: (reads at full scale, read length, genome length, k, seed) — SURVEY §8d configs 4 and 5

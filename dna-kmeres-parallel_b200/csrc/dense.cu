@@ -689,19 +689,27 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (win_begin >= win_end) return KC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, k);
-    const bool can_part = (k == 12);
+    const bool can_part = (k >= 9 && k <= 12);
     if (algo == KC_DENSE_PARTITION && !can_part)
-        return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "partition path is built for k=12 only (k=%d)", k);
+        return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "partition path is built for k = 9..12 (k=%d)", k);
     const bool use_part =
         can_part && (algo == KC_DENSE_PARTITION ||
                      (algo == KC_DENSE_AUTO && (win_end - win_begin) >= g_partition_min_windows));
     if (k == 8 && algo == KC_DENSE_AUTO && (win_end - win_begin) >= (1ull << 22))
         return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
     if (use_part) {
-        // measured on B200 (profiles/r01_scatter_shapes.txt): CAP 16 / depth 3 is the fastest shape
+        // PartCfg<K, A, KB, CAP>: A windows per 32-bit record (K + A - 1 <= 16 bases), KB key bits
+        // inside the bases all A windows share, CAP records per chunk.  k = 12 shape measured on
+        // B200 (profiles/r01_scatter_shapes.txt): CAP 16 / 3 loads in flight is the fastest.
         static const int shape = getenv("KC_PART_SHAPE") ? atoi(getenv("KC_PART_SHAPE")) : 0;  // tuning aid
-        if (shape == 1) return dense_partition<ScatterShape<PartCfg<12, 5, 11, 24>, 1024, 1, 2>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
-        return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+        switch (k) {
+            case 12:
+                if (shape == 1) return dense_partition<ScatterShape<PartCfg<12, 5, 11, 24>, 1024, 1, 2>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+                return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+            case 11: return dense_partition<ScatterShape<PartCfg<11, 6, 11, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+            case 10: return dense_partition<ScatterShape<PartCfg<10, 7, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+            default: return dense_partition<ScatterShape<PartCfg<9, 6, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+        }
     }
     return dense_direct(ctx, g, d_table, st);
 }

@@ -88,16 +88,16 @@ def test_dense_all_k(ctx, kmerlib, oracle, k):
     want, _ = oracle.count_dense(s, k)
     d = to_dev(s)
     assert (dense_gpu(ctx, kmerlib, d, n, k) == want).all()
-    if k == 12:
+    if 9 <= k <= 12:  # the partition path (auto only picks it for >= 2^26 windows)
         assert (dense_gpu(ctx, kmerlib, d, n, k, algo=kmerlib.DENSE_DIRECT) == want).all()
         assert (dense_gpu(ctx, kmerlib, d, n, k, algo=kmerlib.DENSE_PARTITION) == want).all()
 
 
-@pytest.mark.parametrize("k", [3, 8, 12, 16])
+@pytest.mark.parametrize("k", [3, 8, 9, 10, 11, 12, 16])
 def test_dense_edges(ctx, kmerlib, oracle, k):
     torch = _torch()
     rng = np.random.default_rng(k)
-    algos = [kmerlib.DENSE_DIRECT] + ([kmerlib.DENSE_PARTITION] if k == 12 else [])
+    algos = [kmerlib.DENSE_DIRECT] + ([kmerlib.DENSE_PARTITION] if 9 <= k <= 12 else [])
     if k == 16:
         # 16 GiB table: only the code path for tiny inputs against a sparse oracle
         s = oracle.gen_bases(1, 0, 3000)
@@ -122,7 +122,7 @@ def test_dense_edges(ctx, kmerlib, oracle, k):
                 assert (got == want).all(), (n, algo, off)
 
 
-@pytest.mark.parametrize("k,algo", [(5, 1), (12, 1), (12, 2)])
+@pytest.mark.parametrize("k,algo", [(5, 1), (12, 1), (12, 2), (9, 2), (10, 2), (11, 2)])
 def test_dense_range_additivity(ctx, kmerlib, oracle, k, algo):
     n = 900_001
     s = dirty(oracle, n, seed=40 + k)
@@ -150,7 +150,7 @@ def test_dense_skewed_inputs(ctx, kmerlib, oracle):
     n = 3_000_000
     for s in (np.full(n, ord("A"), np.uint8), np.frombuffer(b"AC" * (n // 2), np.uint8),
               np.full(n, ord("N"), np.uint8), np.frombuffer(b"ACGTTGCA" * (n // 8), np.uint8)):
-        for k, algo in ((4, 0), (12, 1), (12, 2)):
+        for k, algo in ((4, 0), (12, 1), (12, 2), (9, 2), (10, 2), (11, 2)):
             want, _ = oracle.count_dense(s, k)
             assert (dense_gpu(ctx, kmerlib, to_dev(s), n, k, algo=algo) == want).all()
 
@@ -180,7 +180,7 @@ def test_sync_entry_point_and_errors(ctx, kmerlib, oracle):
     assert L.kc_count_dense(ctx._h, d.data_ptr(), s.size, 0, table.data_ptr()) == kmerlib.KC_ERR_INVALID
     assert L.kc_count_dense(ctx._h, d.data_ptr(), s.size, 17, table.data_ptr()) == kmerlib.KC_ERR_INVALID
     assert b"dense k must be" in L.kc_last_error(ctx._h)
-    assert L.kc_count_dense_range_async(ctx._h, d.data_ptr(), s.size, 0, s.size, 6, table.data_ptr(), 2, None) == kmerlib.KC_ERR_UNSUPPORTED
+    assert L.kc_count_dense_range_async(ctx._h, d.data_ptr(), s.size, 0, s.size, 6, table.data_ptr(), 2, None) == kmerlib.KC_ERR_UNSUPPORTED  # partition path: k = 9..12
     assert ctx.launch_count > 0
 
 
