@@ -198,6 +198,10 @@ struct DevBuf {
         if (p) cudaFree(p);
     }
     cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    void reset() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
     template <typename T>
     T* as() {
         return (T*)p;
@@ -353,7 +357,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
     // sort path, chunked so that codes + sort buffers stay bounded
     const uint64_t chunk = 1ull << 28;  // windows per chunk (2 GiB of codes)
     DevBuf acc_k, acc_c;
-    uint64_t acc_n = 0, acc_cap = 0;
+    uint64_t acc_n = 0, acc_cap = 0, merged_n = 0;
     for (uint64_t wb = 0; wb < nwin; wb += chunk) {
         const uint64_t we = (wb + chunk < nwin) ? wb + chunk : nwin;
         const uint64_t m = we - wb;
@@ -410,6 +414,31 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         KC_CUDA(ctx, cudaMemcpyAsync(acc_c.as<uint32_t>() + acc_n, cnts.p, nv * 4, cudaMemcpyDeviceToDevice, st));
         KC_CUDA(ctx, cudaStreamSynchronize(st));
         acc_n += nv;
+        // Keep the accumulated runs bounded: with deep coverage most runs of different
+        // chunks are the same k-mers, so merge (sort + reduce-by-key) whenever the list
+        // has grown by more than a chunk's worth since the last merge.
+        if (acc_n > merged_n + 3 * chunk && wb + chunk < nwin) {
+            codes.reset();  // the chunk's buffers are no longer needed: make room for the merge
+            sorted.reset();
+            uniq.reset();
+            cnts.reset();
+            tmp.reset();
+            kc_sparse* part = nullptr;
+            int rc = sort_reduce_pairs(ctx, acc_k.as<uint64_t>(), acc_c.as<uint32_t>(), acc_n, 2 * k, &part);
+            if (rc) {
+                kc_sparse_free(part);
+                return rc;
+            }
+            cudaFree(acc_k.p);
+            cudaFree(acc_c.p);
+            acc_k.p = part->d_keys;
+            acc_c.p = part->d_counts;
+            acc_n = merged_n = part->size;
+            acc_cap = part->size;  // the arrays hold `n input items` each, at least size
+            part->d_keys = nullptr;
+            part->d_counts = nullptr;
+            kc_sparse_free(part);
+        }
     }
     return sort_reduce_pairs(ctx, acc_k.as<uint64_t>(), acc_c.as<uint32_t>(), acc_n, 2 * k, out);
 }

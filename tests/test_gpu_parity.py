@@ -403,3 +403,23 @@ def test_dense_k8_smem16(ctx, kmerlib, oracle):
     assert (dense_gpu(ctx, kmerlib, d, n, 8, offset=5) == want).all()
     nwin = n - 7
     assert (dense_gpu(ctx, kmerlib, to_dev(s), n, 8, ranges=[(0, 4_500_003), (4_500_003, nwin)]) == want).all()
+
+
+def test_sparse_deep_coverage_hash_equals_sort(ctx, kmerlib, oracle):
+    """config 4 shape at 1/20 scale (5 M reads, 750 Mbp): too big for the CPU oracle's sort
+    in test time, so check the two independent GPU algorithms against each other and
+    against sum(counts) = number of windows (reads hold only ACGT)."""
+    nreads, k = 5_000_000, 21
+    reads = ctx.gen_reads(0xB2000004, 25_000_000, 150, 200, 0, nreads)
+    a = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_HASH)
+    b = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_SORT)
+    ka, ca = a.to_host()
+    kb, cb = b.to_host()
+    assert len(a) == len(b) and (ka == kb).all() and (ca == cb).all()
+    assert int(ca.astype(np.int64).sum()) == nreads * (150 - k + 1)
+    assert (np.diff(ka.astype(np.int64)) > 0).all() and int(ka.max()) < (1 << 42)
+    # a slice of it against the oracle
+    part = reads[: 20_000 * 151].cpu().numpy()
+    wk, wc, _ = oracle.count_sparse(part, k)
+    kp, cp = ctx.count_sparse(reads, 20_000 * 151, k, kmerlib.SPARSE_SORT).to_host()
+    assert (kp == wk).all() and (cp == wc).all()
