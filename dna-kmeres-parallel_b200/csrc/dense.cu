@@ -7,7 +7,9 @@
 //   dense_direct_kernel<SMEM>  k <= 7 : CTA-private 4^k uint32 bins in shared
 //                                       memory, flushed once with global REDs.
 //   dense_direct_kernel<GLOBAL> any k : one global RED per window (bins in L2).
-//   partition path (k = 12)           : pass 1 groups A=5 consecutive windows
+//   dense_smem16_kernel         k = 8 : 65536 16-bit bins in shared memory with a
+//                                       provably bounded spill to the global table.
+//   partition path (k = 9..12, shown for 12): pass 1 groups A=5 consecutive windows
 //       into one 32-bit "record" (the 16 bases they span), radix-partitions
 //       records by 11 bits that all five windows share, staging them in shared
 //       memory so every global write is a coalesced run; pass 2 gives each CTA
@@ -18,6 +20,27 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+
+// ---- shared-memory / global primitives as inline PTX (32-bit shared addresses): keeps
+// ptxas from wrapping atomicAdd in its warp-aggregation sequence and pins the program
+// order the staging protocols below rely on.
+__device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+// plain RED (no compiler warp-aggregation wrapper around it)
+__device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ---------------------------------------------------------------------------
 // direct kernels
@@ -61,10 +84,6 @@ __global__ void __launch_bounds__(256) dense_direct_kernel(ScanGeom g, uint32_t*
     }
 }
 
-__device__ __forceinline__ void global_red_add_early(uint32_t* p, uint32_t v) {
-    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // ---------------------------------------------------------------------------
 // k = 8: shared-memory-privatised bins with 16-bit counters
 // ---------------------------------------------------------------------------
@@ -82,12 +101,6 @@ __device__ __forceinline__ void global_red_add_early(uint32_t* p, uint32_t v) {
 // below 0x4000 + 0x8000 = 0xC000 < 0x10000 whatever the scheduling.
 // At the end every CTA writes its 32768 words to partials[cta][] and
 // smem16_reduce_kernel adds them, unpacked, into the table.
-__device__ __forceinline__ uint32_t smem_atom_add_k8(uint32_t saddr, uint32_t v) {
-    uint32_t r;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
-    return r;
-}
-
 template <int DEPTH>
 __global__ void __launch_bounds__(1024, 1)
 dense_smem16_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* __restrict__ table,
@@ -143,10 +156,10 @@ dense_smem16_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
                         const uint32_t code = __funnelshift_r(p0, p1, 2 * j) & 0xFFFFu;
                         const uint32_t inc = (code >> 15) * 0xFFFFu + 1u;  // 1 or 0x10000
                         const uint32_t addr = s_words + (code & 0x7FFFu) * 4;
-                        const uint32_t old = smem_atom_add_k8(addr, inc);
+                        const uint32_t old = smem_atom_add(addr, inc);
                         if (((old + inc) & (inc * 0x3FFFu)) == 0) {  // the field reached 0x4000 or 0x8000
-                            smem_atom_add_k8(addr, 0u - inc * 0x4000u);
-                            global_red_add_early(table + code, 0x4000u);
+                            smem_atom_add(addr, 0u - inc * 0x4000u);
+                            global_red_add(table + code, 0x4000u);
                         }
                     }
                 }
@@ -210,36 +223,11 @@ __device__ __forceinline__ uint32_t part_code(uint32_t rec, int r) {
     return (rec >> (2 * r)) & ((C::K == 16) ? 0xFFFFFFFFu : ((1u << (2 * C::K)) - 1u));
 }
 
-// plain RED (inline PTX: no compiler warp-aggregation wrapper around it)
-__device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
-    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Slow path, deliberately NOT inlined: it is taken by ~1 % of the records (bin full
-// while its flush is in flight, records next to an N run) and inlining its five
-// predicated REDs at every call site quadrupled the size of the scatter kernel.
 template <typename C>
 __device__ __noinline__ void part_fallback(uint32_t rec, uint32_t okbits, uint32_t* table) {
 #pragma unroll
     for (int r = 0; r < C::A; r++)
         if (okbits & (1u << r)) global_red_add(table + part_code<C>(rec, r), 1u);
-}
-
-// ---- shared-memory primitives as inline PTX (32-bit shared addresses): keeps
-// ptxas from wrapping atomicAdd in its warp-aggregation sequence and pins the
-// program order the staging protocol below relies on.
-__device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
-    uint32_t r;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
-    return r;
-}
-__device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
-    return r;
 }
 
 // Pass 1.  Each warp owns a contiguous run of 512-byte groups and never waits for
@@ -499,8 +487,6 @@ part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sla
         //   low (KB0-2r bits) | key << (KB0-2r) | high (2r bits) << (2K-2r)
 #pragma unroll
         for (int r = 0; r < C::A; r++) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int lowbits = C::KB0 - 2 * r;
             const uint32_t keypart = part << lowbits;
             for (int f = tid; f < C::SUB; f += 1024) {

@@ -87,12 +87,6 @@ __global__ void __launch_bounds__(256) sparse_hash_kernel(ScanGeom g, HashTable 
     });
 }
 
-__global__ void hash_add_pairs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
-                                      uint64_t n, HashTable t) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        hash_add(t, keys[i], counts[i]);
-}
-
 __global__ void hash_init_kernel(HashSlot* slots, uint64_t cap) {
     const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
     uint4* p = reinterpret_cast<uint4*>(slots);
