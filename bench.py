@@ -410,8 +410,20 @@ def main():
     achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
     step_bytes = (L + 4 * nk)
     step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this
+    # workload, scaled by the bases this launch processed (bench.py cannot run ncu itself)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if args.workload == "config3" and dom in tj["kernels"]:
+            kj = tj["kernels"][dom]
+            traffic = (kj["dram_bytes_read"] + kj["dram_bytes_write"]) * bases_launch / tj["bases_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu)" if traffic else None,
+                "peak_source": peak_src,
                 "kernel_ms": {n: v[0] for n, v in kernels.items()},
                 "algorithmic_bytes_per_launch": dbytes,
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8000": step_gbs / 8000.0,
