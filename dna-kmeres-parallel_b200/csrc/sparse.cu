@@ -308,6 +308,8 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
     if (!ctx || !out) return KC_ERR_INVALID;
     *out = nullptr;
     if (k < 1 || k > KC_MAX_K) return kc_set_error(ctx, KC_ERR_INVALID, "sparse k must be 1..%d, got %d", KC_MAX_K, k);
+    const bool unsorted = (algo & KC_SPARSE_UNSORTED) != 0;
+    algo &= ~KC_SPARSE_UNSORTED;
     if (algo != KC_SPARSE_HASH && algo != KC_SPARSE_SORT) return kc_set_error(ctx, KC_ERR_INVALID, "unknown sparse algo %d", algo);
     if (!d_data && nbytes) return kc_set_error(ctx, KC_ERR_INVALID, "null data");
     DeviceGuard dg(ctx->device);
@@ -338,6 +340,15 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
             int rc = (halo == 1) ? run_hash<1>(ctx, g, cap, ok, oc, &nd, &full) : run_hash<2>(ctx, g, cap, ok, oc, &nd, &full);
             if (rc) return rc;
             if (!full) {
+                if (unsorted) {  // hand the compacted table over as it is
+                    kc_sparse* res = new kc_sparse();
+                    res->ctx = ctx;
+                    res->size = nd;
+                    res->d_keys = (uint64_t*)ok.release();
+                    res->d_counts = (uint32_t*)oc.release();
+                    *out = res;
+                    return KC_OK;
+                }
                 rc = sort_reduce_pairs(ctx, ok.as<uint64_t>(), oc.as<uint32_t>(), nd, 2 * k, out);
                 return rc;
             }

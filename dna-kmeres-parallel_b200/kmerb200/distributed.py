@@ -75,9 +75,10 @@ def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):
     import torch
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
-    local = ctx.count_sparse(d_reads, nbytes, k, algo)
     if world == 1:
-        return local
+        return ctx.count_sparse(d_reads, nbytes, k, algo)
+    from . import SPARSE_UNSORTED
+    local = ctx.count_sparse(d_reads, nbytes, k, algo | SPARSE_UNSORTED)  # re-bucketed below: no local sort
     n = len(local)
     dev = "cuda:%d" % ctx.device
     ok = torch.empty(max(n, 1), dtype=torch.int64, device=dev)

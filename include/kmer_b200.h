@@ -182,6 +182,9 @@ KC_API int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
  * sorted by code with their uint32 counts.                                  */
 #define KC_SPARSE_HASH 0   /* open-addressing hash table (CAS key, RED count) */
 #define KC_SPARSE_SORT 1   /* radix sort of codes + run-length reduce          */
+/* OR-ed into `algo`: leave the distinct (code,count) pairs in table order instead of
+ * sorting them — for callers that re-bucket and merge anyway (the multi-GPU path).   */
+#define KC_SPARSE_UNSORTED 0x100
 KC_API int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int algo,
                            uint64_t capacity_hint, kc_sparse** out);
 KC_API void kc_sparse_free(kc_sparse* s);
