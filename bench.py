@@ -230,6 +230,7 @@ def run_sparse(args):
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(ctx.launch_count - launches0),
         }
         emit(line)
+    arm_exit_watchdog()
     sp.close()
     if world > 1:
         dist.destroy_process_group()
@@ -254,6 +255,13 @@ def emit(line):
     out = _REAL_STDOUT or sys.stdout
     out.write(json.dumps(line) + "\n")
     out.flush()
+
+
+def arm_exit_watchdog(seconds=45):
+    """The result line is out; if library teardown (NCCL, CUDA graphs) stalls, leave anyway."""
+    t = threading.Timer(seconds, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
 
 
 def main():
@@ -349,7 +357,9 @@ def main():
     # One step = zero-fill + ~8 launches (+ the NCCL reduce): captured once in a CUDA
     # graph and replayed, so the timed region is not paced by Python/ctypes launches.
     graph = None
-    if not args.no_graph:
+    # N > 1 keeps plain launches: a captured NCCL reduce replays fine (N=8: 1.02 ms/step) but the
+    # process then hung in teardown (graph + process group), which no timing gain is worth.
+    if not args.no_graph and world == 1:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -500,7 +510,10 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)
+    arm_exit_watchdog()
+    graph = None
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     ctx.close()
     return 0

@@ -512,9 +512,8 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
     if (ngroups == 0) return KC_OK;
     const int k = g.k;
     const bool use_smem = (k <= 7);
-    // 8 warps per CTA; small inputs are spread over the whole chip (one 512-byte group per
-    // warp: a 1 Mbp sequence is ~245 CTAs, a few microseconds), large ones capped at 8 CTAs per SM
-    uint64_t want = (ngroups + 7) / 8;
+    // 8 warps per CTA; aim at >= 8 groups per warp, at most 8 CTAs per SM
+    uint64_t want = (ngroups + 63) / 64;
     uint64_t maxg = (uint64_t)ctx->sm_count * (use_smem && k == 7 ? 3 : 8);
     int grid = (int)(want < 1 ? 1 : (want > maxg ? maxg : want));
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
