@@ -502,10 +502,12 @@ def main():
             "config": {"workload": w["desc"], "k": k, "bases": L, "kmers_per_sec": (L - k + 1) / (ms_step * 1e-3),
                        "algo": {0: "auto", 1: "direct", 2: "partition"}[args.algo],
                        "launch": "CUDA graph replay" if graph is not None else "plain launches",
-                       "l2": "input %.1f GB per GPU exceeds the 126 MB L2 (no flush needed)" % (nb / 1e9)
-                       if nb > 512e6 else "input smaller than L2: table+scratch writes of each step evict it only partly",
-                       "sharding": ("window ranges + %d-byte halo; ncclReduce of uint32[4^k] in %d slices overlapped with counting"
-                                    % (k - 1, S)) if world > 1 else "single GPU",
+                       "l2": ("input %.2f GB per GPU (+ as much scratch written per step) exceeds the 126 MB L2: "
+                              "no flush needed" % (nb / 1e9)) if nb > 252e6 else
+                             "input is not larger than 2x L2: each step still rewrites table + scratch, no explicit flush",
+                       "sharding": ("window ranges + %d-byte halo; ncclReduce of uint32[4^k] to rank 0%s"
+                                    % (k - 1, "" if S == 1 else " in %d slices overlapped with counting" % S))
+                       if world > 1 else "single GPU",
                        "table_checksum": checksum},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -513,7 +515,6 @@ def main():
     arm_exit_watchdog()
     graph = None
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
     ctx.close()
     return 0
