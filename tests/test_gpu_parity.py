@@ -277,14 +277,6 @@ def test_sparse_vs_oracle(ctx, kmerlib, oracle, k, algo):
     assert len(sp) == len(wk) and (keys == wk).all() and (counts == wc).all()
 
 
-def test_sparse_unsorted_flag(ctx, kmerlib, oracle):
-    s = dirty(oracle, 300_000, seed=77)
-    wk, wc, _ = oracle.count_sparse(s, 21)
-    keys, counts = ctx.count_sparse(to_dev(s), s.size, 21, kmerlib.SPARSE_HASH | kmerlib.SPARSE_UNSORTED).to_host()
-    order = np.argsort(keys)
-    assert (keys[order] == wk).all() and (counts[order] == wc).all()
-
-
 def test_sparse_edges(ctx, kmerlib, oracle):
     for algo in (0, 1):
         for s in (b"", b"ACGT", b"N" * 100, b"ACGT" * 20, b"A" * 1000):
@@ -431,3 +423,11 @@ def test_sparse_deep_coverage_hash_equals_sort(ctx, kmerlib, oracle):
     wk, wc, _ = oracle.count_sparse(part, k)
     kp, cp = ctx.count_sparse(reads, 20_000 * 151, k, kmerlib.SPARSE_SORT).to_host()
     assert (kp == wk).all() and (cp == wc).all()
+
+
+def test_sparse_unsorted_flag(ctx, kmerlib, oracle):
+    s = dirty(oracle, 300_000, seed=77)
+    wk, wc, _ = oracle.count_sparse(s, 21)
+    keys, counts = ctx.count_sparse(to_dev(s), s.size, 21, kmerlib.SPARSE_HASH | kmerlib.SPARSE_UNSORTED).to_host()
+    order = np.argsort(keys)
+    assert (keys[order] == wk).all() and (counts[order] == wc).all()
