@@ -1,7 +1,10 @@
 // api.cu — context, memory helpers, k-mer enumeration, FASTA loader, text dumps.
 // Host-side pieces of the C ABI (include/kmer_b200.h); no kernels here.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 
 #include <string>
 #include <vector>
@@ -263,8 +266,10 @@ int64_t kc_triangular_index(int64_t i, int64_t j, int64_t n) {
 // ---------------------------------------------------------------------------
 struct kc_seqset {
     std::vector<std::string> ids;
-    std::string data;               // sequences, each followed by '\0'
+    char* data = nullptr;           // sequences, each followed by '\0' (malloc'd, uninitialised tail)
+    size_t data_len = 0, data_cap = 0;
     std::vector<int64_t> offsets;   // num_seqs + 1
+    ~kc_seqset() { free(data); }
     uint32_t num_seqs = 0;
     // device copies
     kc_ctx* owner = nullptr;
@@ -293,14 +298,23 @@ struct LineReader {
     }
 };
 
-void close_record(kc_seqset* s, std::string& acc) {
-    s->offsets.push_back((int64_t)s->data.size());
-    for (char& ch : acc)
-        if (ch == '|') ch = '\0';  // main.cu:538-541 turns every '|' of globalAcc into NUL
-    s->data.append(acc);
-    s->data.push_back('\0');       // the record's own '|' separator (main.cu:505,517)
+// A record is built in place at the tail of s->data (no per-record temporary):
+// `rec_begin` is where the open record starts.  data has room for the whole file
+// plus one separator per record (a record needs at least a header line, i.e. two
+// bytes of input that are not copied, for the one byte it adds).
+inline void put(kc_seqset* s, const char* p, size_t n) {
+    memcpy(s->data + s->data_len, p, n);
+    s->data_len += n;
+}
+
+void close_record(kc_seqset* s, size_t rec_begin) {
+    s->offsets.push_back((int64_t)rec_begin);
+    // main.cu:538-541 turns every '|' of globalAcc into NUL
+    char* p = s->data + rec_begin;
+    char* const end = s->data + s->data_len;
+    while ((p = (char*)memchr(p, '|', (size_t)(end - p))) != nullptr) *p++ = '\0';
+    s->data[s->data_len++] = '\0';  // the record's own '|' separator (main.cu:505,517)
     s->num_seqs++;
-    acc.clear();
 }
 
 int parse_fasta(const char* img, size_t n, int mode, long max_seqs, kc_seqset* s) {
@@ -308,7 +322,9 @@ int parse_fasta(const char* img, size_t n, int mode, long max_seqs, kc_seqset* s
     const char* line;
     size_t len;
     bool armed = false, stop = false;
-    std::string acc;
+    s->data_cap = n + 16;
+    s->data = (char*)malloc(s->data_cap);
+    if (!s->data) return kc_set_error(nullptr, KC_ERR_NOMEM, "kc_import_seqs: cannot allocate %zu bytes", s->data_cap);
     while (!stop && rd.next(line, len)) {
         if (len == 0) continue;  // blank line between records
         if (line[0] == '>') {
@@ -318,25 +334,26 @@ int parse_fasta(const char* img, size_t n, int mode, long max_seqs, kc_seqset* s
         }
         if (!armed) continue;  // sequence text without a header is dropped
         armed = false;
-        acc.assign(line, len);
+        const size_t rec_begin = s->data_len;
+        put(s, line, len);
         bool closed = false;
         while (rd.next(line, len)) {
             const bool header = (mode == KC_IMPORT_NONL && len > 0 && line[0] == '>');
             if (header) armed = true;  // NoNL: the header ends the record but is not kept
             if (len == 0 || line[0] == '\r' || header) {
-                close_record(s, acc);
+                close_record(s, rec_begin);
                 closed = true;
                 break;
             }
-            acc.append(line, len);
+            put(s, line, len);
             if (max_seqs > 0 && (long)s->num_seqs >= max_seqs) break;
         }
-        if (!closed && !acc.empty()) {
-            close_record(s, acc);
+        if (!closed && s->data_len > rec_begin) {
+            close_record(s, rec_begin);
             if (max_seqs > 0 && (long)s->num_seqs >= max_seqs) stop = true;
         }
     }
-    s->offsets.push_back((int64_t)s->data.size());  // terminal offset, always
+    s->offsets.push_back((int64_t)s->data_len);  // terminal offset, always
     return KC_OK;
 }
 }  // namespace
@@ -348,7 +365,11 @@ int kc_import_seqs_mem(const char* fasta, size_t nbytes, int mode, long max_seqs
     if (mode != KC_IMPORT_BLANKLINE && mode != KC_IMPORT_NONL)
         return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs: unknown mode %d", mode);
     kc_seqset* s = new kc_seqset();
-    parse_fasta(fasta, nbytes, mode, max_seqs, s);
+    const int rc = parse_fasta(fasta, nbytes, mode, max_seqs, s);
+    if (rc) {
+        delete s;
+        return rc;
+    }
     *out = s;
     return KC_OK;
 }
@@ -359,6 +380,19 @@ int kc_import_seqs(const char* path, int mode, long max_seqs, kc_seqset** out) {
     FILE* f = fopen(path, "rb");
     // the reference prints "Error opening" and exit(0)s here (main.cu:477-480)
     if (!f) return kc_set_error(nullptr, KC_ERR_IO, "Error opening: %s . Check your file or path.", path);
+    // map the file when it has a size (no copy of the input); otherwise read it
+    struct stat stt;
+    const int fd = fileno(f);
+    if (fstat(fd, &stt) == 0 && S_ISREG(stt.st_mode) && stt.st_size > 0) {
+        void* m = mmap(nullptr, (size_t)stt.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, (size_t)stt.st_size, MADV_SEQUENTIAL);
+            const int rc = kc_import_seqs_mem((const char*)m, (size_t)stt.st_size, mode, max_seqs, out);
+            munmap(m, (size_t)stt.st_size);
+            fclose(f);
+            return rc;
+        }
+    }
     std::string img;
     char buf[1 << 16];
     size_t got;
@@ -378,8 +412,8 @@ void kc_seqset_free(kc_seqset* s) {
 }
 uint32_t kc_seqset_num_seqs(const kc_seqset* s) { return s ? s->num_seqs : 0; }
 uint32_t kc_seqset_num_ids(const kc_seqset* s) { return s ? (uint32_t)s->ids.size() : 0; }
-uint64_t kc_seqset_nbytes(const kc_seqset* s) { return s ? s->data.size() : 0; }
-const char* kc_seqset_data(const kc_seqset* s) { return s ? s->data.data() : nullptr; }
+uint64_t kc_seqset_nbytes(const kc_seqset* s) { return s ? s->data_len : 0; }
+const char* kc_seqset_data(const kc_seqset* s) { return s ? s->data : nullptr; }
 const int64_t* kc_seqset_offsets(const kc_seqset* s) { return s ? s->offsets.data() : nullptr; }
 const char* kc_seqset_id(const kc_seqset* s, uint32_t i) {
     return (s && i < s->ids.size()) ? s->ids[i].c_str() : nullptr;
@@ -390,9 +424,9 @@ int kc_seqset_to_device(kc_ctx* ctx, kc_seqset* s, const char** d_data, const in
     DeviceGuard dg(ctx->device);
     if (!s->d_data) {
         s->owner = ctx;
-        KC_CUDA(ctx, cudaMalloc(&s->d_data, s->data.size() ? s->data.size() : 1));
+        KC_CUDA(ctx, cudaMalloc(&s->d_data, s->data_len ? s->data_len : 1));
         KC_CUDA(ctx, cudaMalloc(&s->d_offsets, s->offsets.size() * sizeof(int64_t)));
-        KC_CUDA(ctx, cudaMemcpyAsync(s->d_data, s->data.data(), s->data.size(), cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(ctx, cudaMemcpyAsync(s->d_data, s->data, s->data_len, cudaMemcpyHostToDevice, ctx->stream));
         KC_CUDA(ctx, cudaMemcpyAsync(s->d_offsets, s->offsets.data(), s->offsets.size() * sizeof(int64_t),
                                      cudaMemcpyHostToDevice, ctx->stream));
         KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
