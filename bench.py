@@ -136,6 +136,15 @@ def run_reference(args):
     th = [threading.Thread(target=gen, args=(i,)) for i in range(cores)]
     [t.start() for t in th]
     [t.join() for t in th]
+    # keep the whole run within a few minutes whatever the host: one calibration pass on the
+    # full sample, then shrink the per-step sample if (steps + warmup) of them would not fit
+    t0 = time.perf_counter()
+    O.count_dense(buf, k, threads=cores)
+    t1 = time.perf_counter() - t0
+    budget = args.ref_budget_s
+    if t1 * (args.steps + args.warmup) > budget:
+        sample = max(1 << 26, int(sample * budget / (t1 * (args.steps + args.warmup))))
+        buf = buf[:sample]
     for _ in range(args.warmup):
         O.count_dense(buf, k, threads=cores)
     t0 = time.perf_counter()
@@ -230,10 +239,8 @@ def run_sparse(args):
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(ctx.launch_count - launches0),
         }
         emit(line)
-    arm_exit_watchdog()
+    leave(world)
     sp.close()
-    if world > 1:
-        dist.destroy_process_group()
     ctx.close()
     return 0
 
@@ -257,9 +264,17 @@ def emit(line):
     out.flush()
 
 
-def arm_exit_watchdog(seconds=45):
-    """The result line is out; if library teardown (NCCL, CUDA graphs) stalls, leave anyway."""
-    t = threading.Timer(seconds, lambda: os._exit(0))
+def leave(world):
+    """The result line is out and every collective of the run has completed.  With
+    world > 1 the process leaves WITHOUT library teardown: destroying the process group /
+    a captured graph after the N=8 run stalled for the whole time limit once (round 1,
+    gpurun call 35) and nothing after the JSON line is worth that.  N=1 tears down normally,
+    with a timer as a backstop."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+    t = threading.Timer(45, lambda: os._exit(0))
     t.daemon = True
     t.start()
 
@@ -278,6 +293,8 @@ def main():
     ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="bases of the CPU-baseline sample")
     ap.add_argument("--ref-sample", type=int, default=1 << 30, help="bases per step of the reference arm")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="reference arm: shrink the per-step sample so that steps+warmup fit this many seconds")
     ap.add_argument("--reduce-slices", type=int, default=1,
                     help="N>1: count the shard in S slices and overlap each slice's NCCL reduce with the next count "
                          "(measured slower than S=1 at N=2: 2.24 / 2.57 / 3.35 ms for S=1/2/4)")
@@ -512,10 +529,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)
-    arm_exit_watchdog()
+    leave(world)
     graph = None
-    if world > 1:
-        dist.destroy_process_group()
     ctx.close()
     return 0
 
