@@ -10,12 +10,23 @@
 // (main.cu:641-644, kernels.h:133-140); code is little-endian in the string,
 // idx = sum code(s[p]) * 4^p (utils.h:30-47, main.cu:134-135).
 #pragma once
+#ifndef KC_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
 
 #include "../../include/kmer_b200.h"
+
+// Kernel launch and dynamic shared memory go through two macros so that the same sources
+// also build against the test-only CPU emulator (tests/emu/simt_emu.h, -DKC_EMU), which
+// runs the kernels' logic against the oracle where there is no GPU.  `kern` must be a plain
+// identifier (take `auto kern = some_kernel<...>;` first when the name has commas).
+#ifndef KC_EMU
+#define KC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define KC_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
 
 struct kc_ctx {
     int device = 0;
@@ -136,6 +147,11 @@ __device__ __forceinline__ Decoded16 kc_decode16(uint4 v) {
     return d;
 }
 
+// ---- memory primitives as inline PTX (32-bit shared addresses).  Keeps ptxas from wrapping
+// atomicAdd in its warp-aggregation sequence and pins the program order the staging
+// protocols rely on.  Under KC_EMU (tests/emu) the same operations are plain C++ with a
+// possible fiber switch in front of each, so the protocols meet adversarial interleavings.
+#ifndef KC_EMU
 __device__ __forceinline__ uint4 kc_ldg_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -143,17 +159,79 @@ __device__ __forceinline__ uint4 kc_ldg_stream(const uint4* p) {
                  : "l"(p));
     return r;
 }
-
-// Same load, but INTO the registers of `r` ("+r": the asm formally reads them, so the
-// register allocator must reuse them and cannot hoist the load above the last use of
-// the old value).  This is what makes a register prefetch ring rotate without MOVs:
-// with a plain "=r" load ptxas hoists the LDG, has to pick a spare destination and
-// copies it back at the loop edge — a copy that waits for the load.
-__device__ __forceinline__ void kc_ldg_stream_into(uint4& r, const uint4* p) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
-                 : "l"(p));
+// coherent (L2) 128-bit load: for scratch a kernel wrote earlier in the same launch
+__device__ __forceinline__ uint4 kc_ldg_cg(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
 }
+__device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void smem_st64(uint32_t saddr, uint64_t v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_ld(uint32_t saddr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+// plain RED (no compiler warp-aggregation wrapper around it)
+__device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// x >> 31 of a value known to be < 2^31, i.e. a zero the compiler cannot see through:
+// OR-ing it into a register copy pins the copy behind the producer of x.
+__device__ __forceinline__ uint32_t kc_opaque_zero(uint32_t x) {
+    uint32_t z;
+    asm volatile("shr.u32 %0, %1, 31;" : "=r"(z) : "r"(x) : "memory");
+    return z;
+}
+#else
+static inline uint4 kc_ldg_stream(const uint4* p) { return *p; }
+static inline uint4 kc_ldg_cg(const uint4* p) { return *p; }
+static inline uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
+    emu::maybe_preempt();
+    uint32_t* p = (uint32_t*)emu::smem_ptr(saddr, 4);
+    const uint32_t old = *p;
+    *p = old + v;
+    return old;
+}
+static inline void smem_st(uint32_t saddr, uint32_t v) {
+    emu::maybe_preempt();
+    *(uint32_t*)emu::smem_ptr(saddr, 4) = v;
+}
+static inline void smem_st64(uint32_t saddr, uint64_t v) {
+    emu::maybe_preempt();
+    *(uint64_t*)emu::smem_ptr(saddr, 8) = v;
+}
+static inline uint32_t smem_ld(uint32_t saddr) {
+    emu::maybe_preempt();
+    return *(uint32_t*)emu::smem_ptr(saddr, 4);
+}
+static inline uint4 smem_ld128(uint32_t saddr) {
+    emu::maybe_preempt();
+    return *(uint4*)emu::smem_ptr(saddr, 16);
+}
+static inline void global_red_add(uint32_t* p, uint32_t v) {
+    emu::maybe_preempt();
+    *p += v;
+}
+static inline uint32_t kc_opaque_zero(uint32_t x) { return x >> 31; }
+#endif
 
 // bit j of result set <=> any of bad bits j .. j+k-1 set (k in 1..32)
 __device__ __forceinline__ uint64_t kc_window_bad(uint64_t B, int k) {

@@ -21,27 +21,6 @@
 
 #include "common.cuh"
 
-// ---- shared-memory / global primitives as inline PTX (32-bit shared addresses): keeps
-// ptxas from wrapping atomicAdd in its warp-aggregation sequence and pins the program
-// order the staging protocols below rely on.
-__device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
-    uint32_t r;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
-    return r;
-}
-__device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
-    return r;
-}
-// plain RED (no compiler warp-aggregation wrapper around it)
-__device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
-    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // ---------------------------------------------------------------------------
 // direct kernels
 // ---------------------------------------------------------------------------
@@ -49,7 +28,7 @@ enum { BINS_SMEM = 0, BINS_GLOBAL = 1 };
 
 template <int MODE>
 __global__ void __launch_bounds__(256) dense_direct_kernel(ScanGeom g, uint32_t* __restrict__ table) {
-    extern __shared__ uint32_t s_bins[];
+    KC_DYN_SMEM(uint32_t, s_bins);
     const int k = g.k;
     const uint32_t nbins = (k >= 16) ? 0u : (1u << (2 * k));  // only the smem mode (k <= 7) uses it
     const uint32_t kmask = (k >= 16) ? 0xFFFFFFFFu : (nbins - 1u);
@@ -106,7 +85,7 @@ __global__ void __launch_bounds__(1024, 1)
 dense_smem16_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* __restrict__ table,
                     uint32_t* __restrict__ partials) {
     static_assert(DEPTH == 2, "the barrier period (2 steps = 32768 adds) is the unroll factor");
-    extern __shared__ uint32_t words[];  // 32768
+    KC_DYN_SMEM(uint32_t, words);  // 32768
     const uint32_t s_words = (uint32_t)__cvta_generic_to_shared(words);
     const int tid = threadIdx.x, lane = tid & 31;
     {
@@ -165,8 +144,7 @@ dense_smem16_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
                 }
                 cur16 = nxt;
             }
-            uint32_t zero;
-            asm volatile("shr.u32 %0, %1, 31;" : "=r"(zero) : "r"(cur16.bad) : "memory");  // bad < 2^16: pins the copies here
+            const uint32_t zero = kc_opaque_zero(cur16.bad);  // bad < 2^16: pins the copies here
 #pragma unroll
             for (int q = 0; q < DEPTH; q++) {
                 raw[q].x = fresh[q].x | zero;
@@ -279,7 +257,7 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
                     uint32_t* __restrict__ slabs, uint32_t* __restrict__ counts, uint32_t region_cap) {
     static_assert(C::CAP % 8 == 0, "chunks are moved 128 bits at a time, in two halves");
     constexpr int NW = THREADS / 32;
-    extern __shared__ uint32_t smem[];
+    KC_DYN_SMEM(uint32_t, smem);
     const uint32_t s_state = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t s_cur = s_state + C::P * 4;
     const uint32_t s_buf = s_state + 2 * C::P * 4;
@@ -396,8 +374,7 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
             // copies to just behind the last read of raw[q] (and stall there on the
             // load); OR-ing in a zero it cannot see through, produced after the last
             // shared-memory operation of the iteration, pins them here.
-            uint32_t zero;
-            asm volatile("shr.u32 %0, %1, 31;" : "=r"(zero) : "r"(d) : "memory");  // d in [0, A)
+            const uint32_t zero = kc_opaque_zero((uint32_t)d);  // d in [0, A)
 #pragma unroll
             for (int q = 0; q < DEPTH; q++) {
                 raw[q].x = fresh[q].x | zero;
@@ -435,7 +412,7 @@ __global__ void __launch_bounds__(1024, (C::NBINS * 4 <= 100 * 1024) ? 2 : 1)
 part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slabs,
                   const uint32_t* __restrict__ counts, uint32_t region_cap, uint32_t nregions,
                   uint32_t* __restrict__ work_counter) {
-    extern __shared__ uint32_t bins[];
+    KC_DYN_SMEM(uint32_t, bins);
     __shared__ uint32_t s_part;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -522,9 +499,9 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
         if (smem > 48 * 1024)
             KC_CUDA(ctx, cudaFuncSetAttribute(dense_direct_kernel<BINS_SMEM>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense_direct_kernel<BINS_SMEM><<<grid, 256, smem, st>>>(g, d_table);
+        KC_LAUNCH(dense_direct_kernel<BINS_SMEM>, grid, 256, smem, st, g, d_table);
     } else {
-        dense_direct_kernel<BINS_GLOBAL><<<grid, 256, 0, st>>>(g, d_table);
+        KC_LAUNCH(dense_direct_kernel<BINS_GLOBAL>, grid, 256, 0, st, g, d_table);
     }
     KC_LAUNCH_CHECK(ctx, "dense_direct_kernel");
     if (ctx->timing) {
@@ -592,7 +569,7 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     do {                                                                                                    \
         auto kern = part_scatter_kernel<C, S::THREADS, S::MINB, S::DEPTH, ABL>;                   \
         KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));  \
-        kern<<<grid1, S::THREADS, smem1, st>>>(base, ngroups, d_table, slabs, counts, (uint32_t)cap);       \
+        KC_LAUNCH(kern, grid1, S::THREADS, smem1, st, base, ngroups, d_table, slabs, counts, (uint32_t)cap);       \
     } while (0)
     if (ablate == 1)
         KC_LAUNCH_SCATTER(1);
@@ -606,7 +583,7 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int ctas2 = (smem2 + 1024) * 2 <= ctx->smem_optin + 1024 && smem2 <= 100 * 1024 ? 2 : 1;
     int grid2 = ctx->sm_count * ctas2 < C::P ? ctx->sm_count * ctas2 : C::P;
-    part_count_kernel<C><<<grid2, 1024, smem2, st>>>(d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
+    KC_LAUNCH(part_count_kernel<C>, grid2, 1024, smem2, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
     KC_LAUNCH_CHECK(ctx, "part_count_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
     // the windows before and after the interior
@@ -642,10 +619,10 @@ static int dense_smem16(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64
     const size_t smem = 32768 * sizeof(uint32_t);
     KC_CUDA(ctx, cudaFuncSetAttribute(dense_smem16_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
-    dense_smem16_kernel<DEPTH><<<grid, 1024, smem, st>>>(g.abase + (G0 << 5), ngroups, d_table, partials);
+    KC_LAUNCH(dense_smem16_kernel<DEPTH>, grid, 1024, smem, st, g.abase + (G0 << 5), ngroups, d_table, partials);
     KC_LAUNCH_CHECK(ctx, "dense_smem16_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
-    smem16_reduce_kernel<<<32768 / 256, 256, 0, st>>>(partials, grid, d_table);
+    KC_LAUNCH(smem16_reduce_kernel, 32768 / 256, 256, 0, st, partials, grid, d_table);
     KC_LAUNCH_CHECK(ctx, "smem16_reduce_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
     const bool timing = ctx->timing;

@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t ps_seq_of(const int64_t* __restrict__ off, u
 __global__ void __launch_bounds__(256)
 perseq_kernel(const char* __restrict__ data, const int64_t* __restrict__ off, uint32_t num_seqs, int k,
               int32_t* __restrict__ sums, int use_smem) {
-    extern __shared__ uint32_t s_bins[];
+    KC_DYN_SMEM(uint32_t, s_bins);
     const uint32_t nbins = (k >= 16) ? 0u : (1u << (2 * k));  // smem mode (k <= 6) only
     const uint32_t kmask = (k >= 16) ? 0xFFFFFFFFu : (nbins - 1u);
     const int warp = threadIdx.x >> 5;
@@ -107,7 +107,7 @@ extern "C" int kc_count_per_seq_async(kc_ctx* ctx, const char* d_data, const int
     const int use_smem = k <= PS_SMEM_MAX_K;
     const size_t smem = use_smem ? (sizeof(uint32_t) << (2 * k)) : 0;
     const int grid = ctx->sm_count * 4;
-    perseq_kernel<<<grid, 256, smem, st>>>(d_data, d_offsets, num_seqs, k, d_sums, use_smem);
+    KC_LAUNCH(perseq_kernel, grid, 256, smem, st, d_data, d_offsets, num_seqs, k, d_sums, use_smem);
     KC_LAUNCH_CHECK(ctx, "perseq_kernel");
     return KC_OK;
 }
@@ -170,7 +170,7 @@ extern "C" int kc_kmer_distance(kc_ctx* ctx, const int32_t* d_sums, const int64_
     if (num_seqs > 65535) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "distance step supports up to 65535 sequences");
     DeviceGuard dg(ctx->device);
     dim3 grid((num_seqs - 1 + 255) / 256, num_seqs - 1);
-    distance_kernel<<<grid, 256, 0, ctx->stream>>>(d_sums, d_offsets, num_seqs, k, d_dist);
+    KC_LAUNCH(distance_kernel, grid, 256, 0, ctx->stream, d_sums, d_offsets, num_seqs, k, d_dist);
     KC_LAUNCH_CHECK(ctx, "distance_kernel");
     KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KC_OK;

@@ -13,7 +13,11 @@
 //                   second sort + reduce-by-key.
 //
 // Result in both cases: distinct codes ascending + counts (kc_sparse).
+#ifndef KC_EMU
 #include <cub/cub.cuh>
+#else
+#include "../../tests/emu/cub_emu.h"  // test-only CPU emulator build
+#endif
 
 #include "common.cuh"
 
@@ -268,7 +272,7 @@ int run_hash(kc_ctx* ctx, const ScanGeom& g, uint64_t capacity, DevBuf& okeys, D
                             (unsigned long long)capacity);
     }
     KC_CUDA(ctx, cudaMemsetAsync(ctl.p, 0, 64, st));
-    hash_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(slots.as<HashSlot>(), capacity);
+    KC_LAUNCH(hash_init_kernel, ctx->sm_count * 8, 256, 0, st, slots.as<HashSlot>(), capacity);
     KC_LAUNCH_CHECK(ctx, "hash_init_kernel");
     HashTable t;
     t.slots = slots.as<HashSlot>();
@@ -278,7 +282,7 @@ int run_hash(kc_ctx* ctx, const ScanGeom& g, uint64_t capacity, DevBuf& okeys, D
     t.max_distinct = capacity - capacity / 4;  // load factor <= 0.75
     const uint64_t ngroups = g.g_end - g.g_begin;
     if (ngroups) {
-        sparse_hash_kernel<HALO><<<grid_for(ctx, ngroups), 256, 0, st>>>(g, t);
+        KC_LAUNCH(sparse_hash_kernel<HALO>, grid_for(ctx, ngroups), 256, 0, st, g, t);
         KC_LAUNCH_CHECK(ctx, "sparse_hash_kernel");
     }
     unsigned long long h[2] = {0, 0};
@@ -292,7 +296,7 @@ int run_hash(kc_ctx* ctx, const ScanGeom& g, uint64_t capacity, DevBuf& okeys, D
         return kc_set_error(ctx, KC_ERR_NOMEM, "out of device memory compacting %llu k-mers", h[0]);
     }
     unsigned long long* cursor = ctl.as<unsigned long long>() + 2;
-    hash_compact_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(t.slots, capacity, okeys.as<uint64_t>(),
+    KC_LAUNCH(hash_compact_kernel, ctx->sm_count * 8, 256, 0, st, t.slots, capacity, okeys.as<uint64_t>(),
                                                            ocounts.as<uint32_t>(), cursor);
     KC_LAUNCH_CHECK(ctx, "hash_compact_kernel");
     KC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -374,9 +378,9 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         }
         const uint64_t ngroups = g.g_end - g.g_begin;
         if (halo == 1)
-            sparse_codes_kernel<1><<<grid_for(ctx, ngroups), 256, 0, st>>>(g, codes.as<uint64_t>());
+            KC_LAUNCH(sparse_codes_kernel<1>, grid_for(ctx, ngroups), 256, 0, st, g, codes.as<uint64_t>());
         else
-            sparse_codes_kernel<2><<<grid_for(ctx, ngroups), 256, 0, st>>>(g, codes.as<uint64_t>());
+            KC_LAUNCH(sparse_codes_kernel<2>, grid_for(ctx, ngroups), 256, 0, st, g, codes.as<uint64_t>());
         KC_LAUNCH_CHECK(ctx, "sparse_codes_kernel");
         size_t t1 = 0, t2 = 0;
         const int sort_bits = 2 * k + 1;  // codes + the invalid marker at bit 2k
@@ -393,7 +397,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         KC_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(tmp.p, tb, sorted.as<uint64_t>(), uniq.as<uint64_t>(), cnts.as<uint32_t>(),
                                                         ctl.as<unsigned long long>(), (int)m, st));
         ctx->launches += 8;
-        count_valid_runs_kernel<<<1, 1, 0, st>>>(uniq.as<uint64_t>(), ctl.as<unsigned long long>(), ctl.as<unsigned long long>() + 1, 1ull << (2 * k));
+        KC_LAUNCH(count_valid_runs_kernel, 1, 1, 0, st, uniq.as<uint64_t>(), ctl.as<unsigned long long>(), ctl.as<unsigned long long>() + 1, 1ull << (2 * k));
         KC_LAUNCH_CHECK(ctx, "count_valid_runs_kernel");
         unsigned long long h[2];
         KC_CUDA(ctx, cudaMemcpyAsync(h, ctl.p, 16, cudaMemcpyDeviceToHost, st));
@@ -488,7 +492,7 @@ int kc_sparse_bucket_by_owner(kc_ctx* ctx, const uint64_t* d_keys, const uint32_
     unsigned long long* cursor = hist + num_owners;
     KC_CUDA(ctx, cudaMemsetAsync(hist, 0, 8 * (size_t)num_owners, st));
     const int grid = ctx->sm_count * 8;
-    owner_hist_kernel<<<grid, 256, 0, st>>>(d_keys, n, num_owners, hist);
+    KC_LAUNCH(owner_hist_kernel, grid, 256, 0, st, d_keys, n, num_owners, hist);
     KC_LAUNCH_CHECK(ctx, "owner_hist_kernel");
     std::vector<unsigned long long> h(num_owners), c(num_owners);
     KC_CUDA(ctx, cudaMemcpyAsync(h.data(), hist, 8 * (size_t)num_owners, cudaMemcpyDeviceToHost, st));
@@ -500,7 +504,7 @@ int kc_sparse_bucket_by_owner(kc_ctx* ctx, const uint64_t* d_keys, const uint32_
         h_bucket_sizes[i] = h[i];
     }
     KC_CUDA(ctx, cudaMemcpyAsync(cursor, c.data(), 8 * (size_t)num_owners, cudaMemcpyHostToDevice, st));
-    owner_scatter_kernel<<<grid, 256, 0, st>>>(d_keys, d_counts, n, num_owners, cursor, d_keys_out, d_counts_out);
+    KC_LAUNCH(owner_scatter_kernel, grid, 256, 0, st, d_keys, d_counts, n, num_owners, cursor, d_keys_out, d_counts_out);
     KC_LAUNCH_CHECK(ctx, "owner_scatter_kernel");
     KC_CUDA(ctx, cudaStreamSynchronize(st));
     return KC_OK;

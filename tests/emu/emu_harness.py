@@ -1,0 +1,199 @@
+"""ctypes access to libkmerb200_emu.so — the product's kernels compiled for the CPU against the
+test-only SIMT emulator (tests/emu/simt_emu.h).  TEST INFRASTRUCTURE ONLY: it checks kernel
+LOGIC against the oracle where there is no GPU; it is never the thing measured or shipped.
+
+The emulator reads KC_EMU_SEED (0 = deterministic round-robin, != 0 = random fiber
+scheduling with preemption inside shared-memory/atomic helpers) and KC_EMU_SMS once per
+process, so tests that want several seeds run this module as a subprocess:
+
+    python tests/emu/emu_harness.py <case> [args...]      (see main() below)
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB_PATH = os.path.join(HERE, "_build", "libkmerb200_emu.so")
+_LIB = None
+
+KC_DENSE_AUTO, KC_DENSE_DIRECT, KC_DENSE_PARTITION = 0, 1, 2
+KC_SPARSE_HASH, KC_SPARSE_SORT, KC_SPARSE_RADIX = 0, 1, 2
+KC_SPARSE_UNSORTED = 0x100
+
+
+def build():
+    subprocess.run(["make", "-s", "-j8", "-C", HERE], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.kc_last_error.restype = C.c_char_p
+        L.kc_last_error.argtypes = [C.c_void_p]
+        L.kc_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.kc_ctx_destroy.argtypes = [C.c_void_p]
+        L.kc_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.kc_device_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.kc_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.kc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.kc_memset_d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
+        L.kc_count_dense_range_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                                 C.c_void_p, C.c_int, C.c_void_p]
+        L.kc_count_per_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.kc_count_sparse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64,
+                                      C.POINTER(C.c_void_p)]
+        L.kc_sparse_free.argtypes = [C.c_void_p]
+        L.kc_sparse_size.restype = C.c_uint64
+        L.kc_sparse_size.argtypes = [C.c_void_p]
+        L.kc_sparse_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kc_gen_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
+                                    C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kc_gen_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
+                                   C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+class EmuContext:
+    def __init__(self):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.kc_ctx_create(0, C.byref(h))
+        assert rc == 0, self.L.kc_last_error(None)
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("emu rc=%d: %s" % (rc, self.L.kc_last_error(self.h).decode()))
+
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.L.kc_device_alloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def free(self, p):
+        self.L.kc_device_free(self.h, p)
+
+    def upload(self, arr, offset=0):
+        """device copy of a numpy array, placed `offset` bytes into its allocation"""
+        a = np.ascontiguousarray(arr)
+        base = self.alloc(a.nbytes + offset)
+        p = C.c_void_p(base.value + offset)
+        if a.nbytes:
+            self.check(self.L.kc_memcpy_h2d(self.h, p, a.ctypes.data, a.nbytes))
+        return base, p
+
+    def download(self, p, nbytes, dtype):
+        out = np.empty(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        if nbytes:
+            self.check(self.L.kc_memcpy_d2h(self.h, out.ctypes.data, p, nbytes))
+        return out
+
+    def count_dense_range(self, data, k, wb=None, we=None, algo=KC_DENSE_AUTO, offset=0):
+        a = np.ascontiguousarray(data, dtype=np.uint8)
+        n = a.size
+        nwin = max(0, n - k + 1)
+        wb = 0 if wb is None else wb
+        we = nwin if we is None else we
+        base, p = self.upload(a, offset)
+        nb = 4 << (2 * k)
+        t = self.alloc(nb)
+        self.check(self.L.kc_memset_d(self.h, t, 0, nb))
+        self.check(self.L.kc_count_dense_range_async(self.h, p, n, wb, we, k, t, algo, None))
+        out = self.download(t, nb, np.uint32)
+        self.free(t)
+        self.free(base)
+        return out
+
+    def count_sparse(self, data, k, algo, hint=0, offset=0):
+        a = np.ascontiguousarray(data, dtype=np.uint8)
+        base, p = self.upload(a, offset)
+        sp = C.c_void_p()
+        self.check(self.L.kc_count_sparse(self.h, p, a.size, k, algo, hint, C.byref(sp)))
+        n = int(self.L.kc_sparse_size(sp))
+        keys = np.empty(n, dtype=np.uint64)
+        counts = np.empty(n, dtype=np.uint32)
+        self.check(self.L.kc_sparse_copy_to_host(self.h, sp, keys.ctypes.data, counts.ctypes.data))
+        self.L.kc_sparse_free(sp)
+        self.free(base)
+        return keys, counts
+
+    def close(self):
+        self.L.kc_ctx_destroy(self.h)
+
+
+def _oracle():
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle as O
+    O.lib()
+    return O
+
+
+def make_input(kind, n, seed, k):
+    """Test inputs: 'genome' = the bench generator with N runs; 'dirty' = random bytes from a
+    small alphabet with separators, lower case and N; 'polyA' = one k-mer everywhere."""
+    O = _oracle()
+    if kind == "genome":
+        return O.gen_genome(seed, n, 3, 40, k, 0, n)
+    if kind == "polyA":
+        return np.full(n, ord("A"), dtype=np.uint8)
+    if kind == "skew":  # 90 % of the windows fall into a few partitions
+        rng = np.random.default_rng(seed)
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+        a = a.copy()
+        mask = rng.random(n) < 0.9
+        a[mask] = ord("C")
+        return a
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTACGTNacgt\n\0|>", dtype=np.uint8)
+    return alpha[rng.integers(0, alpha.size, n)]
+
+
+def case_dense(args):
+    k, n, algo, kind, seed, offset = int(args[0]), int(args[1]), int(args[2]), args[3], int(args[4]), int(args[5])
+    O = _oracle()
+    data = make_input(kind, n, seed, k)
+    ctx = EmuContext()
+    got = ctx.count_dense_range(data, k, algo=algo, offset=offset)
+    want, _ = O.count_dense(data, k)
+    assert (got == want).all(), "dense k=%d algo=%d %s n=%d: %d bins differ" % (k, algo, kind, n, int((got != want).sum()))
+    # a window sub-range too (the multi-GPU shard form)
+    wb, we = n // 3, n - n // 5
+    got = ctx.count_dense_range(data, k, wb, we, algo=algo, offset=offset)
+    want = O.count_dense_range(data, k, wb, we)
+    if isinstance(want, tuple):
+        want = want[0]
+    assert (got == want).all(), "dense range k=%d algo=%d: %d bins differ" % (k, algo, int((got != want).sum()))
+    ctx.close()
+    print("ok dense", *args)
+
+
+def case_sparse(args):
+    k, n, algo, kind, seed, offset = int(args[0]), int(args[1]), int(args[2]), args[3], int(args[4]), int(args[5])
+    O = _oracle()
+    if kind == "reads":
+        nreads = n // 101
+        data = O.gen_reads(seed, 5000, 100, 50, 0, nreads)
+    else:
+        data = make_input(kind, n, seed, k)
+    ctx = EmuContext()
+    keys, counts = ctx.count_sparse(data, k, algo, offset=offset)
+    wk, wc, _ = O.count_sparse(data, k)
+    assert keys.size == wk.size, "sparse k=%d algo=%d: %d distinct, oracle %d" % (k, algo, keys.size, wk.size)
+    assert (keys == wk).all() and (counts == wc).all(), "sparse k=%d algo=%d differs from the oracle" % (k, algo)
+    ctx.close()
+    print("ok sparse", *args, "distinct", keys.size)
+
+
+CASES = {"dense": case_dense, "sparse": case_sparse}
+
+if __name__ == "__main__":
+    CASES[sys.argv[1]](sys.argv[2:])

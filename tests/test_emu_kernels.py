@@ -1,0 +1,68 @@
+"""Kernel LOGIC on the CPU: the product's .cu sources compiled against the test-only SIMT
+emulator (tests/emu) and compared with the oracle.  Runs where there is no GPU, so every
+change to a kernel meets the oracle before it meets a B200; the `-m gpu` tests remain the
+parity tests proper.  Each case is a subprocess because the emulator reads its scheduling
+seed once per process (KC_EMU_SEED != 0: random fiber scheduling with preemption inside the
+shared-memory helpers, which is what exercises the barrier-free staging protocols)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "tests", "emu", "emu_harness.py")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "tests", "emu")], check=True)
+
+
+def run_case(*args, seed=0, sms=4, shift=3):
+    env = dict(os.environ, KC_EMU_SEED=str(seed), KC_EMU_SMS=str(sms), KC_EMU_PREEMPT_SHIFT=str(shift))
+    r = subprocess.run([sys.executable, HARNESS] + [str(a) for a in args], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+# (k, bytes, algo, input kind, data seed, misalignment of the device pointer)
+DENSE = [
+    (3, 100_000, 0, "dirty", 1, 3),
+    (7, 200_000, 0, "genome", 2, 0),
+    (8, 300_000, 1, "genome", 2, 9),
+    (8, 4_500_000, 0, "genome", 4, 0),   # 16-bit shared-memory bins + reduce
+    (8, 4_300_000, 0, "polyA", 4, 1),    # one bin takes every hit: the 0x4000 spill path
+    (12, 400_000, 2, "genome", 2, 0),    # partition path
+    (12, 400_000, 2, "dirty", 5, 7),
+    (12, 300_000, 2, "skew", 6, 2),      # region overflow -> RED fallback
+    (11, 300_000, 2, "genome", 7, 15),
+    (10, 300_000, 2, "dirty", 8, 4),
+    (9, 300_000, 2, "genome", 5, 1),
+    (13, 150_000, 0, "dirty", 3, 0),
+]
+
+
+@pytest.mark.parametrize("case", DENSE, ids=lambda c: "k%d-%s-a%d" % (c[0], c[3], c[2]))
+def test_dense_kernels_on_emulator(case):
+    run_case("dense", *case, seed=0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_partition_staging_protocol_random_schedules(seed):
+    # random interleavings of the 1024 threads of a CTA inside the staging protocol
+    run_case("dense", 12, 300_000, 2, "genome", 10 + seed, seed, seed=seed, sms=2)
+    run_case("dense", 12, 200_000, 2, "skew", 20 + seed, 0, seed=seed, sms=1, shift=1)
+
+
+SPARSE = [
+    (21, 60_000, 0, "reads", 1, 0),
+    (31, 60_000, 0, "dirty", 2, 5),
+    (15, 50_000, 1, "genome", 3, 0),
+]
+
+
+@pytest.mark.parametrize("case", SPARSE, ids=lambda c: "k%d-%s-a%d" % (c[0], c[3], c[2]))
+def test_sparse_kernels_on_emulator(case):
+    run_case("sparse", *case, seed=0)
