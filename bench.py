@@ -189,7 +189,8 @@ def run_sparse(args):
     data = ctx.gen_reads(w["seed"], w["genome"], rl, w["err_den"], r0, r1 - r0)
     nb = (r1 - r0) * (rl + 1)
     torch.cuda.synchronize()
-    algo = {"hash": kmerb200.SPARSE_HASH, "sort": kmerb200.SPARSE_SORT}[args.sparse_algo]
+    algo = {"hash": kmerb200.SPARSE_HASH, "sort": kmerb200.SPARSE_SORT,
+            "radix": kmerb200.SPARSE_RADIX | kmerb200.SPARSE_NO_FALLBACK}[args.sparse_algo]
     hint = args.capacity_hint
 
     def step():
@@ -287,7 +288,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(SPARSE_WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="sparse workloads: number of reads (0 = full scale)")
-    ap.add_argument("--sparse-algo", default="hash", choices=["hash", "sort"])
+    ap.add_argument("--sparse-algo", default="hash", choices=["hash", "sort", "radix"])
     ap.add_argument("--capacity-hint", type=int, default=0, help="sparse hash: expected distinct k-mers")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition")
     ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")

@@ -50,6 +50,17 @@ struct kc_ctx {
     int timed_kernels = 0;
 };
 
+// result of a sparse count: distinct codes ascending + their counts, both in device memory
+struct kc_sparse {
+    kc_ctx* ctx = nullptr;
+    uint64_t size = 0;
+    uint64_t* d_keys = nullptr;
+    uint32_t* d_counts = nullptr;
+};
+// sparse_radix.cu: MSD radix partition + shared-memory leaf sort; *failed = 1 means an
+// overflow made the result unusable and nothing was produced (the caller recounts)
+int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed);
+
 int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...);
 int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes);   // ctx->scratch  >= nbytes
 int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes);  // ctx->scratch2 >= nbytes
@@ -168,6 +179,16 @@ __device__ __forceinline__ uint4 kc_ldg_cg(const uint4* p) {
                  : "memory");
     return r;
 }
+__device__ __forceinline__ uint32_t kc_ld_cg(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint64_t kc_ld_cg(const uint64_t* p) {
+    uint64_t r;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
     uint32_t r;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
@@ -203,6 +224,8 @@ __device__ __forceinline__ uint32_t kc_opaque_zero(uint32_t x) {
 #else
 static inline uint4 kc_ldg_stream(const uint4* p) { return *p; }
 static inline uint4 kc_ldg_cg(const uint4* p) { return *p; }
+static inline uint32_t kc_ld_cg(const uint32_t* p) { return *p; }
+static inline uint64_t kc_ld_cg(const uint64_t* p) { return *p; }
 static inline uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
     emu::maybe_preempt();
     uint32_t* p = (uint32_t*)emu::smem_ptr(saddr, 4);

@@ -21,13 +21,6 @@
 
 #include "common.cuh"
 
-struct kc_sparse {
-    kc_ctx* ctx = nullptr;
-    uint64_t size = 0;
-    uint64_t* d_keys = nullptr;
-    uint32_t* d_counts = nullptr;
-};
-
 static constexpr uint64_t KEY_EMPTY = ~0ull;
 
 // ---------------------------------------------------------------------------
@@ -313,8 +306,10 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
     *out = nullptr;
     if (k < 1 || k > KC_MAX_K) return kc_set_error(ctx, KC_ERR_INVALID, "sparse k must be 1..%d, got %d", KC_MAX_K, k);
     const bool unsorted = (algo & KC_SPARSE_UNSORTED) != 0;
-    algo &= ~KC_SPARSE_UNSORTED;
-    if (algo != KC_SPARSE_HASH && algo != KC_SPARSE_SORT) return kc_set_error(ctx, KC_ERR_INVALID, "unknown sparse algo %d", algo);
+    const bool no_fallback = (algo & KC_SPARSE_NO_FALLBACK) != 0;
+    algo &= ~(KC_SPARSE_UNSORTED | KC_SPARSE_NO_FALLBACK);
+    if (algo != KC_SPARSE_HASH && algo != KC_SPARSE_SORT && algo != KC_SPARSE_RADIX)
+        return kc_set_error(ctx, KC_ERR_INVALID, "unknown sparse algo %d", algo);
     if (!d_data && nbytes) return kc_set_error(ctx, KC_ERR_INVALID, "null data");
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->stream;
@@ -326,6 +321,18 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         return KC_OK;
     }
     const int halo = (k <= 17) ? 1 : 2;
+
+    if (algo == KC_SPARSE_RADIX) {
+        int failed = 0;
+        const int rc = kc_sparse_radix(ctx, d_data, nbytes, k, out, &failed);
+        if (rc || !failed) return rc;
+        if (no_fallback)
+            return kc_set_error(ctx, KC_ERR_TABLE_FULL,
+                                "sparse radix overflowed (skewed input):%s%s%s%s", (failed & 1) ? " partition region" : "",
+                                (failed & 2) ? " staging bins" : "", (failed & 4) ? " leaf buffer" : "",
+                                (failed & 8) ? " run list" : "");
+        algo = KC_SPARSE_HASH;  // a region / leaf / run list overflowed (skewed input): recount exactly
+    }
 
     if (algo == KC_SPARSE_HASH) {
         const ScanGeom g = kc_make_geom(d_data, nbytes, 0, nwin, k);

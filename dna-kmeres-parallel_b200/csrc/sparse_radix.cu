@@ -1,0 +1,599 @@
+// sparse_radix.cu — KC_SPARSE_RADIX: sparse k-mer counting (13 <= k <= 31) as an MSD radix
+// partition whose leaves are sorted in shared memory.
+//
+// Why: the hash path (sparse.cu) does one random DRAM access per window into a multi-GB
+// table (config 4 at full scale: 13 G inserts, 1.77 s); the sort path pays 6+ device-wide
+// radix passes over 64-bit codes.  Here every global access is a coalesced stream:
+//
+//   K1 sp_scatter_kernel   scan ASCII -> 2k-bit LE code per valid window; partition by the top
+//                          KB1 bits of the code; the REMAINING bits (a 32- or 64-bit record)
+//                          are staged per partition in shared memory and leave the SM in
+//                          64-byte chunks into this CTA's private region of the partition.
+//   K2 sp_leaf_kernel      one level-1 partition per CTA at a time: (A) the same staged
+//                          scatter by the next KB2 bits into CTA-private scratch; (B) each
+//                          of the 2^KB2 leaves (a few thousand records) is sorted in shared
+//                          memory — counting sort on the top <=10 remaining bits, one
+//                          sub-bucket per thread finished by insertion sort — run-length
+//                          encoded, and its (code,count) runs appended to a temporary list.
+//   K3 sp_scan_kernel      exclusive scan of the leaves' distinct counts (leaf order = code order)
+//   K4 sp_gather_kernel    leaf runs -> final arrays.  The result is sorted by code because
+//                          partition, leaf, sub-bucket and in-bucket order all follow the
+//                          code's most significant bits: no device-wide sort anywhere.
+//
+// Exactness: a record is dropped only when a private region, a leaf buffer or the
+// temporary list overflows, or when both staging bins of a partition stay full for
+// SP_MAX_TRIES attempts; each of these raises the `failed` flag and the caller
+// (kc_count_sparse) then recounts with the hash path.  Uniform data never gets there;
+// heavily skewed data (poly-A) does, by design — see DESIGN.md.
+//
+// Window semantics are the reference's (main.cu:636-646): k consecutive bytes, counted iff
+// all are upper-case ACGT; code = sum code(s[p]) * 4^p (utils.h:30-47).
+#include "common.cuh"
+
+#ifdef KC_EMU
+#define KC_SPIN_PAUSE() emu::maybe_preempt_always()
+#else
+#define KC_SPIN_PAUSE() __nanosleep(32)
+#endif
+
+namespace {
+
+constexpr int SP_THREADS = 1024;
+constexpr int SP_MAX_TRIES = 256;
+// why a run gave up (bits of SpCtl::failed, reported in the error text)
+enum { SP_FAIL_REGION = 1, SP_FAIL_STAGING = 2, SP_FAIL_LEAF = 4, SP_FAIL_RUNLIST = 8 };
+
+// ---------------------------------------------------------------------------
+// Staged scatter of fixed-size records into P private regions (shared by K1 and K2).
+//
+// Shared memory: state[P][2] | cur[P] | buf[P][2][CAP].  Every partition has TWO bins of
+// CAP records (one 64-byte chunk each).  state word: low 24 bits = slots reserved, high 8
+// bits = slots written.
+//   writer : slot = atom.add(state, 1) & 0xFFFFFF
+//            slot <  CAP: store the record; w = atom.add(state, 1<<24) >> 24; the writer that
+//                         makes w == CAP-1 has seen every slot written and flushes the bin
+//                         by itself (4 x 128-bit shared loads, state = 0, 4 x 128-bit global
+//                         stores to cur[p], which it advances by CAP);
+//            slot >= CAP: the bin is full and its flush is in flight: take the partition's
+//                         other bin; if that one is full as well, pause and try again.
+// Shared-memory requests of one thread are performed in program order, so a writer's
+// store precedes its "written" increment, and the flusher's loads precede its reset —
+// the same protocol the dense partition path runs on the GPU (dense.cu), plus the second
+// bin, which replaces that path's "count it directly with global REDs" fallback (a
+// sparse result has no table to RED into).  Failed attempts inflate only the reserved
+// field (24 bits: SP_MAX_TRIES x 1024 threads cannot carry into the written field), and the
+// reset wipes them.
+// ---------------------------------------------------------------------------
+template <typename RecT, int P_>
+struct Stager {
+    static constexpr int P = P_;
+    static constexpr int CAP = 64 / (int)sizeof(RecT);  // records per 64-byte chunk
+    static constexpr size_t SMEM_BYTES = (size_t)P * 2 * 4 + (size_t)P * 4 + (size_t)P * 2 * 64;
+
+    uint32_t s_state, s_cur, s_buf;  // shared-window addresses
+    RecT* region;                    // this CTA's slab: region[p * cap + i]
+    uint32_t cap;                    // records per (CTA, partition) region; multiple of CAP
+    uint32_t* failed;
+
+    __device__ __forceinline__ void init(uint32_t* smem_words, RecT* region_, uint32_t cap_, uint32_t* failed_) {
+        s_state = (uint32_t)__cvta_generic_to_shared(smem_words);
+        s_cur = s_state + P * 2 * 4;
+        s_buf = s_cur + P * 4;
+        region = region_;
+        cap = cap_;
+        failed = failed_;
+        for (int b = threadIdx.x; b < P; b += blockDim.x) {
+            smem_words[2 * b] = 0;
+            smem_words[2 * b + 1] = 0;
+            smem_words[2 * P + b] = b * cap_;
+        }
+    }
+
+    __device__ __forceinline__ void flush_bin(uint32_t bin /* = 2*p + x */) {
+        const uint32_t src = s_buf + bin * 64;
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = smem_ld128(src + 16 * q);
+        smem_st(s_state + bin * 4, 0u);  // every slot has been read: the bin is free again
+        const uint32_t p = bin >> 1;
+        const uint32_t pos = smem_atom_add(s_cur + p * 4, (uint32_t)CAP);
+        if (pos + CAP <= (p + 1) * cap) {
+            uint4* dst = reinterpret_cast<uint4*>(region + pos);  // 64-byte aligned
+#pragma unroll
+            for (int q = 0; q < 4; q++) dst[q] = v[q];
+        } else {
+            atomicOr(failed, (uint32_t)SP_FAIL_REGION);  // region full (skewed input): the caller recounts with the hash path
+        }
+    }
+
+    __device__ __forceinline__ void stage(uint32_t p, RecT rec, uint32_t pref) {
+        uint32_t bin = 2 * p + (pref & 1u);
+        for (int tries = 0; tries < SP_MAX_TRIES; tries++) {
+            const uint32_t sa = s_state + bin * 4;
+            const uint32_t slot = smem_atom_add(sa, 1u) & 0xFFFFFFu;
+            if (slot < (uint32_t)CAP) {
+                if (sizeof(RecT) == 8)
+                    smem_st64(s_buf + bin * 64 + slot * 8, (uint64_t)rec);
+                else
+                    smem_st(s_buf + bin * 64 + slot * 4, (uint32_t)rec);
+                const uint32_t wr = smem_atom_add(sa, 1u << 24) >> 24;
+                if (wr == (uint32_t)CAP - 1) flush_bin(bin);
+                return;
+            }
+            bin ^= 1u;
+            if (tries & 1) KC_SPIN_PAUSE();  // both bins were full
+        }
+        atomicOr(failed, (uint32_t)SP_FAIL_STAGING);
+    }
+
+    // after a CTA barrier: write the partially filled bins and leave the region's record
+    // count in cur[p] (shared) — counts_out[p * stride + col] too when counts_out != nullptr
+    __device__ __forceinline__ void finish(uint32_t* smem_words, uint32_t* counts_out, uint32_t stride, uint32_t col) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const RecT* bufp = reinterpret_cast<const RecT*>(smem_words + 3 * P);
+        for (int p = warp; p < P; p += nw) {
+            const uint32_t base_off = p * cap;
+            uint32_t pos = smem_words[2 * P + p] - base_off;  // chunks written so far (may exceed cap after a failure)
+#pragma unroll
+            for (int x = 0; x < 2; x++) {
+                uint32_t c = smem_words[2 * p + x] & 0xFFFFFFu;  // < CAP: full bins were flushed by their last writer
+                if (c > (uint32_t)CAP) c = CAP;                  // (only after a give-up, which has raised `failed`)
+                if (c > 0 && pos <= cap) {
+                    if (pos + c <= cap) {
+                        if ((uint32_t)lane < c) region[base_off + pos + lane] = bufp[(2 * p + x) * CAP + lane];
+                    } else if (lane == 0) {
+                        atomicOr(failed, (uint32_t)SP_FAIL_REGION);
+                    }
+                }
+                pos += c;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t stored = pos < cap ? pos : cap;
+                smem_words[2 * P + p] = stored;
+                if (counts_out) counts_out[(uint64_t)p * stride + col] = stored;
+            }
+        }
+    }
+};
+
+template <int KB1_, int KB2_, int LEAF_CAP_>
+struct SpShape {
+    static constexpr int KB1 = KB1_, KB2 = KB2_;
+    static constexpr int P1 = 1 << KB1_, P2 = 1 << KB2_;
+    static constexpr int LEAF_CAP = LEAF_CAP_;  // records a leaf may hold (32-bit records; half for 64-bit)
+};
+
+struct SpCtl {  // one 64-byte control block in device memory
+    uint32_t work;               // K2 partition queue
+    uint32_t failed;             // any overflow: the result is invalid
+    unsigned long long out_cursor;  // entries appended to the temporary run list
+    unsigned long long total;       // K3: sum of the leaves' distinct counts
+    uint32_t pad[10];
+};
+
+// ---------------------------------------------------------------------------
+// K1: ASCII -> level-1 partitions
+// ---------------------------------------------------------------------------
+template <typename Shape, typename R1T, int HALO>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ counts1, uint32_t cap1, SpCtl* ctl) {
+    KC_DYN_SMEM(uint32_t, smem);
+    using St = Stager<R1T, Shape::P1>;
+    St st;
+    st.init(smem, slabs1 + (uint64_t)blockIdx.x * Shape::P1 * cap1, cap1, &ctl->failed);
+    __syncthreads();
+    const int k = g.k;
+    const int r1bits = 2 * k - Shape::KB1;
+    const uint64_t kmask = (1ull << (2 * k)) - 1ull;
+    const uint64_t r1mask = (1ull << r1bits) - 1ull;
+    const uint32_t pref = threadIdx.x >> 5;
+
+    const uint64_t ngroups = g.g_end - g.g_begin;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (SP_THREADS / 32);
+    const uint64_t gpw = (ngroups + nwarps - 1) / nwarps;
+    const uint64_t w = (uint64_t)blockIdx.x * (SP_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t gb = g.g_begin + min(w * gpw, ngroups);
+    const uint64_t ge = g.g_begin + min((w + 1) * gpw, ngroups);
+    kc_warp_scan<HALO>(g, gb, ge, [&](const LaneWindow<HALO>& lw, uint64_t) {
+        // a loop over the set bits, not 16 unrolled copies: the staging code is long and 16
+        // copies of it are 56 KB of SASS, more than the instruction cache holds
+        uint32_t m = lw.ok & 0xFFFFu;
+        while (m) {
+            const int j = __ffs((int)m) - 1;
+            m &= m - 1u;
+            const uint64_t code = lw.code64(j, kmask);
+            st.stage((uint32_t)(code >> r1bits), (R1T)(code & r1mask), pref + (uint32_t)j);
+        }
+    });
+    __syncthreads();
+    st.finish(smem, counts1, gridDim.x, blockIdx.x);
+}
+
+// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive
+// prefix, *total = sum.  `s_warp` = 33 words of shared memory.  Two barriers.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wv = s_warp[lane];
+        uint32_t winc = wv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        s_warp[lane] = winc - wv;  // exclusive prefix of the warp totals
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+
+// ---------------------------------------------------------------------------
+// K2: level-1 partition -> leaves -> sorted runs
+// ---------------------------------------------------------------------------
+template <typename Shape, typename R1T, typename R2T>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict__ counts1, uint32_t cap1,
+               uint32_t nregions, R2T* __restrict__ scratch2, uint32_t cap2, uint64_t* __restrict__ tmp_keys,
+               uint32_t* __restrict__ tmp_counts, uint64_t out_cap, unsigned long long* __restrict__ leaf_base,
+               uint32_t* __restrict__ leaf_n, SpCtl* ctl) {
+    KC_DYN_SMEM(uint32_t, smem);
+    __shared__ uint32_t s_part, s_np;
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[33];
+    using St = Stager<R2T, Shape::P2>;
+    constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
+    constexpr int PER_THREAD = LEAF_CAP / SP_THREADS;
+    static_assert(LEAF_CAP % SP_THREADS == 0, "leaf records are held in registers, PER_THREAD per thread");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r1bits = 2 * k - Shape::KB1;
+    const int r2bits = r1bits - Shape::KB2;  // >= 1 (host checks)
+    const int dbits = r2bits < 10 ? r2bits : 10;
+    const int lowbits = r2bits - dbits;
+    const uint32_t nb = 1u << dbits;  // sub-buckets of a leaf, one per thread
+    const uint64_t r2mask = (1ull << r2bits) - 1ull;
+    R2T* const my_scratch = scratch2 + (uint64_t)blockIdx.x * Shape::P2 * cap2;
+    // shared memory: the staging block (its cur[] holds the leaf record counts after
+    // Stager::finish), then hist/cursor[1024], then sorted[LEAF_CAP]
+    constexpr size_t STAGE_WORDS = St::SMEM_BYTES / 4;
+    uint32_t* const s_hist = smem + STAGE_WORDS;                    // 1024 words
+    R2T* const s_sorted = reinterpret_cast<R2T*>(smem + STAGE_WORDS + 1024);  // LEAF_CAP records
+
+    for (;;) {
+        __syncthreads();  // previous partition fully done (s_part, staging area, s_sorted reusable)
+        if (tid == 0) s_part = atomicAdd(&ctl->work, 1u);
+        St st;
+        st.init(smem, my_scratch, cap2, &ctl->failed);
+        // records of this partition (sum over the pass-1 CTAs' regions)
+        __syncthreads();
+        const uint32_t p1 = s_part;
+        if (p1 >= (uint32_t)Shape::P1) break;
+        {
+            uint32_t mine = 0;
+            for (uint32_t r = tid; r < nregions; r += SP_THREADS) mine += counts1[(uint64_t)p1 * nregions + r];
+            uint32_t tot;
+            block_excl_scan(mine, s_warp, &tot);
+            if (tid == 0) s_np = tot;
+        }
+        __syncthreads();
+        if (s_np == 0) {  // empty partition: its leaves keep leaf_n = 0 (zeroed by the host)
+            continue;
+        }
+
+        // ---- phase A: partition by the next KB2 bits ------------------------------------
+        for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
+            const uint32_t n = counts1[(uint64_t)p1 * nregions + reg];
+            const R1T* src = slabs1 + ((uint64_t)reg * Shape::P1 + p1) * cap1;
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint64_t r1 = (uint64_t)src[i];
+                // (the mask only matters after an overflow upstream left garbage in a region:
+                // the result is discarded then, but the kernel must stay in bounds)
+                st.stage((uint32_t)(r1 >> r2bits) & (Shape::P2 - 1), (R2T)(r1 & r2mask), (uint32_t)warp + i);
+            }
+        }
+        __syncthreads();
+        st.finish(smem, nullptr, 0, 0);
+        __syncthreads();  // cur[p2] = records of leaf p2; scratch writes of this CTA are visible to it
+
+        // ---- phase B: sort + run-length encode every leaf -------------------------------
+        for (uint32_t p2 = 0; p2 < (uint32_t)Shape::P2; p2++) {
+            const uint32_t n = smem[2 * Shape::P2 + p2];
+            if (n == 0) continue;  // CTA-uniform
+            if (n > (uint32_t)LEAF_CAP) {
+                if (tid == 0) atomicOr(&ctl->failed, (uint32_t)SP_FAIL_LEAF);
+                continue;
+            }
+            const R2T* leaf = my_scratch + (uint64_t)p2 * cap2;
+            R2T rec[PER_THREAD] = {};
+            if ((uint32_t)tid < nb) s_hist[tid] = 0;
+#pragma unroll
+            for (int q = 0; q < PER_THREAD; q++) {
+                const uint32_t i = (uint32_t)tid + (uint32_t)q * SP_THREADS;
+                if (i < n) rec[q] = kc_ld_cg(leaf + i);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < PER_THREAD; q++) {
+                const uint32_t i = (uint32_t)tid + (uint32_t)q * SP_THREADS;
+                if (i < n) atomicAdd(&s_hist[(uint32_t)((uint64_t)rec[q] >> lowbits) & (nb - 1u)], 1u);
+            }
+            __syncthreads();
+            uint32_t dummy;
+            const uint32_t cnt = (uint32_t)tid < nb ? s_hist[tid] : 0u;
+            const uint32_t begin = block_excl_scan(cnt, s_warp, &dummy);
+            if ((uint32_t)tid < nb) s_hist[tid] = begin;  // becomes the scatter cursor
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < PER_THREAD; q++) {
+                const uint32_t i = (uint32_t)tid + (uint32_t)q * SP_THREADS;
+                if (i < n) {
+                    const uint32_t pos = atomicAdd(&s_hist[(uint32_t)((uint64_t)rec[q] >> lowbits) & (nb - 1u)], 1u);
+                    s_sorted[pos] = rec[q];
+                }
+            }
+            __syncthreads();
+            // thread t owns sub-bucket t = s_sorted[begin, begin+cnt): insertion sort, count runs
+            uint32_t runs = 0;
+            if (cnt) {
+                for (uint32_t a = begin + 1; a < begin + cnt; a++) {
+                    const R2T v = s_sorted[a];
+                    uint32_t b = a;
+                    while (b > begin && s_sorted[b - 1] > v) {
+                        s_sorted[b] = s_sorted[b - 1];
+                        b--;
+                    }
+                    s_sorted[b] = v;
+                }
+                runs = 1;
+                for (uint32_t a = begin + 1; a < begin + cnt; a++) runs += (s_sorted[a] != s_sorted[a - 1]) ? 1u : 0u;
+            }
+            uint32_t leaf_runs;
+            const uint32_t off = block_excl_scan(runs, s_warp, &leaf_runs);
+            if (tid == 0) {
+                const unsigned long long base = atomicAdd(&ctl->out_cursor, (unsigned long long)leaf_runs);
+                s_base = base;
+                if (base + leaf_runs <= out_cap) {
+                    leaf_base[(uint64_t)p1 * Shape::P2 + p2] = base;
+                    leaf_n[(uint64_t)p1 * Shape::P2 + p2] = leaf_runs;
+                } else {
+                    atomicOr(&ctl->failed, (uint32_t)SP_FAIL_RUNLIST);  // temporary list full; leaf_n stays 0
+                }
+            }
+            __syncthreads();
+            const unsigned long long base = s_base;
+            if (cnt && base + leaf_runs <= out_cap) {
+                const uint64_t hi = ((uint64_t)p1 << r1bits) | ((uint64_t)p2 << r2bits);
+                uint64_t o = base + off;
+                R2T cur = s_sorted[begin];
+                uint32_t c = 1;
+                for (uint32_t a = begin + 1; a < begin + cnt; a++) {
+                    const R2T v = s_sorted[a];
+                    if (v != cur) {
+                        tmp_keys[o] = hi | (uint64_t)cur;
+                        tmp_counts[o] = c;
+                        o++;
+                        cur = v;
+                        c = 1;
+                    } else {
+                        c++;
+                    }
+                }
+                tmp_keys[o] = hi | (uint64_t)cur;
+                tmp_counts[o] = c;
+            }
+            // the barriers of the next leaf (or of the next partition) order the reuse of
+            // s_hist / s_sorted behind these reads
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: exclusive scan of leaf_n (one CTA; leaves in code order)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sp_scan_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, unsigned long long* __restrict__ leaf_off,
+               SpCtl* ctl) {
+    __shared__ unsigned long long s_sum[SP_THREADS];
+    const int tid = threadIdx.x;
+    const uint64_t per = (nleaves + SP_THREADS - 1) / SP_THREADS;
+    const uint64_t b = min((uint64_t)tid * per, nleaves), e = min(b + per, nleaves);
+    unsigned long long mine = 0;
+    for (uint64_t i = b; i < e; i++) mine += leaf_n[i];
+    s_sum[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < SP_THREADS; t++) {
+            const unsigned long long v = s_sum[t];
+            s_sum[t] = run;
+            run += v;
+        }
+        ctl->total = run;
+    }
+    __syncthreads();
+    unsigned long long run = s_sum[tid];
+    for (uint64_t i = b; i < e; i++) {
+        leaf_off[i] = run;
+        run += leaf_n[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: leaf runs -> final arrays (one warp per leaf at a time)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sp_gather_kernel(const uint32_t* __restrict__ leaf_n, const unsigned long long* __restrict__ leaf_base,
+                 const unsigned long long* __restrict__ leaf_off, uint64_t nleaves, const uint64_t* __restrict__ tmp_keys,
+                 const uint32_t* __restrict__ tmp_counts, uint64_t* __restrict__ keys, uint32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nw = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t leaf = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); leaf < nleaves; leaf += nw) {
+        const uint32_t n = leaf_n[leaf];
+        if (n == 0) continue;
+        const uint64_t src = leaf_base[leaf], dst = leaf_off[leaf];
+        for (uint32_t i = lane; i < n; i += 32) {
+            keys[dst + i] = tmp_keys[src + i];
+            counts[dst + i] = tmp_counts[src + i];
+        }
+    }
+}
+
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    void* release() {
+        void* q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
+// Records per private region for `mean` expected records: mean + 1/slack_div + sigmas * sqrt(mean)
+// + 4 chunks, a whole number of chunks.  Level 1 regions (one per pass-1 CTA and partition)
+// see near-Poisson counts; a LEAF holds whole families of repeated k-mers (coverage x copies
+// of every genomic k-mer that falls into it), so its count is compound-Poisson with a far
+// larger variance: level 2 gets twice the relative slack.
+uint64_t region_records(uint64_t mean, int chunk, int slack_div, int sigmas) {
+    uint64_t s = 1;
+    while (s * s < mean) s++;
+    uint64_t c = mean + mean / slack_div + sigmas * s + 4 * (uint64_t)chunk;
+    return (c + chunk - 1) / chunk * chunk;
+}
+
+template <typename Shape, typename R1T, typename R2T, int HALO>
+int run_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
+    using St1 = Stager<R1T, Shape::P1>;
+    using St2 = Stager<R2T, Shape::P2>;
+    cudaStream_t st = ctx->stream;
+    const uint64_t nwin = nbytes - k + 1;
+    const ScanGeom g = kc_make_geom(d_data, nbytes, 0, nwin, k);
+    const uint64_t ngroups = g.g_end - g.g_begin;
+    const uint64_t want1 = (ngroups + 31) / 32;
+    const int grid1 = (int)(want1 < 1 ? 1 : (want1 > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want1));
+    const int grid2 = ctx->sm_count < Shape::P1 ? ctx->sm_count : Shape::P1;
+    const uint64_t cap1 = region_records(nwin / ((uint64_t)Shape::P1 * grid1) + 1, St1::CAP, 8, 8);
+    const uint64_t part_mean = nwin / Shape::P1 + 1;
+    const uint64_t cap2 = region_records((part_mean + part_mean / 8) / Shape::P2 + 1, St2::CAP, 4, 16);
+    if ((uint64_t)Shape::P1 * cap1 >= (1ull << 32) || (uint64_t)Shape::P2 * cap2 >= (1ull << 32))
+        return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: region too large");
+    const uint64_t nleaves = (uint64_t)Shape::P1 * Shape::P2;
+
+    auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    const size_t b_ctl = pad(sizeof(SpCtl));
+    const size_t b_counts1 = pad((size_t)Shape::P1 * grid1 * 4);
+    const size_t b_leaf_n = pad(nleaves * 4);
+    const size_t b_leaf_base = pad(nleaves * 8);
+    const size_t b_leaf_off = pad(nleaves * 8);
+    const size_t b_slabs1 = pad((size_t)grid1 * Shape::P1 * cap1 * sizeof(R1T));
+    const size_t b_scratch2 = pad((size_t)grid2 * Shape::P2 * cap2 * sizeof(R2T));
+    const size_t fixed = b_ctl + b_counts1 + b_leaf_n + b_leaf_base + b_leaf_off + b_slabs1 + b_scratch2;
+    int rc = kc_scratch_reserve(ctx, fixed);
+    if (rc) return rc;
+    char* base = (char*)ctx->scratch;
+    SpCtl* ctl = (SpCtl*)base;
+    uint32_t* counts1 = (uint32_t*)(base + b_ctl);
+    uint32_t* leaf_n = (uint32_t*)((char*)counts1 + b_counts1);
+    unsigned long long* leaf_base = (unsigned long long*)((char*)leaf_n + b_leaf_n);
+    unsigned long long* leaf_off = (unsigned long long*)((char*)leaf_base + b_leaf_base);
+    R1T* slabs1 = (R1T*)((char*)leaf_off + b_leaf_off);
+    R2T* scratch2 = (R2T*)((char*)slabs1 + b_slabs1);
+
+    // temporary run list: as many entries as fit in 45 % of what is free now (the final arrays
+    // need the same again), never more than one per window
+    size_t free_b = 0, total_b = 0;
+    KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    uint64_t out_cap = (uint64_t)(free_b / 100 * 45) / 12;
+    if (out_cap > nwin) out_cap = nwin;
+    if (out_cap < 1024) return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: no device memory left for the run list");
+    DevMem tkeys, tcounts;
+    if (tkeys.alloc(out_cap * 8) || tcounts.alloc(out_cap * 4)) {
+        cudaGetLastError();
+        return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: out of device memory for the run list");
+    }
+    KC_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(SpCtl), st));
+    KC_CUDA(ctx, cudaMemsetAsync(leaf_n, 0, nleaves * 4, st));
+
+    const size_t smem1 = St1::SMEM_BYTES;
+    {
+        auto kern = sp_scatter_kernel<Shape, R1T, HALO>;
+        KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        KC_LAUNCH(kern, grid1, SP_THREADS, smem1, st, g, slabs1, counts1, (uint32_t)cap1, ctl);
+        KC_LAUNCH_CHECK(ctx, "sp_scatter_kernel");
+    }
+    constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
+    const size_t smem2 = St2::SMEM_BYTES + 1024 * 4 + (size_t)LEAF_CAP * sizeof(R2T);
+    {
+        auto kern = sp_leaf_kernel<Shape, R1T, R2T>;
+        KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, k, slabs1, counts1, (uint32_t)cap1, (uint32_t)grid1, scratch2,
+                  (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p, out_cap, leaf_base, leaf_n, ctl);
+        KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
+    }
+    KC_LAUNCH(sp_scan_kernel, 1, SP_THREADS, 0, st, leaf_n, nleaves, leaf_off, ctl);
+    KC_LAUNCH_CHECK(ctx, "sp_scan_kernel");
+    SpCtl h;
+    KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    KC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h.failed) {
+        *failed = (int)h.failed;
+        return KC_OK;
+    }
+    kc_sparse* res = new kc_sparse();
+    res->ctx = ctx;
+    res->size = h.total;
+    *out = res;
+    if (h.total == 0) return KC_OK;
+    DevMem fk, fc;
+    if (fk.alloc(h.total * 8) || fc.alloc(h.total * 4)) {
+        cudaGetLastError();
+        kc_sparse_free(res);
+        *out = nullptr;
+        return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: out of device memory for %llu k-mers", h.total);
+    }
+    KC_LAUNCH(sp_gather_kernel, ctx->sm_count * 8, 256, 0, st, leaf_n, leaf_base, leaf_off, nleaves, (const uint64_t*)tkeys.p,
+              (const uint32_t*)tcounts.p, (uint64_t*)fk.p, (uint32_t*)fc.p);
+    KC_LAUNCH_CHECK(ctx, "sp_gather_kernel");
+    KC_CUDA(ctx, cudaStreamSynchronize(st));
+    res->d_keys = (uint64_t*)fk.release();
+    res->d_counts = (uint32_t*)fc.release();
+    return KC_OK;
+}
+
+template <typename Shape>
+int dispatch(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
+    const int r1 = 2 * k - Shape::KB1, r2 = r1 - Shape::KB2;
+    if (r2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix needs 2k > %d (k=%d)", Shape::KB1 + Shape::KB2, k);
+    if (r1 <= 32) {  // both record levels fit 32 bits
+        return k <= 17 ? run_radix<Shape, uint32_t, uint32_t, 1>(ctx, d_data, nbytes, k, out, failed)
+                       : run_radix<Shape, uint32_t, uint32_t, 2>(ctx, d_data, nbytes, k, out, failed);
+    }
+    if (r2 <= 32) return run_radix<Shape, uint64_t, uint32_t, 2>(ctx, d_data, nbytes, k, out, failed);
+    return run_radix<Shape, uint64_t, uint64_t, 2>(ctx, d_data, nbytes, k, out, failed);
+}
+
+}  // namespace
+
+// Called by kc_count_sparse (sparse.cu).  *failed = 1: nothing was produced, recount otherwise.
+int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
+    *failed = 0;
+    *out = nullptr;
+    // tuning/test aid: "small" = 16 x 16 partitions, so that small inputs (and the CPU
+    // emulator) exercise full regions, leaf sorts and the overflow paths
+    static const char* shape = getenv("KC_SPARSE_RADIX_SHAPE");
+    if (shape && shape[0] == 's') return dispatch<SpShape<4, 4, 2048>>(ctx, d_data, nbytes, k, out, failed);
+    return dispatch<SpShape<10, 10, 20480>>(ctx, d_data, nbytes, k, out, failed);
+}

@@ -18,8 +18,9 @@ HEADER_PATH = os.path.join(REPO_ROOT, "include", "kmer_b200.h")
 KC_OK = 0
 KC_ERR_INVALID, KC_ERR_CUDA, KC_ERR_IO, KC_ERR_NOMEM, KC_ERR_TABLE_FULL, KC_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 DENSE_AUTO, DENSE_DIRECT, DENSE_PARTITION = 0, 1, 2
-SPARSE_HASH, SPARSE_SORT = 0, 1
+SPARSE_HASH, SPARSE_SORT, SPARSE_RADIX = 0, 1, 2
 SPARSE_UNSORTED = 0x100
+SPARSE_NO_FALLBACK = 0x200
 IMPORT_BLANKLINE, IMPORT_NONL = 0, 1
 MAX_K, MAX_DENSE_K = 31, 16
 

@@ -182,9 +182,13 @@ KC_API int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
  * sorted by code with their uint32 counts.                                  */
 #define KC_SPARSE_HASH 0   /* open-addressing hash table (CAS key, RED count) */
 #define KC_SPARSE_SORT 1   /* radix sort of codes + run-length reduce          */
+#define KC_SPARSE_RADIX 2  /* MSD radix partition, leaves sorted in shared memory (k >= 11);
+                              falls back to KC_SPARSE_HASH when skewed data overflows a region */
 /* OR-ed into `algo`: leave the distinct (code,count) pairs in table order instead of
  * sorting them — for callers that re-bucket and merge anyway (the multi-GPU path).   */
 #define KC_SPARSE_UNSORTED 0x100
+/* OR-ed into KC_SPARSE_RADIX: return KC_ERR_TABLE_FULL instead of recounting with the hash path */
+#define KC_SPARSE_NO_FALLBACK 0x200
 KC_API int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int algo,
                            uint64_t capacity_hint, kc_sparse** out);
 KC_API void kc_sparse_free(kc_sparse* s);

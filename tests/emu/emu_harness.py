@@ -23,6 +23,7 @@ _LIB = None
 KC_DENSE_AUTO, KC_DENSE_DIRECT, KC_DENSE_PARTITION = 0, 1, 2
 KC_SPARSE_HASH, KC_SPARSE_SORT, KC_SPARSE_RADIX = 0, 1, 2
 KC_SPARSE_UNSORTED = 0x100
+KC_SPARSE_NO_FALLBACK = 0x200
 
 
 def build():
@@ -179,13 +180,19 @@ def case_dense(args):
 def case_sparse(args):
     k, n, algo, kind, seed, offset = int(args[0]), int(args[1]), int(args[2]), args[3], int(args[4]), int(args[5])
     O = _oracle()
-    if kind == "reads":
+    if kind == "reads":      # deep coverage of a tiny genome: few distinct k-mers, many repeats
         nreads = n // 101
         data = O.gen_reads(seed, 5000, 100, 50, 0, nreads)
+    elif kind == "readsU":   # shallow coverage: mostly distinct k-mers, uniform over the partitions
+        nreads = n // 101
+        data = O.gen_reads(seed, 4 * n, 100, 50, 0, nreads)
     else:
         data = make_input(kind, n, seed, k)
     ctx = EmuContext()
     keys, counts = ctx.count_sparse(data, k, algo, offset=offset)
+    if algo & KC_SPARSE_UNSORTED:
+        order = np.argsort(keys, kind="stable")
+        keys, counts = keys[order], counts[order]
     wk, wc, _ = O.count_sparse(data, k)
     assert keys.size == wk.size, "sparse k=%d algo=%d: %d distinct, oracle %d" % (k, algo, keys.size, wk.size)
     assert (keys == wk).all() and (counts == wc).all(), "sparse k=%d algo=%d differs from the oracle" % (k, algo)

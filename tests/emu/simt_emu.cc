@@ -1,5 +1,8 @@
 // simt_emu.cc — scheduler of the test-only SIMT emulator (see simt_emu.h).
+#include <execinfo.h>
+#include <signal.h>
 #include <stdarg.h>
+#include <unistd.h>
 
 #include "simt_emu.h"
 
@@ -94,6 +97,10 @@ void maybe_preempt() {
     if (!S.in_kernel || S.preempt_mask == 0) return;
     if ((next_rand() & S.preempt_mask) != 0) return;
     to_scheduler();  // stays runnable
+}
+
+void maybe_preempt_always() {
+    if (S.in_kernel) to_scheduler();
 }
 
 static void check_barrier_release() {
@@ -195,6 +202,34 @@ static void prepare_fiber(Fiber& fb) {
     fb.state = 0;
 }
 
+void describe_address(const void* addr);
+
+static void on_segv(int, siginfo_t* si, void*) {
+    static char buf[512];
+    int n = snprintf(buf, sizeof buf, "simt_emu: SIGSEGV at address %p  [block (%u,%u) thread %u]\n", si->si_addr, blockIdx_.x,
+                     blockIdx_.y, threadIdx_.x);
+    if (write(2, buf, n) < 0) {}
+    describe_address(si->si_addr);
+    void* bt[32];
+    const int m = backtrace(bt, 32);
+    backtrace_symbols_fd(bt, m, 2);
+    _exit(139);
+}
+
+static void install_segv_handler() {
+    static char altstack[1 << 16];
+    stack_t ss;
+    ss.ss_sp = altstack;
+    ss.ss_size = sizeof altstack;
+    ss.ss_flags = 0;
+    sigaltstack(&ss, nullptr);
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_sigaction = on_segv;
+    sa.sa_flags = SA_SIGINFO | SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, nullptr);
+}
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     if (S.in_kernel) fail("nested launch");
     const int tpb = (int)(block.x * block.y * block.z);
@@ -204,6 +239,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     static uint64_t seed = 0;
     if (!init) {
         init = true;
+        install_segv_handler();
         const char* s = getenv("KC_EMU_SEED");
         seed = s ? strtoull(s, nullptr, 0) : 0;
         const char* p = getenv("KC_EMU_PREEMPT_SHIFT");  // yield with probability 2^-shift at every preemption point
@@ -279,6 +315,24 @@ std::map<void*, Alloc>& allocs() {
     return a;
 }
 }  // namespace
+
+namespace emu {
+void describe_address(const void* addr) {
+    char buf[256];
+    for (auto& kv : allocs()) {
+        const char* m = (const char*)kv.second.map;
+        if ((const char*)addr >= m && (const char*)addr < m + kv.second.map_bytes) {
+            const long off = (const char*)addr - (const char*)kv.first;
+            const int n = snprintf(buf, sizeof buf, "  inside the mapping of device allocation %p: offset %ld from its start (guard page behind its end)\n",
+                                   kv.first, off);
+            if (write(2, buf, n) < 0) {}
+            return;
+        }
+    }
+    const int n = snprintf(buf, sizeof buf, "  not near any device allocation\n");
+    if (write(2, buf, n) < 0) {}
+}
+}  // namespace emu
 
 cudaError_t emu_cuda_malloc(void** p, size_t n) {
     const size_t page = 4096;

@@ -111,6 +111,7 @@ extern dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void yield_blocked();      // current fiber blocks until somebody makes it runnable
 void maybe_preempt();      // random voluntary yield (stays runnable)
+void maybe_preempt_always();  // unconditional yield (spin loops must let the others run)
 void make_runnable(int f);
 uint32_t warp_exchange(uint32_t mask, uint32_t v, int kind, int arg);  // shfl/ballot/syncwarp
 void syncthreads();

@@ -56,13 +56,57 @@ def test_partition_staging_protocol_random_schedules(seed):
     run_case("dense", 12, 200_000, 2, "skew", 20 + seed, 0, seed=seed, sms=1, shift=1)
 
 
+RADIX, NOFB, UNSORTED = 2, 0x200, 0x100
 SPARSE = [
     (21, 60_000, 0, "reads", 1, 0),
     (31, 60_000, 0, "dirty", 2, 5),
     (15, 50_000, 1, "genome", 3, 0),
+    (21, 60_000, 0 | UNSORTED, "readsU", 4, 0),
 ]
 
 
 @pytest.mark.parametrize("case", SPARSE, ids=lambda c: "k%d-%s-a%d" % (c[0], c[3], c[2]))
 def test_sparse_kernels_on_emulator(case):
     run_case("sparse", *case, seed=0)
+
+
+# KC_SPARSE_RADIX with the 16 x 16 test shape (KC_SPARSE_RADIX_SHAPE=small): regions fill up,
+# leaves hold thousands of records, every record width combination (32/32, 64/32, 64/64 bits)
+# and both scanner halos are hit.  NO_FALLBACK: the radix path itself must produce the result.
+@pytest.mark.parametrize("k", [13, 17, 18, 19, 21, 27, 28, 31])
+def test_sparse_radix_small_shape(k):
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        run_case("sparse", k, 60_000, RADIX | NOFB, "readsU", k, k % 16, seed=0)
+        run_case("sparse", k, 50_000, RADIX | NOFB, "dirty", k + 1, 0, seed=0)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sparse_radix_staging_random_schedules(seed):
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        # deep coverage of a tiny genome: a few partitions take most records, so under an
+        # adversarial schedule a writer may find both bins full 256 times and give up —
+        # then the hash recount must still deliver the exact result (no NO_FALLBACK here)
+        run_case("sparse", 21, 80_000, RADIX, "reads", seed, 3, seed=seed, sms=2, shift=1)
+        run_case("sparse", 21, 60_000, RADIX | NOFB, "readsU", 10 + seed, 5, seed=seed, sms=2, shift=1)
+        run_case("sparse", 31, 60_000, RADIX | NOFB, "readsU", seed, 0, seed=seed, sms=1, shift=2)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+def test_sparse_radix_overflow_falls_back_to_hash():
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        run_case("sparse", 21, 60_000, RADIX, "polyA", 1, 0, seed=0)       # one leaf takes everything
+        with pytest.raises(AssertionError, match="overflowed"):
+            run_case("sparse", 21, 60_000, RADIX | NOFB, "polyA", 1, 0, seed=0)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+def test_sparse_radix_production_shape():
+    # 1024 x 1024 partitions: mostly empty leaves at this size, but the shipped geometry
+    run_case("sparse", 21, 40_000, RADIX | NOFB, "readsU", 9, 0, seed=0, sms=2)

@@ -1,0 +1,54 @@
+"""GPU parity tests of paths whose kernels have so far only met the oracle on the CPU
+emulator (tests/test_emu_kernels.py) — written while the round's GPU budget was spent.
+They run LAST (file name) and are marked xfail(strict=False): a pass shows as XPASS, a
+mismatch as XFAIL, and neither hides behind the verified tests above.  Remove the marker
+once a B200 run has been seen green."""
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first B200 run pending (verified on the CPU emulator only)")]
+
+
+def to_dev(arr):
+    import torch
+    a = np.ascontiguousarray(arr, dtype=np.uint8)
+    buf = torch.zeros(a.size + 64, dtype=torch.uint8, device="cuda:0")
+    if a.size:
+        buf[: a.size] = torch.from_numpy(a.copy())
+    return buf
+
+
+@pytest.mark.parametrize("k", [13, 17, 18, 21, 25, 28, 31])
+def test_sparse_radix_vs_oracle(ctx, kmerlib, oracle, k):
+    """KC_SPARSE_RADIX (1024 x 1024 partitions, the shipped shape) on shallow-coverage reads;
+    NO_FALLBACK: the radix kernels themselves must produce the result."""
+    nreads = 30_000
+    reads = oracle.gen_reads(0xB2000004 + k, 4_000_000, 150, 200, 0, nreads)
+    wk, wc, _ = oracle.count_sparse(reads, k)
+    sp = ctx.count_sparse(to_dev(reads), reads.size, k, kmerlib.SPARSE_RADIX | kmerlib.SPARSE_NO_FALLBACK)
+    keys, counts = sp.to_host()
+    assert len(sp) == len(wk) and (keys == wk).all() and (counts == wc).all()
+
+
+def test_sparse_radix_deep_coverage_and_fallback(ctx, kmerlib, oracle):
+    """deep coverage (counts >> 1) and an input that must overflow a leaf (one k-mer only):
+    with fallback allowed both give the oracle's result."""
+    reads = oracle.gen_reads(0xB2000004, 200_000, 150, 200, 0, 40_000)
+    poly = np.full(3_000_000, ord("A"), dtype=np.uint8)
+    for data, k in ((reads, 21), (reads, 31), (poly, 21)):
+        wk, wc, _ = oracle.count_sparse(data, k)
+        keys, counts = ctx.count_sparse(to_dev(data), data.size, k, kmerlib.SPARSE_RADIX).to_host()
+        assert (keys == wk).all() and (counts == wc).all()
+
+
+def test_sparse_radix_equals_hash_at_scale(ctx, kmerlib):
+    """no oracle at this size (20 M windows): the two GPU algorithms must agree exactly"""
+    nreads, k = 150_000, 21
+    reads = ctx.gen_reads(0xB2000004, 50_000_000, 150, 200, 0, nreads)
+    a = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_HASH)
+    b = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_RADIX | kmerlib.SPARSE_NO_FALLBACK)
+    ka, ca = a.to_host()
+    kb, cb = b.to_host()
+    assert len(a) == len(b) and (ka == kb).all() and (ca == cb).all()
+    assert int(ca.astype(np.int64).sum()) == nreads * (150 - k + 1)
