@@ -24,6 +24,7 @@
 // runs the kernels' logic against the oracle where there is no GPU.  `kern` must be a plain
 // identifier (take `auto kern = some_kernel<...>;` first when the name has commas).
 #ifndef KC_EMU
+#define KC_STAT(i) ((void)0)  // rare-path counters exist in the emulator build only
 #define KC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define KC_DYN_SMEM(T, name) extern __shared__ T name[]
 #endif

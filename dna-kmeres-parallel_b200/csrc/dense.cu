@@ -308,6 +308,8 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
         }
     };
 
+    uint32_t pend = 0;       // DEFER variant: a record waiting for its second attempt
+    bool have_pend = false;
     if (nsteps) {
         // record starts are the positions = 0 mod A counted from the first interior byte
         int d = (int)(((gb % C::A) * (512 % C::A) + (uint32_t)lane * (16 % C::A)) % C::A);
@@ -352,6 +354,36 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
                                 part_fallback<C>(rec, okr, table);  // rare: next to an N run
                             } else if (ABLATE == 2) {
                                 if (rec == 0x12345678u && j0 == 77) table[rec] = okr;  // measurement only
+                            } else if (ABLATE == 3) {
+                                // DEFER variant (not the default until measured): a record that meets a
+                                // full bin waits in a register for this lane's next record slot, where it
+                                // gets ONE more attempt before it is counted with REDs.  Motive
+                                // (profiles/r01_ncu_per_source_line.txt): 2.2 % of the records take the
+                                // RED fallback, but that divergent 42-instruction function runs in 30 % of
+                                // the warp iterations and costs 21 % of the kernel's instructions; a bin
+                                // reopens within a few hundred cycles, a lane's next slot comes later.
+                                uint32_t r = have_pend ? pend : rec;
+                                bool retry = have_pend;
+                                have_pend = false;
+                                for (;;) {
+                                    const uint32_t pid = (r >> C::KB0) & (C::P - 1);
+                                    const uint32_t slot = smem_atom_add(s_state + pid * 4, 1u) & 0xFFFFu;
+                                    if (slot < (uint32_t)C::CAP) {
+                                        smem_st(s_buf + (pid * C::CAP + slot) * 4, r);
+                                        const uint32_t wr = smem_atom_add(s_state + pid * 4, 0x10000u) >> 16;
+                                        if (wr == (uint32_t)C::CAP - 1) flush_bin(pid);
+                                    } else if (retry) {
+                                        KC_STAT(2);
+                                        part_fallback<C>(r, C::AMASK, table);
+                                    } else {
+                                        KC_STAT(1);
+                                        pend = r;
+                                        have_pend = true;
+                                    }
+                                    if (!retry) break;
+                                    retry = false;
+                                    r = rec;
+                                }
                             } else {
                                 const uint32_t pid = (rec >> C::KB0) & (C::P - 1);
                                 const uint32_t slot = smem_atom_add(s_state + pid * 4, 1u) & 0xFFFFu;
@@ -360,6 +392,7 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
                                     const uint32_t wr = smem_atom_add(s_state + pid * 4, 0x10000u) >> 16;
                                     if (wr == (uint32_t)C::CAP - 1) flush_bin(pid);
                                 } else {
+                                    KC_STAT(0);
                                     part_fallback<C>(rec, C::AMASK, table);
                                 }
                             }
@@ -385,6 +418,7 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
             ptr += 32 * DEPTH;
         }
     }
+    if (ABLATE == 3 && have_pend) part_fallback<C>(pend, C::AMASK, table);
     // final flush of the partially filled bins, then publish the region lengths
     __syncthreads();
     for (int b = tid >> 5; b < C::P; b += NW) {
@@ -575,6 +609,8 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
         KC_LAUNCH_SCATTER(1);
     else if (ablate == 2)
         KC_LAUNCH_SCATTER(2);
+    else if (ablate == 3)
+        KC_LAUNCH_SCATTER(3);
     else
         KC_LAUNCH_SCATTER(0);
 #undef KC_LAUNCH_SCATTER

@@ -121,8 +121,13 @@ struct Stager {
                 return;
             }
             bin ^= 1u;
-            if (tries & 1) KC_SPIN_PAUSE();  // both bins were full
+            KC_STAT(3);
+            if (tries & 1) {
+                KC_STAT(4);
+                KC_SPIN_PAUSE();  // both bins were full
+            }
         }
+        KC_STAT(5);
         atomicOr(failed, (uint32_t)SP_FAIL_STAGING);
     }
 

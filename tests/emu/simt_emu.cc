@@ -9,6 +9,13 @@
 namespace emu {
 
 State S;
+uint64_t stats[16];
+static void print_stats() {
+    if (!getenv("KC_EMU_STATS")) return;
+    fprintf(stderr, "simt_emu stats:");
+    for (int i = 0; i < 16; i++) fprintf(stderr, " [%d]=%llu", i, (unsigned long long)stats[i]);
+    fprintf(stderr, " launches=%llu switches=%llu\n", (unsigned long long)S.launches, (unsigned long long)S.switches);
+}
 dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 
 static constexpr size_t STACK_BYTES = 256 * 1024;
@@ -240,6 +247,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     if (!init) {
         init = true;
         install_segv_handler();
+        atexit(print_stats);
         const char* s = getenv("KC_EMU_SEED");
         seed = s ? strtoull(s, nullptr, 0) : 0;
         const char* p = getenv("KC_EMU_PREEMPT_SHIFT");  // yield with probability 2^-shift at every preemption point

@@ -106,6 +106,7 @@ struct State {
     bool in_kernel = false;
 };
 extern State S;
+extern uint64_t stats[16];  // KC_STAT(i) counters of rare paths, printed at exit when KC_EMU_STATS is set
 extern dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
@@ -227,6 +228,7 @@ static inline size_t __cvta_generic_to_shared(const void* p) {
     return (size_t)(c - emu::S.dyn_smem) + emu::SMEM_WINDOW;
 }
 
+#define KC_STAT(i) (::emu::stats[i]++)
 #define KC_DYN_SMEM(T, name) T* const name = reinterpret_cast<T*>(::emu::S.dyn_smem)
 #define KC_LAUNCH(kern, grid, block, smem, stream, ...) \
     ::emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
