@@ -1,0 +1,27 @@
+#!/bin/bash
+# First GPU call of the next round: everything that was written while the GPU budget of round 1
+# was spent (sparse radix path, deferred-retry scatter, bench exit path) in ONE gpurun call.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Every step is bounded by its own timeout; outputs land in gpurun_out/r02_*.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+echo "== 1. GPU parity tests (the first-run-pending file is last and xfail(strict=False))"
+timeout 900 python -m pytest tests -m gpu -q -x -rxX > $O/r02_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 $O/r02_pytest.log
+echo "== 2. dense k=12: shipped scatter vs deferred retry (KC_PART_ABLATE=3)"
+for A in 0 3; do
+  KC_PART_ABLATE=$A timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_dense_abl$A.log 2> $O/r02_dense_abl$A.err
+  python - <<PY
+import json
+d=json.load(open("$O/r02_dense_abl$A.log"))
+print("ablate=$A ms/step %.4f kernels %s checksum %s" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
+PY
+done
+echo "== 3. sparse config 4 at 1/5 scale and full scale: hash vs radix"
+for R in 20000000 0; do for A in hash radix; do
+  timeout 600 python bench.py --workload config4 --reads $R --sparse-algo $A --steps 1 --warmup 1 > $O/r02_c4_${A}_$R.log 2> $O/r02_c4_${A}_$R.err
+  echo "config4 reads=$R algo=$A rc=$?"; cut -c1-400 $O/r02_c4_${A}_$R.log; tail -2 $O/r02_c4_${A}_$R.err
+done; done
+echo "== 4. default bench line (with e2e + cpu baseline)"
+timeout 600 python bench.py > $O/r02_bench_n1.log 2> $O/r02_bench_n1.err; echo "bench rc=$?"; cut -c1-600 $O/r02_bench_n1.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_ref.log 2> $O/r02_bench_ref.err; echo "reference arm rc=$?"; cut -c1-300 $O/r02_bench_ref.log
