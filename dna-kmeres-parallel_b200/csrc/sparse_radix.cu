@@ -296,15 +296,37 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
         }
 
         // ---- phase A: partition by the next KB2 bits ------------------------------------
+        // (the P2 mask only matters after an overflow upstream left garbage in a region: the
+        // result is discarded then, but the kernel must stay in bounds)
+        auto stage1 = [&](uint64_t r1, uint32_t pref) {
+            st.stage((uint32_t)(r1 >> r2bits) & (Shape::P2 - 1), (R2T)(r1 & r2mask), pref);
+        };
+        auto stage_vec = [&](uint4 v, uint32_t pref) {  // 4 (32-bit) or 2 (64-bit) records
+            if (sizeof(R1T) == 4) {
+                stage1(v.x, pref);
+                stage1(v.y, pref + 1);
+                stage1(v.z, pref);
+                stage1(v.w, pref + 1);
+            } else {
+                stage1(((uint64_t)v.y << 32) | v.x, pref);
+                stage1(((uint64_t)v.w << 32) | v.z, pref + 1);
+            }
+        };
+        constexpr uint32_t RPV = 16 / sizeof(R1T);  // records per 128-bit load
         for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
             const uint32_t n = counts1[(uint64_t)p1 * nregions + reg];
-            const R1T* src = slabs1 + ((uint64_t)reg * Shape::P1 + p1) * cap1;
-            for (uint32_t i = lane; i < n; i += 32) {
-                const uint64_t r1 = (uint64_t)src[i];
-                // (the mask only matters after an overflow upstream left garbage in a region:
-                // the result is discarded then, but the kernel must stay in bounds)
-                st.stage((uint32_t)(r1 >> r2bits) & (Shape::P2 - 1), (R2T)(r1 & r2mask), (uint32_t)warp + i);
+            const R1T* src = slabs1 + ((uint64_t)reg * Shape::P1 + p1) * cap1;  // 64-byte aligned
+            const uint4* src4 = reinterpret_cast<const uint4*>(src);
+            const uint32_t nv = n / RPV;
+            uint32_t i = lane;
+            for (; i + 32 < nv; i += 64) {  // two 128-bit loads in flight per lane
+                const uint4 v0 = kc_ldg_stream(src4 + i);
+                const uint4 v1 = kc_ldg_stream(src4 + i + 32);
+                stage_vec(v0, (uint32_t)warp);
+                stage_vec(v1, (uint32_t)warp + 1);
             }
+            for (; i < nv; i += 32) stage_vec(kc_ldg_stream(src4 + i), (uint32_t)warp);
+            for (uint32_t t = nv * RPV + lane; t < n; t += 32) stage1((uint64_t)src[t], (uint32_t)warp);
         }
         __syncthreads();
         st.finish(smem, nullptr, 0, 0);
