@@ -301,16 +301,14 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
         auto stage1 = [&](uint64_t r1, uint32_t pref) {
             st.stage((uint32_t)(r1 >> r2bits) & (Shape::P2 - 1), (R2T)(r1 & r2mask), pref);
         };
-        auto stage_vec = [&](uint4 v, uint32_t pref) {  // 4 (32-bit) or 2 (64-bit) records
-            if (sizeof(R1T) == 4) {
-                stage1(v.x, pref);
-                stage1(v.y, pref + 1);
-                stage1(v.z, pref);
-                stage1(v.w, pref + 1);
-            } else {
-                stage1(((uint64_t)v.y << 32) | v.x, pref);
-                stage1(((uint64_t)v.w << 32) | v.z, pref + 1);
-            }
+        // The staging code is long (it contains the bin flush), so it must not be inlined once
+        // per record of a 128-bit load: the records of two loads sit in eight registers and ONE
+        // copy of the staging code runs in a rolled loop that picks them with selects.
+        auto pick = [](const uint32_t (&w)[8], int e) {
+            uint32_t r = w[0];
+#pragma unroll
+            for (int q = 1; q < 8; q++) r = (e == q) ? w[q] : r;
+            return r;
         };
         constexpr uint32_t RPV = 16 / sizeof(R1T);  // records per 128-bit load
         for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
@@ -318,14 +316,19 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
             const R1T* src = slabs1 + ((uint64_t)reg * Shape::P1 + p1) * cap1;  // 64-byte aligned
             const uint4* src4 = reinterpret_cast<const uint4*>(src);
             const uint32_t nv = n / RPV;
-            uint32_t i = lane;
-            for (; i + 32 < nv; i += 64) {  // two 128-bit loads in flight per lane
+            for (uint32_t i = lane; i < nv; i += 64) {  // two 128-bit loads in flight per lane
+                const bool two = i + 32 < nv;
                 const uint4 v0 = kc_ldg_stream(src4 + i);
-                const uint4 v1 = kc_ldg_stream(src4 + i + 32);
-                stage_vec(v0, (uint32_t)warp);
-                stage_vec(v1, (uint32_t)warp + 1);
+                const uint4 v1 = two ? kc_ldg_stream(src4 + i + 32) : make_uint4(0, 0, 0, 0);
+                const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                const int words = two ? 8 : 4;
+#pragma unroll 1
+                for (int e = 0; e < words; e += (int)sizeof(R1T) / 4) {
+                    uint64_t r1 = pick(w, e);
+                    if (sizeof(R1T) == 8) r1 |= (uint64_t)pick(w, e + 1) << 32;
+                    stage1(r1, (uint32_t)warp + (uint32_t)e);
+                }
             }
-            for (; i < nv; i += 32) stage_vec(kc_ldg_stream(src4 + i), (uint32_t)warp);
             for (uint32_t t = nv * RPV + lane; t < n; t += 32) stage1((uint64_t)src[t], (uint32_t)warp);
         }
         __syncthreads();
