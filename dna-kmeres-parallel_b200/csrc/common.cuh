@@ -195,6 +195,9 @@ __device__ __forceinline__ uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(saddr), "r"(v) : "memory");
     return r;
 }
+__device__ __forceinline__ void smem_red_add(uint32_t saddr, uint32_t v) {  // no return value
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void smem_st(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -233,6 +236,10 @@ static inline uint32_t smem_atom_add(uint32_t saddr, uint32_t v) {
     const uint32_t old = *p;
     *p = old + v;
     return old;
+}
+static inline void smem_red_add(uint32_t saddr, uint32_t v) {
+    emu::maybe_preempt();
+    *(uint32_t*)emu::smem_ptr(saddr, 4) += v;
 }
 static inline void smem_st(uint32_t saddr, uint32_t v) {
     emu::maybe_preempt();

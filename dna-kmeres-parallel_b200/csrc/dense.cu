@@ -177,6 +177,171 @@ __global__ void smem16_reduce_kernel(const uint32_t* __restrict__ partials, int 
 }
 
 // ---------------------------------------------------------------------------
+// k = 8, CHECKSUM variant (KC_DENSE_SMEM16C; first B200 run pending, not the default).
+// The kernel above pays for its exactness inside the hot loop: a RETURNING shared atomic,
+// a compare and a branch per window, plus a CTA barrier every two steps (it runs at 4.2
+// windows/clk/SM where shared memory sustains 9).  Here the hot loop is decode + one
+// non-returning `red.shared.add` per window and nothing else; a 16-bit field that wraps
+// is found AFTERWARDS:
+//   every add puts +1 into one 16-bit field, so without a wrap  sum(fields) == adds of the CTA;
+//   a low field that wraps loses 65536 and gives +1 to the high field (sum -65535), a high
+//   field that wraps loses 65536 (sum -65536); c1 and c2 such events change the sum by
+//   -(65535 c1 + 65536 c2), which is 0 only for c1 = c2 = 0.
+// A CTA whose checksum fails raises flags[cta]; the reduce kernel skips its partial table
+// and smem16_repair_kernel recounts exactly that CTA's groups with global REDs.  Uniform
+// data never fails (3.1 Gbp: ~320 hits per bin and CTA); poly-A fails everywhere and is
+// still exact, at the direct path's speed.
+// ---------------------------------------------------------------------------
+template <int DEPTH>
+__global__ void __launch_bounds__(1024, 1)
+dense_smem16c_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* __restrict__ partials,
+                     uint32_t* __restrict__ flags) {
+    KC_DYN_SMEM(uint32_t, words);  // 32768
+    __shared__ unsigned long long s_red[64];
+    const uint32_t s_words = (uint32_t)__cvta_generic_to_shared(words);
+    const int tid = threadIdx.x, lane = tid & 31;
+    {
+        uint4* w4 = reinterpret_cast<uint4*>(words);
+        for (int i = tid; i < 32768 / 4; i += 1024) w4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const uint64_t nwarps = (uint64_t)gridDim.x * 32;
+    const uint64_t units = ngroups / DEPTH;
+    const uint64_t upw = (units + nwarps - 1) / nwarps;
+    const uint64_t w = (uint64_t)blockIdx.x * 32 + (tid >> 5);
+    const uint64_t gb = min(w * upw, units) * DEPTH;
+    const uint32_t nsteps = (uint32_t)(min((w + 1) * upw, units) * DEPTH - gb);
+    const uint4* ptr = base + gb * 32 + lane;
+    uint32_t nadds = 0;
+    if (nsteps) {
+        uint4 raw[DEPTH];
+        Decoded16 cur16 = kc_decode16(kc_ldg_stream(ptr));
+#pragma unroll
+        for (int q = 0; q < DEPTH; q++) raw[q] = kc_ldg_stream(ptr + 32 * (q + 1));
+        for (uint32_t i = 0; i < nsteps; i += DEPTH) {
+            uint4 fresh[DEPTH];
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) fresh[q] = kc_ldg_stream(ptr + 32 * (DEPTH + 1 + q));
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) {
+                const Decoded16 nxt = kc_decode16(raw[q]);
+                uint32_t p1 = __shfl_down_sync(0xffffffffu, cur16.packed, 1);
+                uint32_t b1 = __shfl_down_sync(0xffffffffu, cur16.bad, 1);
+                const uint32_t n0p = __shfl_sync(0xffffffffu, nxt.packed, 0);
+                const uint32_t n0b = __shfl_sync(0xffffffffu, nxt.bad, 0);
+                if (lane == 31) {
+                    p1 = n0p;
+                    b1 = n0b;
+                }
+                const uint32_t p0 = cur16.packed;
+                const uint32_t B32 = cur16.bad | (b1 << 16);
+                uint32_t ok = 0xFFFFu;
+                if (B32) ok = ~(uint32_t)kc_window_bad((uint64_t)B32 | (0xFFFFull << 32), 8) & 0xFFFFu;
+                nadds += (uint32_t)__popc(ok);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (ok & (1u << j)) {
+                        const uint32_t code = __funnelshift_r(p0, p1, 2 * j) & 0xFFFFu;
+                        smem_red_add(s_words + (code & 0x7FFFu) * 4, (code >> 15) * 0xFFFFu + 1u);  // +1 or +0x10000
+                    }
+                }
+                cur16 = nxt;
+            }
+            const uint32_t zero = kc_opaque_zero(cur16.bad);  // bad < 2^16: pins the copies here
+#pragma unroll
+            for (int q = 0; q < DEPTH; q++) {
+                raw[q].x = fresh[q].x | zero;
+                raw[q].y = fresh[q].y | zero;
+                raw[q].z = fresh[q].z | zero;
+                raw[q].w = fresh[q].w | zero;
+            }
+            ptr += 32 * DEPTH;
+        }
+    }
+    __syncthreads();
+    // checksum: sum of all 16-bit fields vs the adds this CTA made
+    unsigned long long fsum = 0, asum = nadds;
+    for (int i = tid; i < 32768; i += 1024) {
+        const uint32_t v = words[i];
+        fsum += (v & 0xFFFFu) + (v >> 16);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        fsum += __shfl_down_sync(0xffffffffu, fsum, d);
+        asum += __shfl_down_sync(0xffffffffu, asum, d);
+    }
+    if (lane == 0) {
+        s_red[tid >> 5] = fsum;
+        s_red[32 + (tid >> 5)] = asum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long f = 0, a = 0;
+        for (int q = 0; q < 32; q++) {
+            f += s_red[q];
+            a += s_red[32 + q];
+        }
+        flags[blockIdx.x] = (f == a) ? 0u : 1u;
+        s_red[0] = (f == a) ? 0ull : 1ull;
+    }
+    __syncthreads();
+    if (s_red[0] == 0) {
+        const uint4* w4 = reinterpret_cast<const uint4*>(words);
+        uint4* out = reinterpret_cast<uint4*>(partials + (uint64_t)blockIdx.x * 32768);
+        for (int i = tid; i < 32768 / 4; i += 1024) out[i] = w4[i];
+    }
+}
+
+__global__ void smem16c_reduce_kernel(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ flags,
+                                      int nparts, uint32_t* __restrict__ table) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 32768) return;
+    uint32_t lo = 0, hi = 0;
+    for (int p = 0; p < nparts; p++) {
+        if (flags[p]) continue;  // that CTA's table wrapped: smem16_repair_kernel recounts its groups
+        const uint32_t v = partials[(uint64_t)p * 32768 + w];
+        lo += v & 0xFFFFu;
+        hi += v >> 16;
+    }
+    table[w] += lo;
+    table[w + 32768] += hi;
+}
+
+// one CTA per pass-1 CTA; does nothing unless that CTA's checksum failed
+template <int DEPTH>
+__global__ void __launch_bounds__(256)
+smem16_repair_kernel(const uint4* __restrict__ base, uint64_t ngroups, int nparts, const uint32_t* __restrict__ flags,
+                     uint32_t* __restrict__ table) {
+    if (flags[blockIdx.x] == 0) return;
+    if (threadIdx.x == 0) KC_STAT(6);
+    const uint64_t nwarps = (uint64_t)nparts * 32;
+    const uint64_t units = ngroups / DEPTH;
+    const uint64_t upw = (units + nwarps - 1) / nwarps;
+    const uint64_t gb = min((uint64_t)blockIdx.x * 32 * upw, units) * DEPTH;        // the failed CTA's 32 warps
+    const uint64_t ge = min(((uint64_t)blockIdx.x + 1) * 32 * upw, units) * DEPTH;  // own one contiguous run
+    ScanGeom g;
+    g.abase = base;
+    g.lo = 0;
+    g.hi = (ngroups + 1) << 9;  // interior groups: the group behind the last one is readable too (host)
+    g.wlo = gb << 9;
+    g.whi = ge << 9;
+    g.g_begin = gb;
+    g.g_end = ge;
+    g.k = 8;
+    const uint64_t ng = ge - gb;
+    const uint64_t per = (ng + 7) >> 3;
+    const int warp = threadIdx.x >> 5;
+    kc_warp_scan<1>(g, gb + min((uint64_t)warp * per, ng), gb + min((uint64_t)(warp + 1) * per, ng),
+                    [&](const LaneWindow<1>& lw, uint64_t) {
+                        const uint32_t ok = lw.ok & 0xFFFFu;
+                        if (ok == 0) return;
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            if (ok & (1u << j)) atomicAdd(&table[lw.code32(j, 0xFFFFu)], 1u);
+                    });
+}
+
+// ---------------------------------------------------------------------------
 // partition path
 // ---------------------------------------------------------------------------
 template <int K_, int A_, int KB_, int CAP_>
@@ -556,7 +721,7 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
 
 template <typename S>
 static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
-                           uint32_t* d_table, cudaStream_t st) {
+                           uint32_t* d_table, cudaStream_t st, bool defer) {
     using C = typename S::Cfg;
     const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, C::K);
     // interior groups [G0, G1): fully readable, all their windows requested, and
@@ -597,7 +762,8 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     const size_t smem1 = (size_t)(2 * C::P + C::P * C::CAP) * sizeof(uint32_t);
     const size_t smem2 = (size_t)C::NBINS * sizeof(uint32_t);
     const uint4* base = g.abase + (G0 << 5);
-    static const int ablate = getenv("KC_PART_ABLATE") ? atoi(getenv("KC_PART_ABLATE")) : 0;  // measurement aid
+    static const int ablate_env = getenv("KC_PART_ABLATE") ? atoi(getenv("KC_PART_ABLATE")) : 0;  // measurement aid
+    const int ablate = defer ? 3 : ablate_env;
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
 #define KC_LAUNCH_SCATTER(ABL)                                                                              \
     do {                                                                                                    \
@@ -633,9 +799,10 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     return rc;
 }
 
-// k = 8 path: interior groups through dense_smem16_kernel, the rest through dense_direct
+// k = 8 path: interior groups through dense_smem16_kernel (or its checksum variant), the rest
+// through dense_direct
 static int dense_smem16(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
-                        uint32_t* d_table, cudaStream_t st) {
+                        uint32_t* d_table, cudaStream_t st, bool checksum) {
     constexpr int DEPTH = 2;
     const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, 8);
     const uint64_t G0 = (max(g.lo, g.wlo) + 511) >> 9;
@@ -649,17 +816,30 @@ static int dense_smem16(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64
     const uint64_t tail_begin = ((G0 + ngroups) << 9) - shift;  // every window start of the interior groups is counted
     const uint64_t want = (ngroups / DEPTH + 31) / 32;
     const int grid = (int)(want > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want);
-    int rc = kc_scratch_reserve(ctx, (size_t)grid * 32768 * sizeof(uint32_t));
+    int rc = kc_scratch_reserve(ctx, ((size_t)grid * 32768 + 1024) * sizeof(uint32_t));
     if (rc) return rc;
     uint32_t* partials = (uint32_t*)ctx->scratch;
+    uint32_t* flags = partials + (size_t)grid * 32768;  // checksum variant: one word per CTA (grid <= 1024)
     const size_t smem = 32768 * sizeof(uint32_t);
-    KC_CUDA(ctx, cudaFuncSetAttribute(dense_smem16_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint4* base = g.abase + (G0 << 5);
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
-    KC_LAUNCH(dense_smem16_kernel<DEPTH>, grid, 1024, smem, st, g.abase + (G0 << 5), ngroups, d_table, partials);
-    KC_LAUNCH_CHECK(ctx, "dense_smem16_kernel");
-    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
-    KC_LAUNCH(smem16_reduce_kernel, 32768 / 256, 256, 0, st, partials, grid, d_table);
-    KC_LAUNCH_CHECK(ctx, "smem16_reduce_kernel");
+    if (checksum) {
+        KC_CUDA(ctx, cudaFuncSetAttribute(dense_smem16c_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KC_LAUNCH(dense_smem16c_kernel<DEPTH>, grid, 1024, smem, st, base, ngroups, partials, flags);
+        KC_LAUNCH_CHECK(ctx, "dense_smem16c_kernel");
+        if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
+        KC_LAUNCH(smem16c_reduce_kernel, 32768 / 256, 256, 0, st, partials, flags, grid, d_table);
+        KC_LAUNCH_CHECK(ctx, "smem16c_reduce_kernel");
+        KC_LAUNCH(smem16_repair_kernel<DEPTH>, grid, 256, 0, st, base, ngroups, grid, flags, d_table);
+        KC_LAUNCH_CHECK(ctx, "smem16_repair_kernel");
+    } else {
+        KC_CUDA(ctx, cudaFuncSetAttribute(dense_smem16_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KC_LAUNCH(dense_smem16_kernel<DEPTH>, grid, 1024, smem, st, base, ngroups, d_table, partials);
+        KC_LAUNCH_CHECK(ctx, "dense_smem16_kernel");
+        if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
+        KC_LAUNCH(smem16_reduce_kernel, 32768 / 256, 256, 0, st, partials, grid, d_table);
+        KC_LAUNCH_CHECK(ctx, "smem16_reduce_kernel");
+    }
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
     const bool timing = ctx->timing;
     ctx->timing = false;
@@ -679,8 +859,19 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (!ctx) return KC_ERR_INVALID;
     if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
     if (!d_table || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
-    if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION)
+    if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION && algo != KC_DENSE_SMEM16C &&
+        algo != KC_DENSE_PARTITION_DEFER)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown dense algo %d", algo);
+    if (algo == KC_DENSE_SMEM16C) {
+        if (k != 8) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_SMEM16C is the k = 8 path (k=%d)", k);
+        DeviceGuard dg8(ctx->device);
+        if (nbytes < 8) return KC_OK;
+        if (win_end > nbytes - 7) win_end = nbytes - 7;
+        if (win_begin >= win_end) return KC_OK;
+        return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream, true);
+    }
+    const bool defer = (algo == KC_DENSE_PARTITION_DEFER);
+    if (defer) algo = KC_DENSE_PARTITION;
     DeviceGuard dg(ctx->device);
     if (nbytes < (uint64_t)k) return KC_OK;
     const uint64_t nwin = nbytes - k + 1;
@@ -695,7 +886,7 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         can_part && (algo == KC_DENSE_PARTITION ||
                      (algo == KC_DENSE_AUTO && (win_end - win_begin) >= g_partition_min_windows));
     if (k == 8 && algo == KC_DENSE_AUTO && (win_end - win_begin) >= (1ull << 22))
-        return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+        return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, st, false);
     if (use_part) {
         // PartCfg<K, A, KB, CAP>: A windows per 32-bit record (K + A - 1 <= 16 bases), KB key bits
         // inside the bases all A windows share, CAP records per chunk.  k = 12 shape measured on
@@ -703,11 +894,11 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         static const int shape = getenv("KC_PART_SHAPE") ? atoi(getenv("KC_PART_SHAPE")) : 0;  // tuning aid
         switch (k) {
             case 12:
-                if (shape == 1) return dense_partition<ScatterShape<PartCfg<12, 5, 11, 24>, 1024, 1, 2>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
-                return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
-            case 11: return dense_partition<ScatterShape<PartCfg<11, 6, 11, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
-            case 10: return dense_partition<ScatterShape<PartCfg<10, 7, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
-            default: return dense_partition<ScatterShape<PartCfg<9, 6, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st);
+                if (shape == 1) return dense_partition<ScatterShape<PartCfg<12, 5, 11, 24>, 1024, 1, 2>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
+                return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
+            case 11: return dense_partition<ScatterShape<PartCfg<11, 6, 11, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
+            case 10: return dense_partition<ScatterShape<PartCfg<10, 7, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
+            default: return dense_partition<ScatterShape<PartCfg<9, 6, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
         }
     }
     return dense_direct(ctx, g, d_table, st);

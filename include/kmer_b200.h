@@ -170,6 +170,10 @@ KC_API int kc_count_dense_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes
 #define KC_DENSE_AUTO 0      /* engine picks by k and size                    */
 #define KC_DENSE_DIRECT 1    /* smem-privatised (small k) / global-atomic bins */
 #define KC_DENSE_PARTITION 2 /* two-pass radix partition + smem sub-tables     */
+/* Variants written after round 1's GPU budget was spent (CPU-emulator verified, never picked by
+ * KC_DENSE_AUTO until a B200 has measured them):                                              */
+#define KC_DENSE_SMEM16C 3   /* k = 8: non-returning shared adds + per-CTA checksum + repair   */
+#define KC_DENSE_PARTITION_DEFER 4 /* partition path, full-bin records retried before REDs     */
 KC_API int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
                                       uint64_t win_begin, uint64_t win_end, int k,
                                       uint32_t* d_table, int algo, void* stream);

@@ -76,6 +76,19 @@ def test_partition_deferred_retry_variant(seed):
     run_case("dense", 9, 200_000, 2, "dirty", 50 + seed, 3, seed=0, sms=2, KC_PART_ABLATE=3)
 
 
+def test_k8_checksum_variant():
+    """KC_DENSE_SMEM16C (algo 3): non-returning shared adds, per-CTA checksum, repair of the CTAs
+    whose 16-bit fields wrapped.  Uniform input: no CTA is repaired; one-bin inputs: every CTA is."""
+    st = emu_stats(run_case("dense", 8, 4_500_000, 3, "genome", 4, 0))
+    assert st[6] == 0, st
+    st = emu_stats(run_case("dense", 8, 4_400_000, 3, "polyA", 4, 1))
+    assert st[6] >= 4, st          # whole table and the window sub-range: all 4 CTAs each time
+    st = emu_stats(run_case("dense", 8, 4_400_000, 3, "skew", 4, 7))
+    assert st[6] >= 1, st
+    run_case("dense", 8, 4_300_000, 3, "dirty", 5, 2, seed=3, sms=2)
+    run_case("dense", 8, 100_000, 3, "genome", 5, 2)  # too small for the interior kernel: direct path
+
+
 SPARSE = [
     (21, 60_000, 0, "reads", 1, 0),
     (31, 60_000, 0, "dirty", 2, 5),

@@ -52,3 +52,41 @@ def test_sparse_radix_equals_hash_at_scale(ctx, kmerlib):
     kb, cb = b.to_host()
     assert len(a) == len(b) and (ka == kb).all() and (ca == cb).all()
     assert int(ca.astype(np.int64).sum()) == nreads * (150 - k + 1)
+
+
+def _dense(ctx, kmerlib, data, k, algo):
+    import torch
+    table = torch.zeros(kmerlib.num_kmers(k), dtype=torch.int32, device="cuda:0")
+    d = to_dev(data)
+    ctx.count_dense_range(d, data.size, 0, data.size, k, table, algo=algo)
+    torch.cuda.synchronize()
+    return table.cpu().numpy().view(np.uint32)
+
+
+def test_k8_checksum_variant(ctx, kmerlib, oracle):
+    """KC_DENSE_SMEM16C: uniform input (no CTA repaired), one-bin input (every CTA repaired), dirty bytes"""
+    n = 30_000_000
+    genome = oracle.gen_genome(0xB2000002, n, 30, 300, 8, 0, n)
+    poly = np.full(8_000_000, ord("A"), dtype=np.uint8)
+    for data in (genome, poly):
+        want, _ = oracle.count_dense(data, 8)
+        got = _dense(ctx, kmerlib, data, 8, kmerlib.DENSE_SMEM16C)
+        assert (got == want).all()
+
+
+def test_partition_deferred_retry(ctx, kmerlib, oracle):
+    """KC_DENSE_PARTITION_DEFER at k = 9..12 against the oracle, and against the shipped path at 1 Gbp"""
+    import torch
+    n = 40_000_000
+    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
+    for k in (9, 10, 11, 12):
+        want, _ = oracle.count_dense(genome, k)
+        assert (_dense(ctx, kmerlib, genome, k, kmerlib.DENSE_PARTITION_DEFER) == want).all()
+    L = 1 << 30
+    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
+    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    b = torch.zeros_like(a)
+    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
+    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_DEFER)
+    torch.cuda.synchronize()
+    assert bool((a == b).all())

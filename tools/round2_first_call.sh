@@ -8,15 +8,24 @@ mkdir -p gpurun_out
 O=gpurun_out
 echo "== 1. GPU parity tests (the first-run-pending file is last and xfail(strict=False))"
 timeout 900 python -m pytest tests -m gpu -q -x -rxX > $O/r02_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 $O/r02_pytest.log
-echo "== 2. dense k=12: shipped scatter vs deferred retry (KC_PART_ABLATE=3)"
-for A in 0 3; do
-  KC_PART_ABLATE=$A timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_dense_abl$A.log 2> $O/r02_dense_abl$A.err
+echo "== 2. dense k=12: shipped scatter (--algo 0) vs deferred retry (--algo 4)"
+for A in 0 4; do
+  timeout 300 python bench.py --algo $A --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_dense_abl$A.log 2> $O/r02_dense_abl$A.err
   python - <<PY
 import json
 d=json.load(open("$O/r02_dense_abl$A.log"))
-print("ablate=$A ms/step %.4f kernels %s checksum %s" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
+print("algo=$A ms/step %.4f kernels %s checksum %s" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
 PY
 done
+echo "== 2b. k=8 (config 2 and the 3.1 Gbp genome): shipped 16-bit bins vs checksum variant (--algo 3)"
+for W in config2 genome_k8; do for A in 0 3; do
+  timeout 300 python bench.py --workload $W --algo $A --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_${W}_a$A.log 2> $O/r02_${W}_a$A.err
+  python - <<PY
+import json
+d=json.load(open("$O/r02_${W}_a$A.log"))
+print("$W algo=$A ms/step %.4f kernels %s checksum %s" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
+PY
+done; done
 echo "== 3. sparse config 4 at 1/5 scale and full scale: hash vs radix"
 for R in 20000000 0; do for A in hash radix; do
   timeout 600 python bench.py --workload config4 --reads $R --sparse-algo $A --steps 1 --warmup 1 > $O/r02_c4_${A}_$R.log 2> $O/r02_c4_${A}_$R.err
