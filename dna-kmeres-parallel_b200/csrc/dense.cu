@@ -238,11 +238,20 @@ dense_smem16c_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t*
                 uint32_t ok = 0xFFFFu;
                 if (B32) ok = ~(uint32_t)kc_window_bad((uint64_t)B32 | (0xFFFFull << 32), 8) & 0xFFFFu;
                 nadds += (uint32_t)__popc(ok);
+                if (ok == 0xFFFFu) {  // the common case carries no per-window predicate
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if (ok & (1u << j)) {
-                        const uint32_t code = __funnelshift_r(p0, p1, 2 * j) & 0xFFFFu;
-                        smem_red_add(s_words + (code & 0x7FFFu) * 4, (code >> 15) * 0xFFFFu + 1u);  // +1 or +0x10000
+                    for (int j = 0; j < 16; j++) {
+                        // code << 2 straight from the funnel shifter: word address = bits [2,17), half = bit 17
+                        const uint32_t c4 = j ? __funnelshift_r(p0, p1, 2 * j - 2) : (p0 << 2);
+                        smem_red_add(s_words + (c4 & 0x1FFFCu), (c4 & 0x20000u) ? 0x10000u : 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if (ok & (1u << j)) {
+                            const uint32_t c4 = j ? __funnelshift_r(p0, p1, 2 * j - 2) : (p0 << 2);
+                            smem_red_add(s_words + (c4 & 0x1FFFCu), (c4 & 0x20000u) ? 0x10000u : 1u);
+                        }
                     }
                 }
                 cur16 = nxt;
