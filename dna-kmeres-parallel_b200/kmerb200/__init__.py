@@ -74,6 +74,7 @@ def lib():
         "kc_kmer_string": (i32, [u64, i32, C.c_char_p]),
         "kc_import_seqs": (i32, [C.c_char_p, i32, C.c_long, C.POINTER(vp)]),
         "kc_import_seqs_mem": (i32, [C.c_char_p, C.c_size_t, i32, C.c_long, C.POINTER(vp)]),
+        "kc_import_seqs_mem_threads": (i32, [C.c_char_p, C.c_size_t, i32, i32, C.POINTER(vp)]),
         "kc_seqset_free": (None, [vp]),
         "kc_seqset_num_seqs": (u32, [vp]),
         "kc_seqset_num_ids": (u32, [vp]),
@@ -211,6 +212,15 @@ class SeqSet:
             fasta = fasta.encode("latin-1")
         h = C.c_void_p()
         _check0(lib().kc_import_seqs_mem(fasta, len(fasta), mode, max_seqs, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_memory_threads(cls, fasta, mode=IMPORT_BLANKLINE, nthreads=0):
+        """the multi-threaded parser (no record limit); nthreads <= 0: one per core"""
+        if isinstance(fasta, str):
+            fasta = fasta.encode("latin-1")
+        h = C.c_void_p()
+        _check0(lib().kc_import_seqs_mem_threads(fasta, len(fasta), mode, nthreads, C.byref(h)))
         return cls(h)
 
     @property

@@ -123,6 +123,11 @@ KC_API int kc_import_seqs(const char* path, int mode, long max_seqs, kc_seqset**
 /* same parser over an in-memory FASTA image */
 KC_API int kc_import_seqs_mem(const char* fasta, size_t nbytes, int mode, long max_seqs,
                               kc_seqset** out);
+/* same result as kc_import_seqs_mem with max_seqs <= 0, parsed by `nthreads` host threads
+ * (<= 0: one per core, at least 4 MiB of text each).  kc_import_seqs[_mem] use it by
+ * themselves for inputs of 32 MiB and more ("next" row f2: ingest at speed).           */
+KC_API int kc_import_seqs_mem_threads(const char* fasta, size_t nbytes, int mode, int nthreads,
+                                      kc_seqset** out);
 KC_API void kc_seqset_free(kc_seqset* s);
 KC_API uint32_t kc_seqset_num_seqs(const kc_seqset* s);
 KC_API uint32_t kc_seqset_num_ids(const kc_seqset* s);

@@ -95,6 +95,50 @@ def test_import_seqs_random_vs_oracle(kmerlib, oracle):
                 assert s.data == r["data"] and s.offsets.tolist() == r["offsets"].tolist(), (text, mode, mx)
 
 
+def test_import_seqs_threads_equal_serial(kmerlib, oracle, golden):
+    """kc_import_seqs_mem_threads (f2: ingest at speed) == the serial loader == the oracle, for
+    every thread count: chunks start in all three parser states, records span chunks, files end
+    inside a record / after a blank line / on a header."""
+    rng = np.random.default_rng(23)
+    pieces = [b">h\n", b"ACGT\n", b"NNAC\n", b"\n", b"\r\n", b"acgt\n", b">x y\n", b"GG|TT\n", b"T", b"\n\n", b"CCC\r\n",
+              b"ACGTACGTACGTACGTACGT\n", b">\n", b"|\n"]
+    texts = [case["fasta"].encode("latin-1") for case in golden["loader"]]
+    for trial in range(120):
+        texts.append(b"".join(pieces[i] for i in rng.integers(0, len(pieces), size=int(rng.integers(0, 60)))))
+    for text in texts:
+        for mode in (0, 1):
+            want = kmerlib.SeqSet.from_memory(text, mode, 0)  # serial path (input below 32 MiB)
+            r = oracle.import_seqs_mem(text, mode, 0)
+            assert want.data == r["data"] and want.offsets.tolist() == r["offsets"].tolist()
+            for nt in (1, 2, 3, 5, 9):
+                s = kmerlib.SeqSet.from_memory_threads(text, mode, nt)
+                assert s.num_seqs == want.num_seqs and s.ids == want.ids, (text, mode, nt)
+                assert s.data == want.data and s.offsets.tolist() == want.offsets.tolist(), (text, mode, nt)
+                s.close()
+            want.close()
+
+
+def test_import_seqs_large_file_takes_threaded_path(kmerlib, oracle, tmp_path):
+    """40 MiB FASTA (70-column lines, blank-line separated records) through kc_import_seqs: the
+    threaded parser is picked by size; result equals the oracle's serial restatement."""
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(40):
+        seq = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, 1 << 20)].tobytes()
+        lines = b"\n".join(seq[j:j + 70] for j in range(0, len(seq), 70))
+        recs.append(b">chr%d test\n" % i + lines + b"\n\n")
+    text = b"".join(recs)
+    assert len(text) > (32 << 20)
+    p = tmp_path / "big.fasta"
+    p.write_bytes(text)
+    for mode in (0, 1):
+        s = kmerlib.SeqSet.from_file(str(p), mode, 0)
+        r = oracle.import_seqs_mem(text, mode, 0)
+        assert s.num_seqs == r["num_seqs"] == 40 and s.ids == r["ids"]
+        assert s.data == r["data"] and s.offsets.tolist() == r["offsets"].tolist()
+        s.close()
+
+
 def test_import_seqs_live_reference(kmerlib, oracle, tmp_path):
     ref = oracle.ref(3)
     if ref is None:
