@@ -53,6 +53,8 @@ def lib():
         L.kc_sparse_size.restype = C.c_uint64
         L.kc_sparse_size.argtypes = [C.c_void_p]
         L.kc_sparse_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kc_kmer_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.kc_gen_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.kc_gen_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
                                     C.c_uint64, C.c_void_p, C.c_void_p]
         L.kc_gen_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
@@ -200,7 +202,54 @@ def case_sparse(args):
     print("ok sparse", *args, "distinct", keys.size)
 
 
-CASES = {"dense": case_dense, "sparse": case_sparse}
+def case_perseq(args):
+    """reference-shaped per-sequence table sums[4^k][n] (kernels.h:113-144 layout) + the distance step"""
+    k, nseq, seed = int(args[0]), int(args[1]), int(args[2])
+    O = _oracle()
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(b"ACGTACGTACGTACGTNa", dtype=np.uint8)
+    seqs = [alpha[rng.integers(0, alpha.size, int(rng.integers(0, 40_000 if i % 7 == 0 else 300)))] for i in range(nseq)]
+    data = np.concatenate([np.concatenate([s, np.zeros(1, np.uint8)]) for s in seqs])
+    offs = np.cumsum([0] + [len(s) + 1 for s in seqs]).astype(np.int64)
+    ctx = EmuContext()
+    b1, d_data = ctx.upload(data, 5)
+    b2, d_off = ctx.upload(offs)
+    nb = (4 << (2 * k)) * nseq
+    d_sums = ctx.alloc(nb)
+    ctx.check(ctx.L.kc_count_per_seq(ctx.h, d_data, d_off, nseq, k, d_sums))
+    got = ctx.download(d_sums, nb, np.int32).reshape(4 ** k, nseq)
+    want, _ = O.count_per_seq(data, offs, k)
+    assert (got == want).all(), "per-seq k=%d: %d cells differ" % (k, int((got != want).sum()))
+    npairs = nseq * (nseq - 1) // 2
+    d_dist = ctx.alloc(4 * max(npairs, 1))
+    ctx.check(ctx.L.kc_kmer_distance(ctx.h, d_sums, d_off, nseq, k, d_dist))
+    dist = ctx.download(d_dist, 4 * npairs, np.float32)
+    wd = O.distance(want, offs, k)
+    assert dist.tobytes() == np.asarray(wd, dtype=np.float32).tobytes(), "distance differs"
+    ctx.close()
+    print("ok perseq", *args)
+
+
+def case_gen(args):
+    """the HBM generators against the oracle's (same bytes on both sides)"""
+    n, seed = int(args[0]), int(args[1])
+    O = _oracle()
+    ctx = EmuContext()
+    d = ctx.alloc(n + 3)
+    p = C.c_void_p(d.value + 3)  # misaligned destination: the scalar tail path
+    ctx.check(ctx.L.kc_gen_genome(ctx.h, seed, 10 * n, 7, 90, 12, 3 * n, n, p, None))
+    assert (ctx.download(p, n, np.uint8) == O.gen_genome(seed, 10 * n, 7, 90, 12, 3 * n, n)).all()
+    ctx.check(ctx.L.kc_gen_bases(ctx.h, seed, 123, n, d, None))
+    assert (ctx.download(d, n, np.uint8) == O.gen_bases(seed, 123, n)).all()
+    nreads = n // 151
+    d2 = ctx.alloc(nreads * 151)
+    ctx.check(ctx.L.kc_gen_reads(ctx.h, seed, 50_000, 150, 200, 17, nreads, d2, None))
+    assert (ctx.download(d2, nreads * 151, np.uint8) == O.gen_reads(seed, 50_000, 150, 200, 17, nreads)).all()
+    ctx.close()
+    print("ok gen", *args)
+
+
+CASES = {"dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

@@ -142,3 +142,10 @@ def test_sparse_radix_overflow_falls_back_to_hash():
 def test_sparse_radix_production_shape():
     # 1024 x 1024 partitions: mostly empty leaves at this size, but the shipped geometry
     run_case("sparse", 21, 40_000, RADIX | NOFB, "readsU", 9, 0, seed=0, sms=2)
+
+
+def test_perseq_distance_and_generators_on_emulator():
+    run_case("perseq", 3, 37, 1)     # shared-memory bins per (sequence, tile) segment
+    run_case("perseq", 6, 9, 2)
+    run_case("perseq", 8, 5, 3)      # global atomics
+    run_case("gen", 200_000, 0xB2000003)
