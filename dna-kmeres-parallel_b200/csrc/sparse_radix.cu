@@ -71,21 +71,24 @@ struct Stager {
     static constexpr size_t SMEM_BYTES = (size_t)P * 2 * 4 + (size_t)P * 4 + (size_t)P * 2 * 64;
 
     uint32_t s_state, s_cur, s_buf;  // shared-window addresses
-    RecT* region;                    // this CTA's slab: region[p * cap + i]
+    RecT* region;                    // this CTA's region of partition p: region[p * pstride + i], i < cap
+    uint64_t pstride;                // records between the regions of consecutive partitions
     uint32_t cap;                    // records per (CTA, partition) region; multiple of CAP
     uint32_t* failed;
 
-    __device__ __forceinline__ void init(uint32_t* smem_words, RecT* region_, uint32_t cap_, uint32_t* failed_) {
+    __device__ __forceinline__ void init(uint32_t* smem_words, RecT* region_, uint64_t pstride_, uint32_t cap_,
+                                         uint32_t* failed_) {
         s_state = (uint32_t)__cvta_generic_to_shared(smem_words);
         s_cur = s_state + P * 2 * 4;
         s_buf = s_cur + P * 4;
         region = region_;
+        pstride = pstride_;
         cap = cap_;
         failed = failed_;
         for (int b = threadIdx.x; b < P; b += blockDim.x) {
             smem_words[2 * b] = 0;
             smem_words[2 * b + 1] = 0;
-            smem_words[2 * P + b] = b * cap_;
+            smem_words[2 * P + b] = 0;  // cur[p]: records of partition p already written by this CTA
         }
     }
 
@@ -97,8 +100,8 @@ struct Stager {
         smem_st(s_state + bin * 4, 0u);  // every slot has been read: the bin is free again
         const uint32_t p = bin >> 1;
         const uint32_t pos = smem_atom_add(s_cur + p * 4, (uint32_t)CAP);
-        if (pos + CAP <= (p + 1) * cap) {
-            uint4* dst = reinterpret_cast<uint4*>(region + pos);  // 64-byte aligned
+        if (pos + CAP <= cap) {
+            uint4* dst = reinterpret_cast<uint4*>(region + (uint64_t)p * pstride + pos);  // 64-byte aligned
 #pragma unroll
             for (int q = 0; q < 4; q++) dst[q] = v[q];
         } else {
@@ -137,8 +140,8 @@ struct Stager {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const RecT* bufp = reinterpret_cast<const RecT*>(smem_words + 3 * P);
         for (int p = warp; p < P; p += nw) {
-            const uint32_t base_off = p * cap;
-            uint32_t pos = smem_words[2 * P + p] - base_off;  // chunks written so far (may exceed cap after a failure)
+            const uint64_t base_off = (uint64_t)p * pstride;
+            uint32_t pos = smem_words[2 * P + p];  // chunks written so far (may exceed cap after a failure)
 #pragma unroll
             for (int x = 0; x < 2; x++) {
                 uint32_t c = smem_words[2 * p + x] & 0xFFFFFFu;  // < CAP: full bins were flushed by their last writer
@@ -186,7 +189,9 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
     KC_DYN_SMEM(uint32_t, smem);
     using St = Stager<R1T, Shape::P1>;
     St st;
-    st.init(smem, slabs1 + (uint64_t)blockIdx.x * Shape::P1 * cap1, cap1, &ctl->failed);
+    // slabs are partition-major, slabs1[p][cta][cap1]: the regions of a RANGE of partitions are one
+    // contiguous block, which is what the multi-GPU path sends to the rank that owns the range
+    st.init(smem, slabs1 + (uint64_t)blockIdx.x * cap1, (uint64_t)gridDim.x * cap1, cap1, &ctl->failed);
     __syncthreads();
     const int k = g.k;
     const int r1bits = 2 * k - Shape::KB1;
@@ -194,12 +199,13 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
     const uint64_t r1mask = (1ull << r1bits) - 1ull;
     const uint32_t pref = threadIdx.x >> 5;
 
+    // groups are dealt out evenly (warp w: [w n / W, (w+1) n / W)): the private regions are sized
+    // for an even split, and a ceil-sized share would leave the last CTA idle on small inputs
     const uint64_t ngroups = g.g_end - g.g_begin;
     const uint64_t nwarps = (uint64_t)gridDim.x * (SP_THREADS / 32);
-    const uint64_t gpw = (ngroups + nwarps - 1) / nwarps;
     const uint64_t w = (uint64_t)blockIdx.x * (SP_THREADS / 32) + (threadIdx.x >> 5);
-    const uint64_t gb = g.g_begin + min(w * gpw, ngroups);
-    const uint64_t ge = g.g_begin + min((w + 1) * gpw, ngroups);
+    const uint64_t gb = g.g_begin + w * ngroups / nwarps;
+    const uint64_t ge = g.g_begin + (w + 1) * ngroups / nwarps;
     kc_warp_scan<HALO>(g, gb, ge, [&](const LaneWindow<HALO>& lw, uint64_t) {
         // a loop over the set bits, not 16 unrolled copies: the staging code is long and 16
         // copies of it are 56 KB of SASS, more than the instruction cache holds
@@ -249,7 +255,8 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 template <typename Shape, typename R1T, typename R2T>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict__ counts1, uint32_t cap1,
-               uint32_t nregions, R2T* __restrict__ scratch2, uint32_t cap2, uint64_t* __restrict__ tmp_keys,
+               uint32_t grid1, uint32_t nsrc, uint32_t nparts, uint32_t part_first, R2T* __restrict__ scratch2,
+               uint32_t cap2, uint64_t* __restrict__ tmp_keys,
                uint32_t* __restrict__ tmp_counts, uint64_t out_cap, unsigned long long* __restrict__ leaf_base,
                uint32_t* __restrict__ leaf_n, SpCtl* ctl) {
     KC_DYN_SMEM(uint32_t, smem);
@@ -278,14 +285,22 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
         __syncthreads();  // previous partition fully done (s_part, staging area, s_sorted reusable)
         if (tid == 0) s_part = atomicAdd(&ctl->work, 1u);
         St st;
-        st.init(smem, my_scratch, cap2, &ctl->failed);
+        st.init(smem, my_scratch, (uint64_t)cap2, cap2, &ctl->failed);
         // records of this partition (sum over the pass-1 CTAs' regions)
         __syncthreads();
-        const uint32_t p1 = s_part;
-        if (p1 >= (uint32_t)Shape::P1) break;
+        // Local partition q of `nparts`; its records lie in nsrc * grid1 regions: source rank s sent
+        // the block [s][q][cta][cap1] (single GPU: nsrc = 1, nparts = P1, part_first = 0).
+        const uint32_t q1 = s_part;
+        if (q1 >= nparts) break;
+        const uint32_t p1 = part_first + q1;  // global partition = top KB1 bits of the codes in it
+        const uint32_t nregions = nsrc * grid1;
+        auto region_index = [&](uint32_t reg) {  // reg = s * grid1 + cta
+            const uint32_t sr = reg / grid1, cta = reg - sr * grid1;
+            return ((uint64_t)sr * nparts + q1) * grid1 + cta;
+        };
         {
             uint32_t mine = 0;
-            for (uint32_t r = tid; r < nregions; r += SP_THREADS) mine += counts1[(uint64_t)p1 * nregions + r];
+            for (uint32_t r = tid; r < nregions; r += SP_THREADS) mine += counts1[region_index(r)];
             uint32_t tot;
             block_excl_scan(mine, s_warp, &tot);
             if (tid == 0) s_np = tot;
@@ -312,8 +327,9 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
         };
         constexpr uint32_t RPV = 16 / sizeof(R1T);  // records per 128-bit load
         for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
-            const uint32_t n = counts1[(uint64_t)p1 * nregions + reg];
-            const R1T* src = slabs1 + ((uint64_t)reg * Shape::P1 + p1) * cap1;  // 64-byte aligned
+            const uint64_t ri = region_index(reg);
+            const uint32_t n = counts1[ri];
+            const R1T* src = slabs1 + ri * cap1;  // 64-byte aligned
             const uint4* src4 = reinterpret_cast<const uint4*>(src);
             const uint32_t nv = n / RPV;
             for (uint32_t i = lane; i < nv; i += 64) {  // two 128-bit loads in flight per lane
@@ -393,8 +409,8 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
                 const unsigned long long base = atomicAdd(&ctl->out_cursor, (unsigned long long)leaf_runs);
                 s_base = base;
                 if (base + leaf_runs <= out_cap) {
-                    leaf_base[(uint64_t)p1 * Shape::P2 + p2] = base;
-                    leaf_n[(uint64_t)p1 * Shape::P2 + p2] = leaf_runs;
+                    leaf_base[(uint64_t)q1 * Shape::P2 + p2] = base;
+                    leaf_n[(uint64_t)q1 * Shape::P2 + p2] = leaf_runs;
                 } else {
                     atomicOr(&ctl->failed, (uint32_t)SP_FAIL_RUNLIST);  // temporary list full; leaf_n stays 0
                 }
@@ -504,50 +520,61 @@ uint64_t region_records(uint64_t mean, int chunk, int slack_div, int sigmas) {
     return (c + chunk - 1) / chunk * chunk;
 }
 
-template <typename Shape, typename R1T, typename R2T, int HALO>
-int run_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
+// The three stages of the host side.  A single GPU runs them back to back (kc_sparse_radix);
+// the multi-GPU path runs `scatter` on every rank, exchanges the slab blocks of each rank's
+// partition range with ONE all-to-all (kmerb200/distributed.py), and runs `count` on what it
+// received — every rank then owns a disjoint, sorted range of codes and nothing is merged.
+template <typename Shape, typename R1T, int HALO>
+int run_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs, uint32_t* d_counts,
+                SpCtl* ctl) {
     using St1 = Stager<R1T, Shape::P1>;
+    cudaStream_t st = ctx->stream;
+    const int k = plan->k;
+    const uint64_t nwin = nbytes >= (uint64_t)k ? nbytes - k + 1 : 0;
+    KC_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(SpCtl), st));
+    if (nwin == 0) {  // nothing to scan: every region is empty
+        KC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)plan->counts_bytes, st));
+        return KC_OK;
+    }
+    const ScanGeom g = kc_make_geom(d_data, nbytes, 0, nwin, k);
+    const size_t smem1 = St1::SMEM_BYTES;
+    auto kern = sp_scatter_kernel<Shape, R1T, HALO>;
+    KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    KC_LAUNCH(kern, (int)plan->grid, SP_THREADS, smem1, st, g, (R1T*)d_slabs, d_counts, (uint32_t)plan->region_records, ctl);
+    KC_LAUNCH_CHECK(ctx, "sp_scatter_kernel");
+    return KC_OK;
+}
+
+template <typename Shape, typename R1T, typename R2T>
+int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+              uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, kc_sparse** out, int* failed) {
     using St2 = Stager<R2T, Shape::P2>;
     cudaStream_t st = ctx->stream;
-    const uint64_t nwin = nbytes - k + 1;
-    const ScanGeom g = kc_make_geom(d_data, nbytes, 0, nwin, k);
-    const uint64_t ngroups = g.g_end - g.g_begin;
-    const uint64_t want1 = (ngroups + 31) / 32;
-    const int grid1 = (int)(want1 < 1 ? 1 : (want1 > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want1));
-    const int grid2 = ctx->sm_count < Shape::P1 ? ctx->sm_count : Shape::P1;
-    const uint64_t cap1 = region_records(nwin / ((uint64_t)Shape::P1 * grid1) + 1, St1::CAP, 8, 8);
-    const uint64_t part_mean = nwin / Shape::P1 + 1;
+    const int k = plan->k;
+    const int grid2 = ctx->sm_count < (int)nparts ? ctx->sm_count : (int)nparts;
+    const uint64_t part_mean = (uint64_t)nsrc * plan->max_windows / Shape::P1 + 1;
     const uint64_t cap2 = region_records((part_mean + part_mean / 8) / Shape::P2 + 1, St2::CAP, 4, 16);
-    if ((uint64_t)Shape::P1 * cap1 >= (1ull << 32) || (uint64_t)Shape::P2 * cap2 >= (1ull << 32))
-        return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: region too large");
-    const uint64_t nleaves = (uint64_t)Shape::P1 * Shape::P2;
-
+    if ((uint64_t)Shape::P2 * cap2 >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: leaf region too large");
+    const uint64_t nleaves = (uint64_t)nparts * Shape::P2;
     auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
     const size_t b_ctl = pad(sizeof(SpCtl));
-    const size_t b_counts1 = pad((size_t)Shape::P1 * grid1 * 4);
-    const size_t b_leaf_n = pad(nleaves * 4);
-    const size_t b_leaf_base = pad(nleaves * 8);
-    const size_t b_leaf_off = pad(nleaves * 8);
-    const size_t b_slabs1 = pad((size_t)grid1 * Shape::P1 * cap1 * sizeof(R1T));
+    const size_t b_leaf_n = pad(nleaves * 4), b_leaf_base = pad(nleaves * 8), b_leaf_off = pad(nleaves * 8);
     const size_t b_scratch2 = pad((size_t)grid2 * Shape::P2 * cap2 * sizeof(R2T));
-    const size_t fixed = b_ctl + b_counts1 + b_leaf_n + b_leaf_base + b_leaf_off + b_slabs1 + b_scratch2;
-    int rc = kc_scratch_reserve(ctx, fixed);
-    if (rc) return rc;
-    char* base = (char*)ctx->scratch;
-    SpCtl* ctl = (SpCtl*)base;
-    uint32_t* counts1 = (uint32_t*)(base + b_ctl);
-    uint32_t* leaf_n = (uint32_t*)((char*)counts1 + b_counts1);
+    if (b_ctl + b_leaf_n + b_leaf_base + b_leaf_off + b_scratch2 > work_bytes)
+        return kc_set_error(ctx, KC_ERR_INVALID, "sparse radix: internal work area too small");
+    SpCtl* ctl = (SpCtl*)work;
+    uint32_t* leaf_n = (uint32_t*)(work + b_ctl);
     unsigned long long* leaf_base = (unsigned long long*)((char*)leaf_n + b_leaf_n);
     unsigned long long* leaf_off = (unsigned long long*)((char*)leaf_base + b_leaf_base);
-    R1T* slabs1 = (R1T*)((char*)leaf_off + b_leaf_off);
-    R2T* scratch2 = (R2T*)((char*)slabs1 + b_slabs1);
+    R2T* scratch2 = (R2T*)((char*)leaf_off + b_leaf_off);
 
     // temporary run list: as many entries as fit in 45 % of what is free now (the final arrays
     // need the same again), never more than one per window
     size_t free_b = 0, total_b = 0;
     KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     uint64_t out_cap = (uint64_t)(free_b / 100 * 45) / 12;
-    if (out_cap > nwin) out_cap = nwin;
+    const uint64_t most = (uint64_t)nsrc * plan->max_windows + 1024;
+    if (out_cap > most) out_cap = most;
     if (out_cap < 1024) return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: no device memory left for the run list");
     DevMem tkeys, tcounts;
     if (tkeys.alloc(out_cap * 8) || tcounts.alloc(out_cap * 4)) {
@@ -556,21 +583,14 @@ int run_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse
     }
     KC_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(SpCtl), st));
     KC_CUDA(ctx, cudaMemsetAsync(leaf_n, 0, nleaves * 4, st));
-
-    const size_t smem1 = St1::SMEM_BYTES;
-    {
-        auto kern = sp_scatter_kernel<Shape, R1T, HALO>;
-        KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        KC_LAUNCH(kern, grid1, SP_THREADS, smem1, st, g, slabs1, counts1, (uint32_t)cap1, ctl);
-        KC_LAUNCH_CHECK(ctx, "sp_scatter_kernel");
-    }
     constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
     const size_t smem2 = St2::SMEM_BYTES + 1024 * 4 + (size_t)LEAF_CAP * sizeof(R2T);
     {
         auto kern = sp_leaf_kernel<Shape, R1T, R2T>;
         KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, k, slabs1, counts1, (uint32_t)cap1, (uint32_t)grid1, scratch2,
-                  (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p, out_cap, leaf_base, leaf_n, ctl);
+        KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, k, (const R1T*)d_slabs, d_counts, (uint32_t)plan->region_records,
+                  plan->grid, nsrc, nparts, part_first, scratch2, (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p,
+                  out_cap, leaf_base, leaf_n, ctl);
         KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
     }
     KC_LAUNCH(sp_scan_kernel, 1, SP_THREADS, 0, st, leaf_n, nleaves, leaf_off, ctl);
@@ -603,27 +623,147 @@ int run_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse
     return KC_OK;
 }
 
+// bytes of the work area run_count needs (ctl + leaf directory + level-2 scratch)
 template <typename Shape>
-int dispatch(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
+size_t count_work_bytes(const kc_ctx* ctx, const kc_radix_plan* plan, uint32_t nsrc, uint32_t nparts) {
+    const int rec2 = (2 * plan->k - Shape::KB1 - Shape::KB2) <= 32 ? 4 : 8;
+    const int grid2 = ctx->sm_count < (int)nparts ? ctx->sm_count : (int)nparts;
+    const uint64_t part_mean = (uint64_t)nsrc * plan->max_windows / Shape::P1 + 1;
+    const uint64_t cap2 = region_records((part_mean + part_mean / 8) / Shape::P2 + 1, 64 / rec2, 4, 16);
+    const uint64_t nleaves = (uint64_t)nparts * Shape::P2;
+    auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    return pad(sizeof(SpCtl)) + pad(nleaves * 4) + 2 * pad(nleaves * 8) + pad((size_t)grid2 * Shape::P2 * cap2 * rec2);
+}
+
+template <typename Shape>
+int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t shape_id, kc_radix_plan* plan) {
     const int r1 = 2 * k - Shape::KB1, r2 = r1 - Shape::KB2;
     if (r2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix needs 2k > %d (k=%d)", Shape::KB1 + Shape::KB2, k);
-    if (r1 <= 32) {  // both record levels fit 32 bits
-        return k <= 17 ? run_radix<Shape, uint32_t, uint32_t, 1>(ctx, d_data, nbytes, k, out, failed)
-                       : run_radix<Shape, uint32_t, uint32_t, 2>(ctx, d_data, nbytes, k, out, failed);
-    }
-    if (r2 <= 32) return run_radix<Shape, uint64_t, uint32_t, 2>(ctx, d_data, nbytes, k, out, failed);
-    return run_radix<Shape, uint64_t, uint64_t, 2>(ctx, d_data, nbytes, k, out, failed);
+    if (world < 1 || Shape::P1 % world) return kc_set_error(ctx, KC_ERR_INVALID, "sparse radix: world %u must divide %d partitions", world, Shape::P1);
+    memset(plan, 0, sizeof *plan);
+    plan->k = k;
+    plan->world = world;
+    plan->partitions = Shape::P1;
+    plan->parts_per_rank = Shape::P1 / world;
+    plan->shape = shape_id;
+    plan->rec_bytes = r1 <= 32 ? 4 : 8;
+    plan->max_windows = max_windows;
+    const uint64_t ngroups = (max_windows + k + 511 + 15) / 512 + 1;
+    const uint64_t want1 = (ngroups + 31) / 32;
+    plan->grid = (uint32_t)(want1 < 1 ? 1 : (want1 > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want1));
+    plan->region_records = region_records(max_windows / ((uint64_t)Shape::P1 * plan->grid) + 1, 64 / (int)plan->rec_bytes, 8, 8);
+    if (plan->region_records >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: region too large");
+    plan->slab_bytes = (uint64_t)Shape::P1 * plan->grid * plan->region_records * plan->rec_bytes;
+    plan->counts_bytes = (uint64_t)Shape::P1 * plan->grid * 4;
+    return KC_OK;
+}
+
+template <typename Shape>
+int scatter_dispatch(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs,
+                     uint32_t* d_counts, SpCtl* ctl) {
+    if (plan->rec_bytes == 4)
+        return plan->k <= 17 ? run_scatter<Shape, uint32_t, 1>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl)
+                             : run_scatter<Shape, uint32_t, 2>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl);
+    return run_scatter<Shape, uint64_t, 2>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl);
+}
+
+template <typename Shape>
+int count_dispatch(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+                   uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, kc_sparse** out, int* failed) {
+    const int r2 = 2 * plan->k - Shape::KB1 - Shape::KB2;
+    if (plan->rec_bytes == 4)
+        return run_count<Shape, uint32_t, uint32_t>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+    if (r2 <= 32)
+        return run_count<Shape, uint64_t, uint32_t>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+    return run_count<Shape, uint64_t, uint64_t>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+}
+
+using ShapeShipped = SpShape<10, 10, 20480>;
+using ShapeSmall = SpShape<4, 4, 2048>;  // test shape: small inputs (and the CPU emulator) fill regions and leaves
+
+uint32_t shape_from_env() {
+    static const char* shape = getenv("KC_SPARSE_RADIX_SHAPE");
+    return (shape && shape[0] == 's') ? 1u : 0u;
+}
+
+bool plan_ok(kc_ctx* ctx, const kc_radix_plan* plan) {
+    return ctx && plan && plan->k >= 1 && plan->k <= KC_MAX_K && plan->shape <= 1 && plan->grid >= 1 && plan->region_records >= 1 &&
+           plan->partitions == (plan->shape ? (uint32_t)ShapeSmall::P1 : (uint32_t)ShapeShipped::P1);
 }
 
 }  // namespace
 
-// Called by kc_count_sparse (sparse.cu).  *failed = 1: nothing was produced, recount otherwise.
+extern "C" {
+
+int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world, kc_radix_plan* plan) {
+    if (!ctx || !plan) return KC_ERR_INVALID;
+    if (k < 1 || k > KC_MAX_K) return kc_set_error(ctx, KC_ERR_INVALID, "sparse k must be 1..%d, got %d", KC_MAX_K, k);
+    const uint32_t sh = shape_from_env();
+    return sh ? make_plan<ShapeSmall>(ctx, max_windows_per_rank, k, world, sh, plan)
+              : make_plan<ShapeShipped>(ctx, max_windows_per_rank, k, world, sh, plan);
+}
+
+int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs,
+                            uint32_t* d_counts) {
+    if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_scatter: bad argument");
+    const uint64_t nwin = nbytes >= (uint64_t)plan->k ? nbytes - plan->k + 1 : 0;
+    if (nwin > plan->max_windows) return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_scatter: %llu windows, plan made for %llu", (unsigned long long)nwin, (unsigned long long)plan->max_windows);
+    DeviceGuard dg(ctx->device);
+    int rc = kc_scratch2_reserve(ctx, 256);
+    if (rc) return rc;
+    SpCtl* ctl = (SpCtl*)ctx->scratch2;
+    rc = plan->shape ? scatter_dispatch<ShapeSmall>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl)
+                     : scatter_dispatch<ShapeShipped>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl);
+    if (rc) return rc;
+    SpCtl h;
+    KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h.failed)
+        return kc_set_error(ctx, KC_ERR_TABLE_FULL, "sparse radix scatter overflowed (skewed input):%s%s", (h.failed & 1) ? " partition region" : "",
+                            (h.failed & 2) ? " staging bins" : "");
+    return KC_OK;
+}
+
+int kc_sparse_radix_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+                          uint32_t part_first, uint32_t nparts, kc_sparse** out) {
+    if (!out) return KC_ERR_INVALID;
+    *out = nullptr;
+    if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || nsrc < 1 || nparts < 1 || (uint64_t)part_first + nparts > plan->partitions)
+        return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_count: bad argument");
+    DeviceGuard dg(ctx->device);
+    const size_t wb = plan->shape ? count_work_bytes<ShapeSmall>(ctx, plan, nsrc, nparts) : count_work_bytes<ShapeShipped>(ctx, plan, nsrc, nparts);
+    int rc = kc_scratch2_reserve(ctx, wb);
+    if (rc) return rc;
+    int failed = 0;
+    rc = plan->shape ? count_dispatch<ShapeSmall>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed)
+                     : count_dispatch<ShapeShipped>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed);
+    if (rc) return rc;
+    if (failed)
+        return kc_set_error(ctx, KC_ERR_TABLE_FULL, "sparse radix count overflowed (skewed input):%s%s%s%s", (failed & 1) ? " leaf region" : "",
+                            (failed & 2) ? " staging bins" : "", (failed & 4) ? " leaf buffer" : "", (failed & 8) ? " run list" : "");
+    return KC_OK;
+}
+
+}  // extern "C"
+
+// Single GPU: plan + scatter + count with the slabs in the ctx's scratch.  Called by
+// kc_count_sparse (sparse.cu).  *failed != 0: nothing was produced, the caller recounts.
 int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
     *failed = 0;
     *out = nullptr;
-    // tuning/test aid: "small" = 16 x 16 partitions, so that small inputs (and the CPU
-    // emulator) exercise full regions, leaf sorts and the overflow paths
-    static const char* shape = getenv("KC_SPARSE_RADIX_SHAPE");
-    if (shape && shape[0] == 's') return dispatch<SpShape<4, 4, 2048>>(ctx, d_data, nbytes, k, out, failed);
-    return dispatch<SpShape<10, 10, 20480>>(ctx, d_data, nbytes, k, out, failed);
+    kc_radix_plan plan;
+    int rc = kc_sparse_radix_plan(ctx, nbytes - k + 1, k, 1, &plan);
+    if (rc) return rc;
+    auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    rc = kc_scratch_reserve(ctx, pad((size_t)plan.slab_bytes) + pad((size_t)plan.counts_bytes));
+    if (rc) return rc;
+    void* slabs = ctx->scratch;
+    uint32_t* counts = (uint32_t*)((char*)ctx->scratch + pad((size_t)plan.slab_bytes));
+    rc = kc_sparse_radix_scatter(ctx, d_data, nbytes, &plan, slabs, counts);
+    if (rc == KC_OK) rc = kc_sparse_radix_count(ctx, &plan, slabs, counts, 1, 0, plan.partitions, out);
+    if (rc == KC_ERR_TABLE_FULL) {  // an overflow: the error text says which; the caller falls back
+        *failed = 1;
+        return KC_OK;
+    }
+    return rc;
 }

@@ -90,6 +90,9 @@ def lib():
         "kc_count_dense_range_async": (i32, [vp, vp, u64, u64, u64, i32, vp, i32, vp]),
         "kc_count_dense_host": (i32, [vp, vp, u64, i32, vp]),
         "kc_count_sparse": (i32, [vp, vp, u64, i32, i32, u64, C.POINTER(vp)]),
+        "kc_sparse_radix_plan": (i32, [vp, u64, i32, C.c_uint32, vp]),
+        "kc_sparse_radix_scatter": (i32, [vp, vp, u64, vp, vp, vp]),
+        "kc_sparse_radix_count": (i32, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
         "kc_sparse_free": (None, [vp]),
         "kc_sparse_size": (u64, [vp]),
         "kc_sparse_d_keys": (vp, [vp]),
@@ -261,6 +264,14 @@ class SeqSet:
             pass
 
 
+class RadixPlan(C.Structure):
+    """kc_radix_plan (include/kmer_b200.h)"""
+    _fields_ = [("k", C.c_int32), ("world", C.c_uint32), ("partitions", C.c_uint32), ("parts_per_rank", C.c_uint32),
+                ("grid", C.c_uint32), ("rec_bytes", C.c_uint32), ("shape", C.c_uint32), ("reserved", C.c_uint32),
+                ("max_windows", C.c_uint64), ("region_records", C.c_uint64), ("slab_bytes", C.c_uint64),
+                ("counts_bytes", C.c_uint64)]
+
+
 class Sparse:
     def __init__(self, ctx, handle):
         self._ctx, self._h = ctx, handle
@@ -379,6 +390,31 @@ class Context:
         self._torch().cuda.current_stream().synchronize()
         h = C.c_void_p()
         self._check(lib().kc_count_sparse(self._h, _ptr(d_data), nbytes, k, algo, capacity_hint, C.byref(h)))
+        return Sparse(self, h)
+
+    # ---- stages of KC_SPARSE_RADIX (the multi-GPU path runs an all-to-all between them) ----
+    def radix_plan(self, max_windows, k, world):
+        plan = RadixPlan()
+        self._check(lib().kc_sparse_radix_plan(self._h, max_windows, k, world, C.addressof(plan)))
+        return plan
+
+    def radix_scatter(self, d_data, nbytes, plan):
+        """-> (slabs uint8[plan.slab_bytes], counts int32[plan.counts_bytes / 4]) on this GPU,
+        partition-major; raises KmerError(KC_ERR_TABLE_FULL) when a region overflowed"""
+        torch = self._torch()
+        torch.cuda.current_stream().synchronize()
+        dev = "cuda:%d" % self.device
+        slabs = torch.empty(plan.slab_bytes, dtype=torch.uint8, device=dev)
+        counts = torch.empty(plan.counts_bytes // 4, dtype=torch.int32, device=dev)
+        torch.cuda.current_stream().synchronize()
+        self._check(lib().kc_sparse_radix_scatter(self._h, _ptr(d_data), nbytes, C.addressof(plan), _ptr(slabs), _ptr(counts)))
+        return slabs, counts
+
+    def radix_count(self, plan, slabs, counts, nsrc, part_first, nparts):
+        self._torch().cuda.current_stream().synchronize()
+        h = C.c_void_p()
+        self._check(lib().kc_sparse_radix_count(self._h, C.addressof(plan), _ptr(slabs), _ptr(counts), nsrc, part_first, nparts,
+                                                C.byref(h)))
         return Sparse(self, h)
 
     def sparse_merge(self, d_keys, d_counts, n):

@@ -69,15 +69,83 @@ def count_dense_sharded(count_range, make_shard, nbytes, k, table, rank, world, 
     return reduce_table(table, dst)
 
 
+def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
+    """Range-sharded radix path: every rank scatters its reads into the 1024 level-1 partitions
+    (top 10 bits of the code), ONE equal-split all-to-all moves each rank's partition range to it
+    (the slabs are partition-major, so a range is one contiguous block), and every rank counts the
+    partitions it owns: rank r ends with the sorted k-mers of code range r, nothing is merged.
+
+    `engine` provides radix_plan / radix_scatter / radix_count (kmerb200.Context on the GPU; the
+    CPU tests pass an adapter over the emulator build).  Returns None when any rank overflowed
+    (skewed input): the caller then takes the hash-sharded path.  `table_full` = exception
+    types that mean "overflow" for this engine."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(), dist.get_rank()
+
+    def all_ok(ok, dev):
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    dev = reads.device if hasattr(reads, "device") else "cpu"
+    t = torch.tensor([max(nbytes - k + 1, 0)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    plan = engine.radix_plan(int(t.item()), k, world)
+    slabs = counts = None
+    try:
+        slabs, counts = engine.radix_scatter(reads, nbytes, plan)
+    except table_full:
+        pass
+    if not all_ok(slabs is not None, dev):
+        return None
+    recv_s, recv_c = torch.empty_like(slabs), torch.empty_like(counts)
+    dist.all_to_all_single(recv_s, slabs)  # equal splits: block o = partitions [o, o+1) * parts_per_rank
+    dist.all_to_all_single(recv_c, counts)
+    del slabs, counts
+    res = None
+    try:
+        res = engine.radix_count(plan, recv_s, recv_c, world, rank * plan.parts_per_rank, plan.parts_per_rank)
+    except table_full:
+        pass
+    if not all_ok(res is not None, dev):
+        return None
+    return res
+
+
 def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):
-    """GPU path of the hash-sharded all-to-all: `d_reads` holds THIS rank's reads.
-    Returns a kmerb200.Sparse with the keys this rank owns."""
+    """GPU path of the sharded sparse count: `d_reads` holds THIS rank's reads.  Returns a
+    kmerb200.Sparse with the keys this rank owns: a code RANGE with SPARSE_RADIX (sorted
+    across ranks), the codes with mix64(code) % world == rank otherwise."""
     import torch
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return ctx.count_sparse(d_reads, nbytes, k, algo)
-    from . import SPARSE_UNSORTED
+    from . import KC_ERR_TABLE_FULL, SPARSE_HASH, SPARSE_NO_FALLBACK, SPARSE_RADIX, SPARSE_UNSORTED, KmerError
+    if (algo & 0xFF) == SPARSE_RADIX:
+        class _Full(KmerError):
+            pass
+
+        class _Engine:  # turns KC_ERR_TABLE_FULL into its own exception type, passes the rest on
+            def __getattr__(self, name):
+                f = getattr(ctx, name)
+
+                def call(*a):
+                    try:
+                        return f(*a)
+                    except KmerError as e:
+                        if e.code == KC_ERR_TABLE_FULL:
+                            raise _Full(e.code, str(e))
+                        raise
+                return call
+
+        res = count_sparse_radix_sharded(_Engine(), d_reads, nbytes, k, table_full=(_Full,))
+        if res is not None:
+            return res
+        if algo & SPARSE_NO_FALLBACK:
+            raise KmerError(KC_ERR_TABLE_FULL, "sharded sparse radix overflowed on some rank (skewed input)")
+        algo = SPARSE_HASH
     local = ctx.count_sparse(d_reads, nbytes, k, algo | SPARSE_UNSORTED)  # re-bucketed below: no local sort
     n = len(local)
     dev = "cuda:%d" % ctx.device

@@ -200,6 +200,38 @@ KC_API int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
 #define KC_SPARSE_NO_FALLBACK 0x200
 KC_API int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int algo,
                            uint64_t capacity_hint, kc_sparse** out);
+/* The stages of KC_SPARSE_RADIX, exposed for the multi-GPU path ("each GPU owns a disjoint key
+ * range"): every rank scatters its reads into level-1 partitions (the top 10 bits of the code),
+ * the ranks exchange the slab blocks of each other's partition range with one all-to-all (the
+ * slabs are partition-major, so a range is one contiguous block), and every rank counts the
+ * partitions it owns.  Concatenating the ranks' results in rank order gives the sorted whole. */
+typedef struct kc_radix_plan {
+    int32_t k;
+    uint32_t world;           /* ranks the partitions are split over; must divide `partitions` */
+    uint32_t partitions;      /* level-1 partitions (1024)                                      */
+    uint32_t parts_per_rank;  /* partitions / world                                             */
+    uint32_t grid;            /* pass-1 CTAs = regions per partition and rank                   */
+    uint32_t rec_bytes;       /* size of a level-1 record: 4 (k <= 21) or 8                     */
+    uint32_t shape;           /* 0 = shipped 1024 x 1024, 1 = 16 x 16 (KC_SPARSE_RADIX_SHAPE=small, tests) */
+    uint32_t reserved;
+    uint64_t max_windows;     /* the plan is good for inputs of up to this many windows per rank */
+    uint64_t region_records;  /* capacity of one (partition, CTA) region                         */
+    uint64_t slab_bytes;      /* partitions * grid * region_records * rec_bytes                  */
+    uint64_t counts_bytes;    /* partitions * grid * 4                                           */
+} kc_radix_plan;
+/* same plan on every rank: pass the LARGEST per-rank window count */
+KC_API int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world,
+                                kc_radix_plan* plan);
+/* d_slabs: plan->slab_bytes, d_counts: plan->counts_bytes, both [partition][cta]...; synchronous;
+ * KC_ERR_TABLE_FULL when a region overflowed (skewed input)                                  */
+KC_API int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
+                                   const kc_radix_plan* plan, void* d_slabs, uint32_t* d_counts);
+/* counts `nparts` partitions starting at global partition `part_first`; d_slabs / d_counts hold
+ * `nsrc` blocks of [nparts][grid][region_records] / [nparts][grid], one per source rank (what an
+ * equal-split all-to-all of the scatter outputs delivers; nsrc = 1, nparts = partitions on one GPU) */
+KC_API int kc_sparse_radix_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs,
+                                 const uint32_t* d_counts, uint32_t nsrc, uint32_t part_first,
+                                 uint32_t nparts, kc_sparse** out);
 KC_API void kc_sparse_free(kc_sparse* s);
 KC_API uint64_t kc_sparse_size(const kc_sparse* s);
 KC_API const uint64_t* kc_sparse_d_keys(const kc_sparse* s);    /* device, sorted */

@@ -55,12 +55,23 @@ def lib():
         L.kc_sparse_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_kmer_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.kc_gen_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
+        L.kc_sparse_radix_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.POINTER(C.c_void_p)]
         L.kc_gen_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
                                     C.c_uint64, C.c_void_p, C.c_void_p]
         L.kc_gen_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
                                    C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+class RadixPlan(C.Structure):  # kc_radix_plan (include/kmer_b200.h)
+    _fields_ = [("k", C.c_int32), ("world", C.c_uint32), ("partitions", C.c_uint32), ("parts_per_rank", C.c_uint32),
+                ("grid", C.c_uint32), ("rec_bytes", C.c_uint32), ("shape", C.c_uint32), ("reserved", C.c_uint32),
+                ("max_windows", C.c_uint64), ("region_records", C.c_uint64), ("slab_bytes", C.c_uint64),
+                ("counts_bytes", C.c_uint64)]
 
 
 class EmuContext:
@@ -249,7 +260,56 @@ def case_gen(args):
     print("ok gen", *args)
 
 
-CASES = {"dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+def case_radix_sharded(args):
+    """The multi-GPU radix path with the ranks emulated one after the other: every rank scatters
+    its reads, the slab blocks of each rank's partition range are exchanged (numpy slicing stands
+    in for the all-to-all), every rank counts what it owns; the concatenation in rank order must
+    be the oracle's sorted result for ALL the reads."""
+    k, nreads, world, seed = int(args[0]), int(args[1]), int(args[2]), int(args[3])
+    O = _oracle()
+    ctx = EmuContext()
+    L = ctx.L
+    shards = [(nreads * r // world, nreads * (r + 1) // world) for r in range(world)]
+    reads = [O.gen_reads(seed, 8 * nreads, 100, 50, r0, r1 - r0) for r0, r1 in shards]
+    plan = RadixPlan()
+    ctx.check(L.kc_sparse_radix_plan(ctx.h, max(max(x.size - k + 1, 0) for x in reads), k, world, C.byref(plan)))
+    assert plan.parts_per_rank * world == plan.partitions
+    slabs, counts = [], []
+    for x in reads:
+        base, p = ctx.upload(x, 3)
+        d_s, d_c = ctx.alloc(plan.slab_bytes), ctx.alloc(plan.counts_bytes)
+        ctx.check(L.kc_sparse_radix_scatter(ctx.h, p, x.size, C.byref(plan), d_s, d_c))
+        slabs.append(ctx.download(d_s, plan.slab_bytes, np.uint8))
+        counts.append(ctx.download(d_c, plan.counts_bytes, np.uint32))
+        for q in (base, d_s, d_c):
+            ctx.free(q)
+    sb, cb = plan.slab_bytes // world, plan.counts_bytes // 4 // world   # one rank's block of a scatter output
+    keys, cnts = [], []
+    for o in range(world):
+        recv_s = np.concatenate([slabs[src][o * sb:(o + 1) * sb] for src in range(world)])
+        recv_c = np.concatenate([counts[src][o * cb:(o + 1) * cb] for src in range(world)])
+        b1, d_s = ctx.upload(recv_s)
+        b2, d_c = ctx.upload(recv_c)
+        sp = C.c_void_p()
+        ctx.check(L.kc_sparse_radix_count(ctx.h, C.byref(plan), d_s, d_c, world, o * plan.parts_per_rank, plan.parts_per_rank,
+                                          C.byref(sp)))
+        n = int(L.kc_sparse_size(sp))
+        kk, cc = np.empty(n, np.uint64), np.empty(n, np.uint32)
+        ctx.check(L.kc_sparse_copy_to_host(ctx.h, sp, kk.ctypes.data, cc.ctypes.data))
+        L.kc_sparse_free(sp)
+        ctx.free(b1)
+        ctx.free(b2)
+        keys.append(kk)
+        cnts.append(cc)
+    allk, allc = np.concatenate(keys), np.concatenate(cnts)
+    wk, wc, _ = O.count_sparse(np.concatenate(reads), k)
+    assert allk.size == wk.size and (allk == wk).all() and (allc == wc).all(), "sharded radix differs from the oracle"
+    assert all(kk.size > 0 for kk in keys), "a rank owns nothing?"
+    ctx.close()
+    print("ok radix_sharded", *args, "distinct per rank", [int(kk.size) for kk in keys])
+
+
+CASES = {"radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

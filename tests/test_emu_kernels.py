@@ -149,3 +149,15 @@ def test_perseq_distance_and_generators_on_emulator():
     run_case("perseq", 6, 9, 2)
     run_case("perseq", 8, 5, 3)      # global atomics
     run_case("gen", 200_000, 0xB2000003)
+
+
+@pytest.mark.parametrize("k,nreads,world", [(21, 600, 4), (31, 500, 2), (15, 500, 8)])
+def test_sparse_radix_range_sharded_ranks_emulated(k, nreads, world):
+    """the multi-GPU radix path with the ranks run one after the other on the emulator (numpy
+    slicing stands in for the all-to-all); tests/test_sharding_gloo.py runs the same with real
+    processes and gloo"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        run_case("radix_sharded", k, nreads, world, 7 + world)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]

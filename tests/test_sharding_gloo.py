@@ -18,6 +18,17 @@ def test_world2_gloo():
     assert "GLOO_WORKER_OK world=2" in r.stdout
 
 
+def test_world2_gloo_radix():
+    """range-sharded sparse radix path: production host logic over gloo, emulator kernels per rank"""
+    subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "tests", "emu")], check=True)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29657", os.path.join(ROOT, "tests", "_gloo_radix_worker.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="1", KC_SPARSE_RADIX_SHAPE="small", KC_EMU_SMS="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "GLOO_RADIX_WORKER_OK world=2" in r.stdout
+
+
 def test_mix64_np_matches_engine(kmerlib, oracle):
     from kmerb200 import distributed as D
     xs = np.array([0, 1, 0xDEADBEEF, (1 << 62) - 1, 12345678901234567], dtype=np.uint64)

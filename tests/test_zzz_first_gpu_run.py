@@ -3,8 +3,14 @@ emulator (tests/test_emu_kernels.py) — written while the round's GPU budget wa
 They run LAST (file name) and are marked xfail(strict=False): a pass shows as XPASS, a
 mismatch as XFAIL, and neither hides behind the verified tests above.  Remove the marker
 once a B200 run has been seen green."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first B200 run pending (verified on the CPU emulator only)")]
@@ -90,3 +96,17 @@ def test_partition_deferred_retry(ctx, kmerlib, oracle):
     ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_DEFER)
     torch.cuda.synchronize()
     assert bool((a == b).all())
+
+
+def test_nccl_range_sharded_radix():
+    """multi-GPU (>= 2 GPUs visible): scatter, all-to-all of the slabs, count per rank, vs the oracle"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (tests/test_sharding_gloo.py covers the host logic with gloo + emulator kernels)")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+           "--master-addr", "127.0.0.1", "--master-port", "29661", os.path.join(ROOT, "tests", "_nccl_radix_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "NCCL_RADIX_WORKER_OK world=%d" % world in r.stdout
