@@ -326,11 +326,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         int failed = 0;
         const int rc = kc_sparse_radix(ctx, d_data, nbytes, k, out, &failed);
         if (rc || !failed) return rc;
-        if (no_fallback)
-            return kc_set_error(ctx, KC_ERR_TABLE_FULL,
-                                "sparse radix overflowed (skewed input):%s%s%s%s", (failed & 1) ? " partition region" : "",
-                                (failed & 2) ? " staging bins" : "", (failed & 4) ? " leaf buffer" : "",
-                                (failed & 8) ? " run list" : "");
+        if (no_fallback) return KC_ERR_TABLE_FULL;  // kc_last_error names the stage and what overflowed
         algo = KC_SPARSE_HASH;  // a region / leaf / run list overflowed (skewed input): recount exactly
     }
 

@@ -207,6 +207,9 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
     const uint64_t gb = g.g_begin + w * ngroups / nwarps;
     const uint64_t ge = g.g_begin + (w + 1) * ngroups / nwarps;
     kc_warp_scan<HALO>(g, gb, ge, [&](const LaneWindow<HALO>& lw, uint64_t) {
+        // once anything has overflowed the result is void: stop staging, so that a hopelessly
+        // skewed input (every record into one partition) fails in microseconds, not minutes
+        if (*(volatile uint32_t*)&ctl->failed) return;
         // a loop over the set bits, not 16 unrolled copies: the staging code is long and 16
         // copies of it are 56 KB of SASS, more than the instruction cache holds
         uint32_t m = lw.ok & 0xFFFFu;
@@ -327,6 +330,7 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
         };
         constexpr uint32_t RPV = 16 / sizeof(R1T);  // records per 128-bit load
         for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
+            if (*(volatile uint32_t*)&ctl->failed) break;  // the result is void already: do not grind on
             const uint64_t ri = region_index(reg);
             const uint32_t n = counts1[ri];
             const R1T* src = slabs1 + ri * cap1;  // 64-byte aligned
