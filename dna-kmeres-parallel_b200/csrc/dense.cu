@@ -462,15 +462,34 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
     auto flush_bin = [&](uint32_t b) {
         constexpr int Q = C::CAP / 4;  // 128-bit pieces
         const uint32_t src = s_buf + b * (C::CAP * 4);
+        if (ABLATE == 4) {
+            // TMA variant (not the default until measured): the bin leaves through ONE bulk copy
+            // instead of Q shared loads + Q global stores of this lane (the per-lane flush is half
+            // of the kernel's LSU wavefronts, profiles/r01_ncu_instruction_mix.txt).  The bin is
+            // reopened only when the unit has read it.
+            const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
+            if (pos + C::CAP <= (b + 1) * region_cap) {
+                kc_bulk_s2g(my_slabs + pos, src, C::CAP * 4);
+                smem_st(s_state + b * 4, 0u);
+                return;
+            }
+            // region full: fall through to the register path below (its cursor bump is harmless:
+            // the region stays full)
+        }
         uint4 v[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) v[q] = smem_ld128(src + 16 * q);
         smem_st(s_state + b * 4, 0u);  // every slot has been read: the bin is free again
         const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
         if (pos + C::CAP <= (b + 1) * region_cap) {
-            uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
+            if (ABLATE == 5 && Q % 2 == 0) {  // 256-bit stores (STG.E.256): half the store instructions
 #pragma unroll
-            for (int q = 0; q < Q; q++) dst[q] = v[q];
+                for (int q = 0; q < Q; q += 2) kc_stg256(my_slabs + pos + 4 * q, v[q], v[q + 1]);
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
+#pragma unroll
+                for (int q = 0; q < Q; q++) dst[q] = v[q];
+            }
         } else {  // region full (skewed input): rare, slow, exact (static indices: v stays in registers)
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -786,6 +805,10 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
         KC_LAUNCH_SCATTER(2);
     else if (ablate == 3)
         KC_LAUNCH_SCATTER(3);
+    else if (ablate == 4)
+        KC_LAUNCH_SCATTER(4);
+    else if (ablate == 5)
+        KC_LAUNCH_SCATTER(5);
     else
         KC_LAUNCH_SCATTER(0);
 #undef KC_LAUNCH_SCATTER

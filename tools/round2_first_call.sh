@@ -17,6 +17,18 @@ d=json.load(open("$O/r02_dense_abl$A.log"))
 print("algo=$A ms/step %.4f kernels %s checksum %s" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
 PY
 done
+echo "== 2a. dense k=12 scatter flush variants (env KC_PART_ABLATE: 3 deferred retry, 4 TMA bulk flush, 5 256-bit stores)"
+for A in 3 4 5; do
+  KC_PART_ABLATE=$A timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_dense_env$A.log 2> $O/r02_dense_env$A.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("$O/r02_dense_env$A.log"))
+    print("KC_PART_ABLATE=$A ms/step %.4f kernels %s checksum %s (must equal the shipped path's)" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
+except Exception as e:
+    print("KC_PART_ABLATE=$A failed:", e)
+PY
+done
 echo "== 2b. k=8 (config 2 and the 3.1 Gbp genome): shipped 16-bit bins vs checksum variant (--algo 3)"
 for W in config2 genome_k8; do for A in 0 3; do
   timeout 300 python bench.py --workload $W --algo $A --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_${W}_a$A.log 2> $O/r02_${W}_a$A.err
