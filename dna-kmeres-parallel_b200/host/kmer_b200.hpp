@@ -110,6 +110,26 @@ class Engine {
         return table;
     }
 
+    // sparse count (k <= 31) of a host byte buffer: distinct LE codes ascending + counts.
+    // algo: KC_SPARSE_HASH / KC_SPARSE_SORT / KC_SPARSE_RADIX (the last falls back to the hash
+    // path by itself when skewed data overflows one of its regions)
+    void countSparse(const char* h_data, uint64_t nbytes, int k, int algo, std::vector<uint64_t>& keys,
+                     std::vector<uint32_t>& counts) {
+        void* d_data = nullptr;
+        check(kc_device_alloc(ctx_, nbytes, &d_data), ctx_);
+        kc_sparse* sp = nullptr;
+        int rc = kc_memcpy_h2d(ctx_, d_data, h_data, nbytes);
+        if (rc == KC_OK) rc = kc_count_sparse(ctx_, (const char*)d_data, nbytes, k, algo, 0, &sp);
+        if (rc == KC_OK) {
+            keys.resize((size_t)kc_sparse_size(sp));
+            counts.resize(keys.size());
+            rc = kc_sparse_copy_to_host(ctx_, sp, keys.data(), counts.data());
+        }
+        kc_sparse_free(sp);
+        kc_device_free(ctx_, d_data);
+        check(rc, ctx_);
+    }
+
     // packed strict upper triangle of k-mer distances (main.cu:327-358)
     std::vector<float> minKmeres(const int32_t* d_sums, Sequences& seqs, int k) {
         const char* d_data;
