@@ -512,6 +512,39 @@ def main():
         assert (chk.cpu().numpy().view(np.uint32) == want).all(), "GPU table differs from the oracle on the CPU sample"
         cpu["parity_on_sample"] = "bit-exact"
 
+    # ---- BASELINE configs[0] (1 Mbp, k=3) on the reference's OWN counting code ------------
+    # oracle/_ref holds main.cu's permutationsCountAll compiled unmodified (K=3); the engine's
+    # reference-shaped entry point kc_count_per_seq must give the same 64 counts.  Reported
+    # beside the headline so that one number in this line rests on reference code itself.
+    ref1 = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            import oracle as O
+            R = O.ref(3)
+            if R is not None:
+                n1 = WORKLOADS["config1"]["L"]
+                seq = O.gen_bases(WORKLOADS["config1"]["seed"], 0, n1)
+                t0 = time.perf_counter()
+                rc = R.count_all(seq)  # [0] = invalid windows, [idx+1] = count of k-mer idx (main.cu:636-646)
+                dt_ref = time.perf_counter() - t0
+                d_seq = torch.zeros(n1 + 1, dtype=torch.uint8, device=dev)  # sequence + its '\0' separator
+                d_seq[:n1] = torch.from_numpy(seq.copy())
+                d_off = torch.tensor([0, n1 + 1], dtype=torch.int64, device=dev)
+                sums = ctx.count_per_seq(d_seq, d_off, 1, 3)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    sums = ctx.count_per_seq(d_seq, d_off, 1, 3, sums=sums, sync=False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms1 = e0.elapsed_time(e1) / 20
+                same = bool((sums.cpu().numpy().reshape(-1) == rc[1:]).all())
+                ref1 = {"workload": WORKLOADS["config1"]["desc"], "reference_cpu_bases_per_s": n1 / dt_ref,
+                        "reference_cpu": "main.cu permutationsCountAll via oracle/_ref/libref_k3.so, 1 thread (the reference is serial), %.3f s" % dt_ref,
+                        "kc_count_per_seq_bases_per_s": n1 / (ms1 * 1e-3), "kc_count_per_seq_ms": ms1, "parity": "bit-exact" if same else "MISMATCH"}
+        except Exception as ex:  # the reference library is optional (built only where /root/reference exists)
+            ref1 = {"unavailable": str(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
@@ -528,6 +561,7 @@ def main():
                        if world > 1 else "single GPU",
                        "table_checksum": checksum},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "reference_config1": ref1,
         }
         emit(line)
     leave(world)
