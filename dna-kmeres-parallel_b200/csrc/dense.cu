@@ -19,6 +19,8 @@
 //       shared memory (32 banks/clk/SM).  See DESIGN.md §3.3.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -708,6 +710,178 @@ part_count_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sla
 
 using Part12 = PartCfg<12, 5, 11, 16>;
 
+// Pass 2, PAIRED variant for k = 12 (KC_DENSE_PARTITION_PAIR; first B200 run pending, not the
+// default).  The count kernel above is bound by shared-memory wavefronts: one random atomic per
+// window, 3.35 wavefronts per 32-lane atomic (profiles/r01_ncu_instruction_mix.txt).  A record
+// holds 5 consecutive windows; windows (0,1) are the two 12-mers of the 13-mer at offset 0 and
+// (2,3) those of the 13-mer at offset 2, so counting the two 13-mers and window 4 is THREE
+// increments per record instead of five, and the 13-mer counts are folded into 12-mer bins while
+// the sub-tables are flushed (the number of global REDs stays 40960 per partition):
+//   T0[32768]  13-mer at offset 0, index = 13-mer code minus the 11 key bits   16-bit fields
+//   T2[32768]  13-mer at offset 2                                               16-bit fields
+//   T4[8192]   window 4 (as in the kernel above)                                32-bit
+// = 160 KB, the same shared memory.  16-bit fields can wrap on skewed input; as in
+// dense_smem16c_kernel a wrap is found afterwards (sum of all fields != 2 x records of the
+// partition) and the CTA then recounts the partition with the five 32-bit tables.
+__global__ void __launch_bounds__(1024, 1)
+part_count_pair12_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slabs,
+                         const uint32_t* __restrict__ counts, uint32_t region_cap, uint32_t nregions,
+                         uint32_t* __restrict__ work_counter) {
+    using C = Part12;
+    KC_DYN_SMEM(uint32_t, bins);  // 40960 words
+    __shared__ uint32_t s_part, s_bad;
+    __shared__ unsigned long long s_red[64];
+    const uint32_t s_bins = (uint32_t)__cvta_generic_to_shared(bins);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t W0 = 0, W2 = 16384, W4 = 32768;  // word offsets of T0, T2, T4
+    for (;;) {
+        if (tid == 0) s_part = atomicAdd(work_counter, 1u);
+        {
+            uint4* b4 = reinterpret_cast<uint4*>(bins);
+            for (int i = tid; i < 40960 / 4; i += 1024) b4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        const uint32_t part = s_part;
+        if (part >= (uint32_t)C::P) break;
+        uint32_t nrec = 0;
+        auto count_rec = [&](uint32_t rec) {
+            const uint32_t c0 = rec & 0x3FFFFFFu;          // bases 0..12
+            const uint32_t c2 = (rec >> 4) & 0x3FFFFFFu;   // bases 2..14
+            const uint32_t c4 = rec >> 8;                  // bases 4..15
+            const uint32_t i0 = (c0 & 0x1FFFu) | ((c0 >> 24) << 13);  // key = record bits [13,24) removed: 15 bits
+            const uint32_t i2 = (c2 & 0x1FFu) | ((c2 >> 20) << 9);    // 15 bits
+            const uint32_t i4 = (c4 & 0x1Fu) | ((c4 >> 16) << 5);     // 13 bits
+            smem_red_add(s_bins + (W0 + (i0 & 0x3FFFu)) * 4, (i0 & 0x4000u) ? 0x10000u : 1u);
+            smem_red_add(s_bins + (W2 + (i2 & 0x3FFFu)) * 4, (i2 & 0x4000u) ? 0x10000u : 1u);
+            smem_red_add(s_bins + (W4 + i4) * 4, 1u);
+            nrec++;
+        };
+        auto count_rec_classic = [&](uint32_t rec) {  // the five 32-bit sub-tables of part_count_kernel
+            const uint32_t Y = (rec & 0x1FFFu) | ((rec >> 24) << 13);
+#pragma unroll
+            for (int r = 0; r < 5; r++) smem_red_add(s_bins + (r * 8192 + ((Y >> (2 * r)) & 0x1FFFu)) * 4, 1u);
+        };
+        auto for_each_record = [&](auto&& f) {
+            for (uint32_t reg = warp; reg < nregions; reg += 32) {
+                const uint32_t n = counts[(uint64_t)part * nregions + reg];
+                const uint32_t* src = slabs + ((uint64_t)reg * C::P + part) * region_cap;  // chunk aligned
+                const uint4* src4 = reinterpret_cast<const uint4*>(src);
+                const uint32_t n4 = n >> 2;
+                uint32_t i = lane;
+                for (; i + 32 < n4; i += 64) {  // two loads in flight per lane
+                    const uint4 v0 = kc_ldg_stream(src4 + i);
+                    const uint4 v1 = kc_ldg_stream(src4 + i + 32);
+                    f(v0.x);
+                    f(v0.y);
+                    f(v0.z);
+                    f(v0.w);
+                    f(v1.x);
+                    f(v1.y);
+                    f(v1.z);
+                    f(v1.w);
+                }
+                for (; i < n4; i += 32) {
+                    const uint4 v = kc_ldg_stream(src4 + i);
+                    f(v.x);
+                    f(v.y);
+                    f(v.z);
+                    f(v.w);
+                }
+                for (uint32_t t = (n4 << 2) + lane; t < n; t += 32) f(src[t]);
+            }
+        };
+        for_each_record(count_rec);
+        __syncthreads();
+        // checksum: the 16-bit fields of T0 and T2 must add up to two increments per record
+        unsigned long long fsum = 0, asum = 2ull * nrec;
+        for (int i = tid; i < 32768; i += 1024) {
+            const uint32_t v = bins[i];
+            fsum += (v & 0xFFFFu) + (v >> 16);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            fsum += __shfl_down_sync(0xffffffffu, fsum, d);
+            asum += __shfl_down_sync(0xffffffffu, asum, d);
+        }
+        if (lane == 0) {
+            s_red[warp] = fsum;
+            s_red[32 + warp] = asum;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long f = 0, a = 0;
+            for (int q = 0; q < 32; q++) {
+                f += s_red[q];
+                a += s_red[32 + q];
+            }
+            s_bad = (f == a) ? 0u : 1u;
+#ifdef KC_EMU  // a real wrap needs > 65535 records of one partition in one bin (0.7 GB of input): the
+               // emulator tests force the recount path instead (the detection itself is the one
+               // dense_smem16c_kernel's tests exercise with real wraps)
+            if (getenv("KC_EMU_FORCE_PAIR_RECOUNT") && (part & 1u)) s_bad = 1u;
+#endif
+        }
+        __syncthreads();
+        if (s_bad) {  // a field wrapped (skewed input): recount this partition with 32-bit bins
+            KC_STAT(7);
+            {
+                uint4* b4 = reinterpret_cast<uint4*>(bins);
+                for (int i = tid; i < 40960 / 4; i += 1024) b4[i] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            for_each_record(count_rec_classic);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const int lowbits = 13 - 2 * r;
+                for (int f = tid; f < 8192; f += 1024) {
+                    const uint32_t v = bins[r * 8192 + f];
+                    if (v) {
+                        const uint32_t low = (uint32_t)f & ((1u << lowbits) - 1u), high = (uint32_t)f >> lowbits;
+                        global_red_add(table + (low | (part << lowbits) | (high << (24 - 2 * r))), v);
+                    }
+                }
+            }
+        } else {
+            // fold and flush.  A field f of a 16-bit table lives in word f & 0x3FFF, half f >> 14.
+            // T0, f = low13 | h << 13 (h = the 13-mer's last base):
+            //   window 0 = low13 | key << 13                      (sum over h)
+            //   window 1 = low13 >> 2 | key << 11 | h << 22       (sum over the 13-mer's first base)
+            // T2, f = low9 | hi6 << 9:
+            //   window 2 = low9 | key << 9 | (hi6 & 15) << 20     (sum over hi6 >> 4)
+            //   window 3 = low9 >> 2 | key << 7 | hi6 << 18       (sum over low9 & 3)
+            for (int x = tid; x < 8192; x += 1024) {
+                const uint32_t a = bins[W0 + x], b = bins[W0 + 8192 + x];
+                const uint32_t v0 = (a & 0xFFFFu) + (a >> 16) + (b & 0xFFFFu) + (b >> 16);
+                if (v0) global_red_add(table + ((uint32_t)x | (part << 13)), v0);
+                const uint32_t c = bins[W2 + x], d = bins[W2 + 8192 + x];
+                const uint32_t v2 = (c & 0xFFFFu) + (c >> 16) + (d & 0xFFFFu) + (d >> 16);
+                if (v2) global_red_add(table + (((uint32_t)x & 0x1FFu) | (part << 9) | (((uint32_t)x >> 9) << 20)), v2);
+                const uint32_t v4 = bins[W4 + x];
+                if (v4) global_red_add(table + (((uint32_t)x & 0x1Fu) | (part << 5) | (((uint32_t)x >> 5) << 16)), v4);
+            }
+            for (int y = tid; y < 4096; y += 1024) {  // y = word block (4 words) of a 16-bit table
+                const uint4 w = *reinterpret_cast<const uint4*>(bins + W0 + 4 * y);
+                const uint32_t lo = (w.x & 0xFFFFu) + (w.y & 0xFFFFu) + (w.z & 0xFFFFu) + (w.w & 0xFFFFu);
+                const uint32_t hi = (w.x >> 16) + (w.y >> 16) + (w.z >> 16) + (w.w >> 16);
+                // words 4y..4y+3 hold fields f = 4y + t (half 0) and f + 16384 (half 1); f = low13 | h << 13
+                const uint32_t q = (uint32_t)y & 2047u, hb = (uint32_t)y >> 11;  // low13 >> 2, h & 1
+                if (lo) global_red_add(table + (q | (part << 11) | (hb << 22)), lo);
+                if (hi) global_red_add(table + (q | (part << 11) | ((hb + 2u) << 22)), hi);
+                const uint4 u = *reinterpret_cast<const uint4*>(bins + W2 + 4 * y);
+                const uint32_t lo2 = (u.x & 0xFFFFu) + (u.y & 0xFFFFu) + (u.z & 0xFFFFu) + (u.w & 0xFFFFu);
+                const uint32_t hi2 = (u.x >> 16) + (u.y >> 16) + (u.z >> 16) + (u.w >> 16);
+                // fields f = 4y + t = low9 | hi6 << 9 with hi6 < 32 (half 0) and hi6 + 32 (half 1)
+                const uint32_t q2 = (uint32_t)y & 127u, h6 = (uint32_t)y >> 7;  // low9 >> 2, hi6 & 31
+                if (lo2) global_red_add(table + (q2 | (part << 7) | (h6 << 18)), lo2);
+                if (hi2) global_red_add(table + (q2 | (part << 7) | ((h6 + 32u) << 18)), hi2);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -749,7 +923,7 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
 
 template <typename S>
 static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
-                           uint32_t* d_table, cudaStream_t st, bool defer) {
+                           uint32_t* d_table, cudaStream_t st, bool defer, bool pair = false) {
     using C = typename S::Cfg;
     const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, C::K);
     // interior groups [G0, G1): fully readable, all their windows requested, and
@@ -814,11 +988,18 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
 #undef KC_LAUNCH_SCATTER
     KC_LAUNCH_CHECK(ctx, "part_scatter_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
-    KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int ctas2 = (smem2 + 1024) * 2 <= ctx->smem_optin + 1024 && smem2 <= 100 * 1024 ? 2 : 1;
     int grid2 = ctx->sm_count * ctas2 < C::P ? ctx->sm_count * ctas2 : C::P;
-    KC_LAUNCH(part_count_kernel<C>, grid2, 1024, smem2, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
-    KC_LAUNCH_CHECK(ctx, "part_count_kernel");
+    static const int pair_env = getenv("KC_PART_PAIR") ? atoi(getenv("KC_PART_PAIR")) : 0;  // measurement aid
+    if ((pair || pair_env) && std::is_same<C, Part12>::value) {
+        KC_CUDA(ctx, cudaFuncSetAttribute(part_count_pair12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        KC_LAUNCH(part_count_pair12_kernel, grid2, 1024, smem2, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
+        KC_LAUNCH_CHECK(ctx, "part_count_pair12_kernel");
+    } else {
+        KC_CUDA(ctx, cudaFuncSetAttribute(part_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        KC_LAUNCH(part_count_kernel<C>, grid2, 1024, smem2, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
+        KC_LAUNCH_CHECK(ctx, "part_count_kernel");
+    }
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
     // the windows before and after the interior
     const bool timing = ctx->timing;
@@ -892,7 +1073,7 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
     if (!d_table || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION && algo != KC_DENSE_SMEM16C &&
-        algo != KC_DENSE_PARTITION_DEFER)
+        algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown dense algo %d", algo);
     if (algo == KC_DENSE_SMEM16C) {
         if (k != 8) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_SMEM16C is the k = 8 path (k=%d)", k);
@@ -903,7 +1084,9 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream, true);
     }
     const bool defer = (algo == KC_DENSE_PARTITION_DEFER);
-    if (defer) algo = KC_DENSE_PARTITION;
+    const bool pair = (algo == KC_DENSE_PARTITION_PAIR);
+    if (pair && k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_PAIR is built for k = 12 (k=%d)", k);
+    if (defer || pair) algo = KC_DENSE_PARTITION;
     DeviceGuard dg(ctx->device);
     if (nbytes < (uint64_t)k) return KC_OK;
     const uint64_t nwin = nbytes - k + 1;
@@ -927,7 +1110,7 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         switch (k) {
             case 12:
                 if (shape == 1) return dense_partition<ScatterShape<PartCfg<12, 5, 11, 24>, 1024, 1, 2>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
-                return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
+                return dense_partition<ScatterShape<Part12, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer, pair);
             case 11: return dense_partition<ScatterShape<PartCfg<11, 6, 11, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
             case 10: return dense_partition<ScatterShape<PartCfg<10, 7, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);
             default: return dense_partition<ScatterShape<PartCfg<9, 6, 8, 16>, 1024, 1, 3>>(ctx, d_data, nbytes, win_begin, win_end, d_table, st, defer);

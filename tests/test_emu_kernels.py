@@ -84,6 +84,18 @@ def test_partition_flush_variants(ablate):
     run_case("dense", 10, 200_000, 2, "dirty", 3, 5, KC_PART_ABLATE=ablate)
 
 
+def test_partition_paired_count_variant():
+    """KC_DENSE_PARTITION_PAIR (algo 5, k = 12): pass 2 counts the 13-mers at offsets 0 and 2 and the
+    12-mer at offset 4 of every record (3 increments instead of 5) and folds them into 12-mer bins at
+    the flush; a partition whose 16-bit fields wrapped is recounted with 32-bit bins (forced here for
+    every odd partition: a real wrap needs 0.7 GB of input)."""
+    run_case("dense", 12, 400_000, 5, "genome", 2, 0)
+    run_case("dense", 12, 400_000, 5, "dirty", 5, 7, seed=3, sms=2)
+    run_case("dense", 12, 300_000, 5, "skew", 6, 2)
+    st = emu_stats(run_case("dense", 12, 400_000, 5, "genome", 8, 3, KC_EMU_FORCE_PAIR_RECOUNT=1))
+    assert st[7] >= 1024, st   # the odd partitions went through the 32-bit recount
+
+
 def test_k8_checksum_variant():
     """KC_DENSE_SMEM16C (algo 3): non-returning shared adds, per-CTA checksum, repair of the CTAs
     whose 16-bit fields wrapped.  Uniform input: no CTA is repaired; one-bin inputs: every CTA is."""

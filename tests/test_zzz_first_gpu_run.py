@@ -98,6 +98,31 @@ def test_partition_deferred_retry(ctx, kmerlib, oracle):
     assert bool((a == b).all())
 
 
+def test_partition_paired_count(ctx, kmerlib, oracle):
+    """KC_DENSE_PARTITION_PAIR (k = 12) against the oracle, and against the shipped path at 1 Gbp;
+    2^30 'A's: partition 0's regions hold ~127 K identical records (148 regions of ~860), one 16-bit
+    field wraps, the checksum fails and the 32-bit recount runs"""
+    import torch
+    n = 40_000_000
+    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
+    want, _ = oracle.count_dense(genome, 12)
+    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_PAIR) == want).all()
+    L = 1 << 30
+    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
+    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    b = torch.zeros_like(a)
+    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
+    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_PAIR)
+    torch.cuda.synchronize()
+    assert bool((a == b).all())
+    del data, a, b
+    poly = torch.full((1 << 30,), ord("A"), dtype=torch.uint8, device="cuda:0")
+    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    ctx.count_dense_range(poly, 1 << 30, 0, 1 << 30, 12, t, algo=kmerlib.DENSE_PARTITION_PAIR)
+    torch.cuda.synchronize()
+    assert int(t[0].item()) == (1 << 30) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 30) - 11
+
+
 def test_nccl_range_sharded_radix():
     """multi-GPU (>= 2 GPUs visible): scatter, all-to-all of the slabs, count per rank, vs the oracle"""
     import torch
