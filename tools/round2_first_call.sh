@@ -29,6 +29,16 @@ except Exception as e:
     print("KC_PART_ABLATE=$A failed:", e)
 PY
 done
+echo "== 2a'. deferred-retry scatter + paired count together"
+KC_PART_ABLATE=3 KC_PART_PAIR=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_dense_env3_pair.log 2> $O/r02_dense_env3_pair.err
+python - <<PY
+import json
+try:
+    d=json.load(open("$O/r02_dense_env3_pair.log"))
+    print("KC_PART_ABLATE=3 KC_PART_PAIR=1 ms/step %.4f kernels %s checksum %s" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"]["table_checksum"]))
+except Exception as e:
+    print("combined run failed:", e)
+PY
 echo "== 2b. k=8 (config 2 and the 3.1 Gbp genome): shipped 16-bit bins vs checksum variant (--algo 3)"
 for W in config2 genome_k8; do for A in 0 3; do
   timeout 300 python bench.py --workload $W --algo $A --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_${W}_a$A.log 2> $O/r02_${W}_a$A.err
