@@ -882,6 +882,187 @@ part_count_pair12_kernel(uint32_t* __restrict__ table, const uint32_t* __restric
     }
 }
 
+// Pass 2, TWO increments per record (KC_DENSE_PARTITION_TRIO; first B200 run pending): the same
+// idea one step further.  The 14-mer at offset 0 contains windows 0, 1, 2 and the 13-mer at offset 3
+// windows 3, 4:
+//   T14[131072]  14-mer at offset 0 minus the 11 key bits, 8-bit fields   (128 KB)
+//   T13[32768]   13-mer at offset 3 minus the key bits,   16-bit fields   ( 64 KB)
+// A partition of the 3.1 Gbp genome puts 300 K records into 131072 fields (2.3 per field), so 8 bits
+// are plenty for unskewed data; a wrapped field changes the sum of all fields by -255 / -256 (8-bit)
+// or -65535 / -65536 (16-bit), never by 0, so  sum(T14) == records && sum(T13) == records  proves
+// that nothing wrapped; otherwise the partition is recounted with the five 32-bit tables.
+// Fold at the flush (f = field index, key = partition):
+//   T14, f = low13 | hi4 << 13 (hi4 = bases 12,13); word f & 0x7FFF, byte f >> 15
+//     window 0 = low13 | key << 13                         sum over hi4            (16 fields)
+//     window 1 = low13 >> 2 | key << 11 | (hi4 & 3) << 22  sum over low13 & 3, hi4 >> 2
+//     window 2 = low13 >> 4 | key << 9 | hi4 << 20         sum over low13 & 15
+//   T13, f = low7 | hi8 << 7; word f & 0x3FFF, half f >> 14
+//     window 3 = low7 | key << 7 | (hi8 & 63) << 18        sum over hi8 >> 6
+//     window 4 = low7 >> 2 | key << 5 | hi8 << 16          sum over low7 & 3
+__global__ void __launch_bounds__(1024, 1)
+part_count_trio12_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ slabs,
+                         const uint32_t* __restrict__ counts, uint32_t region_cap, uint32_t nregions,
+                         uint32_t* __restrict__ work_counter) {
+    using C = Part12;
+    KC_DYN_SMEM(uint32_t, bins);  // 49152 words: T14 = words [0, 32768), T13 = words [32768, 49152)
+    __shared__ uint32_t s_part, s_bad;
+    __shared__ unsigned long long s_red[96];
+    const uint32_t s_bins = (uint32_t)__cvta_generic_to_shared(bins);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t W13 = 32768, NWORDS = 49152;
+    auto bytesum = [](uint32_t v) { return (v & 0xFFu) + ((v >> 8) & 0xFFu) + ((v >> 16) & 0xFFu) + (v >> 24); };
+    auto bytesum4 = [](uint4 w, int sh) {  // the byte at bit `sh` of four words
+        return ((w.x >> sh) & 0xFFu) + ((w.y >> sh) & 0xFFu) + ((w.z >> sh) & 0xFFu) + ((w.w >> sh) & 0xFFu);
+    };
+    for (;;) {
+        if (tid == 0) s_part = atomicAdd(work_counter, 1u);
+        {
+            uint4* b4 = reinterpret_cast<uint4*>(bins);
+            for (int i = tid; i < (int)NWORDS / 4; i += 1024) b4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        const uint32_t part = s_part;
+        if (part >= (uint32_t)C::P) break;
+        uint32_t nrec = 0;
+        auto count_rec = [&](uint32_t rec) {
+            const uint32_t c14 = rec & 0xFFFFFFFu;  // bases 0..13
+            const uint32_t c13 = rec >> 6;          // bases 3..15
+            const uint32_t i0 = (c14 & 0x1FFFu) | ((c14 >> 24) << 13);  // key = record bits [13,24) removed: 17 bits
+            const uint32_t i3 = (c13 & 0x7Fu) | ((c13 >> 18) << 7);     // 15 bits
+            smem_red_add(s_bins + (i0 & 0x7FFFu) * 4, 1u << (8 * (i0 >> 15)));
+            smem_red_add(s_bins + (W13 + (i3 & 0x3FFFu)) * 4, (i3 & 0x4000u) ? 0x10000u : 1u);
+            nrec++;
+        };
+        auto count_rec_classic = [&](uint32_t rec) {  // the five 32-bit sub-tables of part_count_kernel
+            const uint32_t Y = (rec & 0x1FFFu) | ((rec >> 24) << 13);
+#pragma unroll
+            for (int r = 0; r < 5; r++) smem_red_add(s_bins + (r * 8192 + ((Y >> (2 * r)) & 0x1FFFu)) * 4, 1u);
+        };
+        auto for_each_record = [&](auto&& f) {
+            for (uint32_t reg = warp; reg < nregions; reg += 32) {
+                const uint32_t n = counts[(uint64_t)part * nregions + reg];
+                const uint32_t* src = slabs + ((uint64_t)reg * C::P + part) * region_cap;  // chunk aligned
+                const uint4* src4 = reinterpret_cast<const uint4*>(src);
+                const uint32_t n4 = n >> 2;
+                uint32_t i = lane;
+                for (; i + 32 < n4; i += 64) {  // two loads in flight per lane
+                    const uint4 v0 = kc_ldg_stream(src4 + i);
+                    const uint4 v1 = kc_ldg_stream(src4 + i + 32);
+                    f(v0.x);
+                    f(v0.y);
+                    f(v0.z);
+                    f(v0.w);
+                    f(v1.x);
+                    f(v1.y);
+                    f(v1.z);
+                    f(v1.w);
+                }
+                for (; i < n4; i += 32) {
+                    const uint4 v = kc_ldg_stream(src4 + i);
+                    f(v.x);
+                    f(v.y);
+                    f(v.z);
+                    f(v.w);
+                }
+                for (uint32_t t = (n4 << 2) + lane; t < n; t += 32) f(src[t]);
+            }
+        };
+        for_each_record(count_rec);
+        __syncthreads();
+        // checksums: every record put one increment into each table
+        unsigned long long s14 = 0, s13 = 0, asum = nrec;
+        for (int i = tid; i < (int)W13; i += 1024) s14 += bytesum(bins[i]);
+        for (int i = tid; i < 16384; i += 1024) {
+            const uint32_t v = bins[W13 + i];
+            s13 += (v & 0xFFFFu) + (v >> 16);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            s14 += __shfl_down_sync(0xffffffffu, s14, d);
+            s13 += __shfl_down_sync(0xffffffffu, s13, d);
+            asum += __shfl_down_sync(0xffffffffu, asum, d);
+        }
+        if (lane == 0) {
+            s_red[warp] = s14;
+            s_red[32 + warp] = s13;
+            s_red[64 + warp] = asum;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long a = 0, b = 0, c = 0;
+            for (int q = 0; q < 32; q++) {
+                a += s_red[q];
+                b += s_red[32 + q];
+                c += s_red[64 + q];
+            }
+            s_bad = (a == c && b == c) ? 0u : 1u;
+#ifdef KC_EMU  // see part_count_pair12_kernel
+            if (getenv("KC_EMU_FORCE_PAIR_RECOUNT") && (part & 1u)) s_bad = 1u;
+#endif
+        }
+        __syncthreads();
+        if (s_bad) {  // a field wrapped (skewed input): recount this partition with 32-bit bins
+            KC_STAT(7);
+            {
+                uint4* b4 = reinterpret_cast<uint4*>(bins);
+                for (int i = tid; i < 40960 / 4; i += 1024) b4[i] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            for_each_record(count_rec_classic);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const int lowbits = 13 - 2 * r;
+                for (int f = tid; f < 8192; f += 1024) {
+                    const uint32_t v = bins[r * 8192 + f];
+                    if (v) {
+                        const uint32_t low = (uint32_t)f & ((1u << lowbits) - 1u), high = (uint32_t)f >> lowbits;
+                        global_red_add(table + (low | (part << lowbits) | (high << (24 - 2 * r))), v);
+                    }
+                }
+            }
+        } else {
+            for (int x = tid; x < 8192; x += 1024) {
+                // window 0: all 16 fields low13 = x (4 words x + 8192 b12, 4 bytes each)
+                const uint32_t v0 = bytesum(bins[x]) + bytesum(bins[x + 8192]) + bytesum(bins[x + 16384]) + bytesum(bins[x + 24576]);
+                if (v0) global_red_add(table + ((uint32_t)x | (part << 13)), v0);
+                // window 3: low7 | (hi8 & 63) << 7 = x; the four hi8 >> 6 are the two halves of words x and x + 8192
+                const uint32_t c = bins[W13 + x], d = bins[W13 + 8192 + x];
+                const uint32_t v3 = (c & 0xFFFFu) + (c >> 16) + (d & 0xFFFFu) + (d >> 16);
+                if (v3) global_red_add(table + (((uint32_t)x & 0x7Fu) | (part << 7) | (((uint32_t)x >> 7) << 18)), v3);
+            }
+            for (int y = tid; y < 8192; y += 1024) {
+                // window 1: word block y of T14 = fields 4q + t (t < 4) with b12 = y >> 11; all four bytes (b13)
+                const uint4 w = *reinterpret_cast<const uint4*>(bins + 4 * y);
+                const uint32_t v1 = bytesum(w.x) + bytesum(w.y) + bytesum(w.z) + bytesum(w.w);
+                if (v1) global_red_add(table + (((uint32_t)y & 2047u) | (part << 11) | (((uint32_t)y >> 11) << 22)), v1);
+            }
+            for (int z = tid; z < 2048; z += 1024) {
+                // window 2: 16 consecutive words (low13 & 15) of block z = q4 | b12 << 9; one bin per byte (b13)
+                const uint4* p4 = reinterpret_cast<const uint4*>(bins + 16 * z);
+                const uint4 a = p4[0], b = p4[1], c = p4[2], d = p4[3];
+                const uint32_t q4 = (uint32_t)z & 511u, b12 = (uint32_t)z >> 9;
+#pragma unroll
+                for (int b13 = 0; b13 < 4; b13++) {
+                    const uint32_t v2 = bytesum4(a, 8 * b13) + bytesum4(b, 8 * b13) + bytesum4(c, 8 * b13) + bytesum4(d, 8 * b13);
+                    if (v2) global_red_add(table + (q4 | (part << 9) | ((b12 | ((uint32_t)b13 << 2)) << 20)), v2);
+                }
+            }
+            for (int y = tid; y < 4096; y += 1024) {
+                // window 4: word block y of T13 = fields low7 = 4q + t, hi8 & 127 = y >> 5; halves = hi8 >> 7
+                const uint4 u = *reinterpret_cast<const uint4*>(bins + W13 + 4 * y);
+                const uint32_t lo = (u.x & 0xFFFFu) + (u.y & 0xFFFFu) + (u.z & 0xFFFFu) + (u.w & 0xFFFFu);
+                const uint32_t hi = (u.x >> 16) + (u.y >> 16) + (u.z >> 16) + (u.w >> 16);
+                const uint32_t q = (uint32_t)y & 31u, h7 = (uint32_t)y >> 5;
+                if (lo) global_red_add(table + (q | (part << 5) | (h7 << 16)), lo);
+                if (hi) global_red_add(table + (q | (part << 5) | ((h7 + 128u) << 16)), hi);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -923,7 +1104,7 @@ static int dense_direct(kc_ctx* ctx, const ScanGeom& g, uint32_t* d_table, cudaS
 
 template <typename S>
 static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
-                           uint32_t* d_table, cudaStream_t st, bool defer, bool pair = false) {
+                           uint32_t* d_table, cudaStream_t st, bool defer, int pair = 0) {
     using C = typename S::Cfg;
     const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, C::K);
     // interior groups [G0, G1): fully readable, all their windows requested, and
@@ -991,7 +1172,13 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     const int ctas2 = (smem2 + 1024) * 2 <= ctx->smem_optin + 1024 && smem2 <= 100 * 1024 ? 2 : 1;
     int grid2 = ctx->sm_count * ctas2 < C::P ? ctx->sm_count * ctas2 : C::P;
     static const int pair_env = getenv("KC_PART_PAIR") ? atoi(getenv("KC_PART_PAIR")) : 0;  // measurement aid
-    if ((pair || pair_env) && std::is_same<C, Part12>::value) {
+    const int pair_mode = pair ? pair : pair_env;  // 1 = pairs (3 increments per record), 2 = 14-mer + 13-mer (2 increments)
+    if (pair_mode == 2 && std::is_same<C, Part12>::value) {
+        const size_t smem3 = 49152 * sizeof(uint32_t);
+        KC_CUDA(ctx, cudaFuncSetAttribute(part_count_trio12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        KC_LAUNCH(part_count_trio12_kernel, grid2, 1024, smem3, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
+        KC_LAUNCH_CHECK(ctx, "part_count_trio12_kernel");
+    } else if (pair_mode && std::is_same<C, Part12>::value) {
         KC_CUDA(ctx, cudaFuncSetAttribute(part_count_pair12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         KC_LAUNCH(part_count_pair12_kernel, grid2, 1024, smem2, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
         KC_LAUNCH_CHECK(ctx, "part_count_pair12_kernel");
@@ -1073,7 +1260,7 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
     if (!d_table || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION && algo != KC_DENSE_SMEM16C &&
-        algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR)
+        algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR && algo != KC_DENSE_PARTITION_TRIO)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown dense algo %d", algo);
     if (algo == KC_DENSE_SMEM16C) {
         if (k != 8) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_SMEM16C is the k = 8 path (k=%d)", k);
@@ -1084,8 +1271,8 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream, true);
     }
     const bool defer = (algo == KC_DENSE_PARTITION_DEFER);
-    const bool pair = (algo == KC_DENSE_PARTITION_PAIR);
-    if (pair && k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_PAIR is built for k = 12 (k=%d)", k);
+    const int pair = (algo == KC_DENSE_PARTITION_PAIR) ? 1 : (algo == KC_DENSE_PARTITION_TRIO) ? 2 : 0;
+    if (pair && k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_PAIR/TRIO are built for k = 12 (k=%d)", k);
     if (defer || pair) algo = KC_DENSE_PARTITION;
     DeviceGuard dg(ctx->device);
     if (nbytes < (uint64_t)k) return KC_OK;

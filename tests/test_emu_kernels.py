@@ -96,6 +96,17 @@ def test_partition_paired_count_variant():
     assert st[7] >= 1024, st   # the odd partitions went through the 32-bit recount
 
 
+def test_partition_two_increment_count_variant():
+    """KC_DENSE_PARTITION_TRIO (algo 6, k = 12): one 14-mer (8-bit fields) + one 13-mer (16-bit fields)
+    per record = 2 increments instead of 5; poly-A makes 8-bit fields wrap for real (partition 0 holds
+    ~500 identical records): the checksum must catch it and the 32-bit recount must be exact."""
+    run_case("dense", 12, 400_000, 6, "genome", 2, 0)
+    run_case("dense", 12, 400_000, 6, "dirty", 5, 7, seed=3, sms=2)
+    run_case("dense", 12, 300_000, 6, "skew", 6, 2)
+    st = emu_stats(run_case("dense", 12, 2_500_000, 6, "polyA", 6, 2))
+    assert st[7] == 2048, st   # partition 0, twice (whole table + window sub-range), 1024 threads each
+
+
 def test_k8_checksum_variant():
     """KC_DENSE_SMEM16C (algo 3): non-returning shared adds, per-CTA checksum, repair of the CTAs
     whose 16-bit fields wrapped.  Uniform input: no CTA is repaired; one-bin inputs: every CTA is."""
