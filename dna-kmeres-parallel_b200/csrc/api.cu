@@ -6,6 +6,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -386,6 +387,14 @@ int parse_fasta(const char* img, size_t n, int mode, long max_seqs, kc_seqset* s
 // ---------------------------------------------------------------------------
 enum { ST_IDLE = 0, ST_ARMED = 1, ST_INREC = 2 };
 
+struct ThreadGroup {  // joins whatever was started, also when starting the next thread throws
+    std::vector<std::thread> th;
+    ~ThreadGroup() {
+        for (auto& t : th)
+            if (t.joinable()) t.join();
+    }
+};
+
 struct ChunkSummary {
     int end_state[3];
     uint64_t bytes[3], recs[3], ids[3];
@@ -482,10 +491,9 @@ int parse_fasta_threads(const char* img, size_t n, int mode, int nthreads, kc_se
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_a = now();
     {
-        std::vector<std::thread> th;
-        for (int c = 1; c < nc; c++) th.emplace_back(summarize_chunk, img + cut[c], img + cut[c + 1], mode, &sum[c]);
+        ThreadGroup g;
+        for (int c = 1; c < nc; c++) g.th.emplace_back(summarize_chunk, img + cut[c], img + cut[c + 1], mode, &sum[c]);
         summarize_chunk(img + cut[0], img + cut[1], mode, &sum[0]);
-        for (auto& t : th) t.join();
     }
     const double t_b = now();
     std::vector<int> st0(nc);
@@ -511,14 +519,20 @@ int parse_fasta_threads(const char* img, size_t n, int mode, int nthreads, kc_se
     s->offsets.assign(rec + 1, 0);
     s->ids.assign(nid, std::string());
     const double t_c = now();
+    std::atomic<int> emit_failed{0};
+    auto emit_guarded = [&](int c) {
+        try {
+            emit_chunk(img + cut[c], img + cut[c + 1], mode, st0[c], s->data, pos0[c], s->offsets.data(), rec0[c], s->ids.data() + id0[c]);
+        } catch (...) {  // std::string growth of an id: the only allocation in pass 2
+            emit_failed = 1;
+        }
+    };
     {
-        std::vector<std::thread> th;
-        for (int c = 1; c < nc; c++)
-            th.emplace_back(emit_chunk, img + cut[c], img + cut[c + 1], mode, st0[c], s->data, pos0[c], s->offsets.data(), rec0[c],
-                            s->ids.data() + id0[c]);
-        emit_chunk(img + cut[0], img + cut[1], mode, st0[0], s->data, pos0[0], s->offsets.data(), rec0[0], s->ids.data() + id0[0]);
-        for (auto& t : th) t.join();
+        ThreadGroup g;
+        for (int c = 1; c < nc; c++) g.th.emplace_back(emit_guarded, c);
+        emit_guarded(0);
     }
+    if (emit_failed) return kc_set_error(nullptr, KC_ERR_NOMEM, "kc_import_seqs: out of memory while copying record ids");
     if (dbg)
         fprintf(stderr, "kc_import_seqs: %d chunks, pass 1 %.3f s, stitch+alloc %.3f s, pass 2 %.3f s\n", nc, t_b - t_a, t_c - t_b,
                 now() - t_c);
@@ -534,6 +548,7 @@ extern "C" {
 
 int kc_import_seqs_mem_threads(const char* fasta, size_t nbytes, int mode, int nthreads, kc_seqset** out) {
     if (!out || (!fasta && nbytes)) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs_mem_threads: null pointer");
+    *out = nullptr;
     if (mode != KC_IMPORT_BLANKLINE && mode != KC_IMPORT_NONL)
         return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs: unknown mode %d", mode);
     if (nthreads <= 0) {
@@ -544,7 +559,12 @@ int kc_import_seqs_mem_threads(const char* fasta, size_t nbytes, int mode, int n
         if ((size_t)nthreads > by_size) nthreads = (int)by_size;
     }
     kc_seqset* s = new kc_seqset();
-    const int rc = parse_fasta_threads(fasta, nbytes, mode, nthreads, s);
+    int rc;
+    try {  // no C++ exception may cross the C ABI (thread creation, allocation of ids / offsets)
+        rc = parse_fasta_threads(fasta, nbytes, mode, nthreads, s);
+    } catch (const std::exception& e) {
+        rc = kc_set_error(nullptr, KC_ERR_NOMEM, "kc_import_seqs: %s", e.what());
+    }
     if (rc) {
         delete s;
         return rc;
