@@ -580,7 +580,12 @@ int kc_import_seqs_mem(const char* fasta, size_t nbytes, int mode, long max_seqs
     if (mode != KC_IMPORT_BLANKLINE && mode != KC_IMPORT_NONL)
         return kc_set_error(nullptr, KC_ERR_INVALID, "kc_import_seqs: unknown mode %d", mode);
     kc_seqset* s = new kc_seqset();
-    const int rc = parse_fasta(fasta, nbytes, mode, max_seqs, s);
+    int rc;
+    try {
+        rc = parse_fasta(fasta, nbytes, mode, max_seqs, s);
+    } catch (const std::exception& e) {
+        rc = kc_set_error(nullptr, KC_ERR_NOMEM, "kc_import_seqs: %s", e.what());
+    }
     if (rc) {
         delete s;
         return rc;
