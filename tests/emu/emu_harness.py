@@ -55,6 +55,8 @@ def lib():
         L.kc_sparse_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_kmer_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.kc_gen_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kc_count_dense_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.kc_count_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
         L.kc_sparse_radix_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -309,7 +311,27 @@ def case_radix_sharded(args):
     print("ok radix_sharded", *args, "distinct per rank", [int(kk.size) for kk in keys])
 
 
-CASES = {"radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+def case_dense_host(args):
+    """kc_count_dense_host: host buffer in, host table out (chunked staging + counting of the windows
+    that END inside each chunk), and kc_count_dense (zeroing entry point)"""
+    k, n, seed = int(args[0]), int(args[1]), int(args[2])
+    O = _oracle()
+    data = make_input("genome", n, seed, k)
+    ctx = EmuContext()
+    table = np.full(4 ** k, 0xDEADBEEF, dtype=np.uint32)
+    ctx.check(ctx.L.kc_count_dense_host(ctx.h, data.ctypes.data, n, k, table.ctypes.data))
+    want, _ = O.count_dense(data, k)
+    assert (table == want).all(), "kc_count_dense_host differs"
+    base, p = ctx.upload(data, 9)
+    t = ctx.alloc(4 << (2 * k))
+    ctx.check(ctx.L.kc_memset_d(ctx.h, t, 0x5A, 4 << (2 * k)))  # kc_count_dense must overwrite, not add
+    ctx.check(ctx.L.kc_count_dense(ctx.h, p, n, k, t))
+    assert (ctx.download(t, 4 << (2 * k), np.uint32) == want).all(), "kc_count_dense differs"
+    ctx.close()
+    print("ok dense_host", *args)
+
+
+CASES = {"dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

@@ -177,6 +177,11 @@ def test_sparse_radix_production_shape():
     run_case("sparse", 21, 40_000, RADIX | NOFB, "readsU", 9, 0, seed=0, sms=2)
 
 
+def test_host_entry_points_on_emulator():
+    run_case("dense_host", 5, 300_000, 1)
+    run_case("dense_host", 12, 200_000, 2)
+
+
 def test_perseq_distance_and_generators_on_emulator():
     run_case("perseq", 3, 37, 1)     # shared-memory bins per (sequence, tile) segment
     run_case("perseq", 6, 9, 2)
