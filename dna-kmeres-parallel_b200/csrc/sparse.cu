@@ -322,6 +322,9 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
     }
     const int halo = (k <= 17) ? 1 : 2;
 
+    // 2^20 leaves and a 1024-partition queue only pay off on real volumes: below 4 M windows the
+    // hash path is the faster one (KC_SPARSE_NO_FALLBACK insists on the radix kernels: tests)
+    if (algo == KC_SPARSE_RADIX && !no_fallback && nwin < (1ull << 22) && !getenv("KC_SPARSE_RADIX_SHAPE")) algo = KC_SPARSE_HASH;
     if (algo == KC_SPARSE_RADIX) {
         int failed = 0;
         const int rc = kc_sparse_radix(ctx, d_data, nbytes, k, out, &failed);

@@ -196,7 +196,8 @@ KC_API int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
 #define KC_SPARSE_HASH 0   /* open-addressing hash table (CAS key, RED count) */
 #define KC_SPARSE_SORT 1   /* radix sort of codes + run-length reduce          */
 #define KC_SPARSE_RADIX 2  /* MSD radix partition, leaves sorted in shared memory (k >= 11);
-                              falls back to KC_SPARSE_HASH when skewed data overflows a region */
+                              falls back to KC_SPARSE_HASH when skewed data overflows a region, and
+                              takes that path directly for inputs below 4 M windows            */
 /* OR-ed into `algo`: leave the distinct (code,count) pairs in table order instead of
  * sorting them — for callers that re-bucket and merge anyway (the multi-GPU path).   */
 #define KC_SPARSE_UNSORTED 0x100
