@@ -41,7 +41,7 @@ def test_sparse_radix_deep_coverage_and_fallback(ctx, kmerlib, oracle):
     """deep coverage (counts >> 1) and an input that must overflow a leaf (one k-mer only):
     with fallback allowed both give the oracle's result."""
     reads = oracle.gen_reads(0xB2000004, 200_000, 150, 200, 0, 40_000)
-    poly = np.full(3_000_000, ord("A"), dtype=np.uint8)
+    poly = np.full(8_000_000, ord("A"), dtype=np.uint8)  # >= 4 M windows: the radix kernels run, overflow, and the hash path recounts
     for data, k in ((reads, 21), (reads, 31), (poly, 21)):
         wk, wc, _ = oracle.count_sparse(data, k)
         keys, counts = ctx.count_sparse(to_dev(data), data.size, k, kmerlib.SPARSE_RADIX).to_host()
