@@ -53,6 +53,9 @@ for R in 20000000 0; do for A in hash radix; do
   timeout 600 python bench.py --workload config4 --reads $R --sparse-algo $A --steps 1 --warmup 1 > $O/r02_c4_${A}_$R.log 2> $O/r02_c4_${A}_$R.err
   echo "config4 reads=$R algo=$A rc=$?"; cut -c1-400 $O/r02_c4_${A}_$R.log; tail -2 $O/r02_c4_${A}_$R.err
 done; done
+echo "== 3a. sparse radix with 256-bit flush stores (KC_RADIX_FLUSH=1), config 4 at 1/5 scale"
+KC_RADIX_FLUSH=1 timeout 600 python bench.py --workload config4 --reads 20000000 --sparse-algo radix --steps 1 --warmup 1 > $O/r02_c4_radix256.log 2> $O/r02_c4_radix256.err
+echo "rc=$?"; cut -c1-300 $O/r02_c4_radix256.log
 echo "== 3b. primitive rates (tools/microbench3): shared increments by pattern, flush variants"
 make -s -C tools microbench3 2>/dev/null; timeout 120 tools/microbench3 > $O/r02_microbench3.txt 2>&1; cat $O/r02_microbench3.txt
 echo "== 4. default bench line (with e2e + cpu baseline)"
