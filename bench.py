@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="sparse workloads: number of reads (0 = full scale)")
     ap.add_argument("--sparse-algo", default="hash", choices=["hash", "sort", "radix"])
     ap.add_argument("--capacity-hint", type=int, default=0, help="sparse hash: expected distinct k-mers")
-    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition, 3 k=8 checksum variant, 4 partition with deferred retry, 5 partition with paired count (k=12), 6 partition with 14-mer + 13-mer count (k=12)")
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition, 3 k=8 checksum variant, 4 partition with deferred retry, 5 partition with paired count (k=12), 6 partition with 14-mer + 13-mer count (k=12), 7 partition with seven windows per record (k=12)")
     ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="bases of the CPU-baseline sample")
     ap.add_argument("--ref-sample", type=int, default=1 << 30, help="bases per step of the reference arm")
@@ -432,7 +432,10 @@ def main():
     elif p2 > 0:  # two-pass partition path (the count kernel has measured-later variants: --algo 5/6, KC_PART_PAIR)
         pm = {5: 1, 6: 2}.get(args.algo, int(os.environ.get("KC_PART_PAIR", "0") or 0)) if k == 12 else 0
         cname = {0: "part_count_kernel", 1: "part_count_pair12_kernel", 2: "part_count_trio12_kernel"}.get(pm, "part_count_kernel")
-        kernels = {"part_scatter_kernel": (p1, bases_launch), cname: (p2, 4 * nk)}
+        sname = "part_scatter_kernel"
+        if args.algo == 7:
+            sname, cname = "part_scatter7_kernel", "part_count7_kernel"
+        kernels = {sname: (p1, bases_launch), cname: (p2, 4 * nk)}
     else:
         kernels = {"dense_direct_kernel": (p1, bases_launch + 4 * nk)}
     dom = max(kernels, key=lambda n: kernels[n][0])
@@ -553,7 +556,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "bases": L, "kmers_per_sec": (L - k + 1) / (ms_step * 1e-3),
-                       "algo": {0: "auto", 1: "direct", 2: "partition", 3: "smem16-checksum", 4: "partition-deferred-retry", 5: "partition-paired-count", 6: "partition-two-increment-count"}[args.algo],
+                       "algo": {0: "auto", 1: "direct", 2: "partition", 3: "smem16-checksum", 4: "partition-deferred-retry", 5: "partition-paired-count", 6: "partition-two-increment-count", 7: "partition-wide-records"}[args.algo],
                        "launch": "CUDA graph replay" if graph is not None else "plain launches",
                        "l2": ("input %.2f GB per GPU (+ as much scratch written per step) exceeds the 126 MB L2: "
                               "no flush needed" % (nb / 1e9)) if nb > 252e6 else

@@ -62,6 +62,13 @@ struct kc_sparse {
 // overflow made the result unusable and nothing was produced (the caller recounts)
 int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed);
 
+// dense.cu: the direct (shared-bin / global-RED) kernels on a window range; dense_wide.cu: the k = 12
+// partition path with seven windows per record
+int kc_dense_direct_range(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end, int k,
+                          uint32_t* d_table, cudaStream_t st);
+int kc_dense_partition_wide(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
+                            uint32_t* d_table, cudaStream_t st);
+
 int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...);
 int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes);   // ctx->scratch  >= nbytes
 int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes);  // ctx->scratch2 >= nbytes

@@ -1251,6 +1251,11 @@ static int dense_smem16(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64
     return rc;
 }
 
+int kc_dense_direct_range(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end, int k,
+                          uint32_t* d_table, cudaStream_t st) {
+    return dense_direct(ctx, kc_make_geom(d_data, nbytes, win_begin, win_end, k), d_table, st);
+}
+
 static uint64_t g_partition_min_windows = 1ull << 26;  // below this the direct path wins
 
 extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
@@ -1260,7 +1265,8 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
     if (!d_table || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION && algo != KC_DENSE_SMEM16C &&
-        algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR && algo != KC_DENSE_PARTITION_TRIO)
+        algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR && algo != KC_DENSE_PARTITION_TRIO &&
+        algo != KC_DENSE_PARTITION_WIDE)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown dense algo %d", algo);
     if (algo == KC_DENSE_SMEM16C) {
         if (k != 8) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_SMEM16C is the k = 8 path (k=%d)", k);
@@ -1269,6 +1275,14 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         if (win_end > nbytes - 7) win_end = nbytes - 7;
         if (win_begin >= win_end) return KC_OK;
         return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream, true);
+    }
+    if (algo == KC_DENSE_PARTITION_WIDE) {
+        if (k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_WIDE is built for k = 12 (k=%d)", k);
+        DeviceGuard dgw(ctx->device);
+        if (nbytes < 12) return KC_OK;
+        if (win_end > nbytes - 11) win_end = nbytes - 11;
+        if (win_begin >= win_end) return KC_OK;
+        return kc_dense_partition_wide(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream);
     }
     const bool defer = (algo == KC_DENSE_PARTITION_DEFER);
     const int pair = (algo == KC_DENSE_PARTITION_PAIR) ? 1 : (algo == KC_DENSE_PARTITION_TRIO) ? 2 : 0;

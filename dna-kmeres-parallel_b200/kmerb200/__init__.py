@@ -18,7 +18,8 @@ HEADER_PATH = os.path.join(REPO_ROOT, "include", "kmer_b200.h")
 KC_OK = 0
 KC_ERR_INVALID, KC_ERR_CUDA, KC_ERR_IO, KC_ERR_NOMEM, KC_ERR_TABLE_FULL, KC_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 DENSE_AUTO, DENSE_DIRECT, DENSE_PARTITION = 0, 1, 2
-DENSE_SMEM16C, DENSE_PARTITION_DEFER, DENSE_PARTITION_PAIR, DENSE_PARTITION_TRIO = 3, 4, 5, 6  # first B200 run pending; never chosen by DENSE_AUTO
+DENSE_SMEM16C, DENSE_PARTITION_DEFER, DENSE_PARTITION_PAIR, DENSE_PARTITION_TRIO = 3, 4, 5, 6
+DENSE_PARTITION_WIDE = 7  # first B200 run pending; never chosen by DENSE_AUTO
 SPARSE_HASH, SPARSE_SORT, SPARSE_RADIX = 0, 1, 2
 SPARSE_UNSORTED = 0x100
 SPARSE_NO_FALLBACK = 0x200

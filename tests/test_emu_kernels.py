@@ -107,6 +107,18 @@ def test_partition_two_increment_count_variant():
     assert st[7] == 2048, st   # partition 0, twice (whole table + window sub-range), 1024 threads each
 
 
+def test_partition_wide_record_variant():
+    """KC_DENSE_PARTITION_WIDE (algo 7, k = 12): seven windows per record (18 bases; the slab record omits
+    the 11 key bits), pass 2 with two 4-bit 14-mer tables + one 16-bit 12-mer table.  Random schedule on
+    skewed input: deferred retries, nibble wraps -> 32-bit recount; poly-A; forced recount."""
+    run_case("dense", 12, 400_000, 7, "genome", 2, 0)
+    run_case("dense", 12, 400_000, 7, "dirty", 5, 7)
+    st = emu_stats(run_case("dense", 12, 300_000, 7, "skew", 6, 2, seed=3, sms=2, shift=1))
+    assert st[1] > 100 and st[7] >= 1024, st   # deferred retries happened; at least one partition wrapped and was recounted
+    st = emu_stats(run_case("dense", 12, 2_500_000, 7, "polyA", 6, 2))
+    assert st[7] >= 1024, st
+
+
 def test_k8_checksum_variant():
     """KC_DENSE_SMEM16C (algo 3): non-returning shared adds, per-CTA checksum, repair of the CTAs
     whose 16-bit fields wrapped.  Uniform input: no CTA is repaired; one-bin inputs: every CTA is."""

@@ -122,6 +122,30 @@ def test_partition_two_increment_count(ctx, kmerlib, oracle):
     assert int(t[0].item()) == (1 << 26) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 26) - 11
 
 
+def test_partition_wide_records(ctx, kmerlib, oracle):
+    """KC_DENSE_PARTITION_WIDE (k = 12, seven windows per record) against the oracle, against the shipped
+    path at 1 Gbp, and on 2^26 'A's (4-bit fields wrap: checksum + 32-bit recount)"""
+    import torch
+    n = 40_000_000
+    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
+    want, _ = oracle.count_dense(genome, 12)
+    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_WIDE) == want).all()
+    L = 1 << 30
+    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
+    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    b = torch.zeros_like(a)
+    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
+    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_WIDE)
+    torch.cuda.synchronize()
+    assert bool((a == b).all())
+    del data, a, b
+    poly = torch.full((1 << 26,), ord("A"), dtype=torch.uint8, device="cuda:0")
+    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    ctx.count_dense_range(poly, 1 << 26, 0, 1 << 26, 12, t, algo=kmerlib.DENSE_PARTITION_WIDE)
+    torch.cuda.synchronize()
+    assert int(t[0].item()) == (1 << 26) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 26) - 11
+
+
 def test_partition_paired_count(ctx, kmerlib, oracle):
     """KC_DENSE_PARTITION_PAIR (k = 12) against the oracle, and against the shipped path at 1 Gbp;
     2^30 'A's: partition 0's regions hold ~127 K identical records (148 regions of ~860), one 16-bit
