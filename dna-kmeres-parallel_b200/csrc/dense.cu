@@ -271,16 +271,13 @@ dense_smem16c_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t*
     }
     __syncthreads();
     // checksum: sum of all 16-bit fields vs the adds this CTA made
-    unsigned long long fsum = 0, asum = nadds;
+    // (per-warp sums fit 32 bits: a CTA makes < 2^32 adds; REDUX does each in one instruction)
+    uint32_t f32 = 0;
     for (int i = tid; i < 32768; i += 1024) {
         const uint32_t v = words[i];
-        fsum += (v & 0xFFFFu) + (v >> 16);
+        f32 += (v & 0xFFFFu) + (v >> 16);
     }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        fsum += __shfl_down_sync(0xffffffffu, fsum, d);
-        asum += __shfl_down_sync(0xffffffffu, asum, d);
-    }
+    const unsigned long long fsum = __reduce_add_sync(0xffffffffu, f32), asum = __reduce_add_sync(0xffffffffu, nadds);
     if (lane == 0) {
         s_red[tid >> 5] = fsum;
         s_red[32 + (tid >> 5)] = asum;
@@ -794,16 +791,12 @@ part_count_pair12_kernel(uint32_t* __restrict__ table, const uint32_t* __restric
         for_each_record(count_rec);
         __syncthreads();
         // checksum: the 16-bit fields of T0 and T2 must add up to two increments per record
-        unsigned long long fsum = 0, asum = 2ull * nrec;
+        uint32_t f32 = 0;  // per-warp sums fit 32 bits (a partition holds < 2^31 records); one REDUX each
         for (int i = tid; i < 32768; i += 1024) {
             const uint32_t v = bins[i];
-            fsum += (v & 0xFFFFu) + (v >> 16);
+            f32 += (v & 0xFFFFu) + (v >> 16);
         }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            fsum += __shfl_down_sync(0xffffffffu, fsum, d);
-            asum += __shfl_down_sync(0xffffffffu, asum, d);
-        }
+        const unsigned long long fsum = __reduce_add_sync(0xffffffffu, f32), asum = __reduce_add_sync(0xffffffffu, 2u * nrec);
         if (lane == 0) {
             s_red[warp] = fsum;
             s_red[32 + warp] = asum;
@@ -971,18 +964,14 @@ part_count_trio12_kernel(uint32_t* __restrict__ table, const uint32_t* __restric
         for_each_record(count_rec);
         __syncthreads();
         // checksums: every record put one increment into each table
-        unsigned long long s14 = 0, s13 = 0, asum = nrec;
-        for (int i = tid; i < (int)W13; i += 1024) s14 += bytesum(bins[i]);
+        uint32_t a14 = 0, a13 = 0;  // per-warp sums fit 32 bits; one REDUX each
+        for (int i = tid; i < (int)W13; i += 1024) a14 += bytesum(bins[i]);
         for (int i = tid; i < 16384; i += 1024) {
             const uint32_t v = bins[W13 + i];
-            s13 += (v & 0xFFFFu) + (v >> 16);
+            a13 += (v & 0xFFFFu) + (v >> 16);
         }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            s14 += __shfl_down_sync(0xffffffffu, s14, d);
-            s13 += __shfl_down_sync(0xffffffffu, s13, d);
-            asum += __shfl_down_sync(0xffffffffu, asum, d);
-        }
+        const unsigned long long s14 = __reduce_add_sync(0xffffffffu, a14), s13 = __reduce_add_sync(0xffffffffu, a13),
+                                 asum = __reduce_add_sync(0xffffffffu, nrec);
         if (lane == 0) {
             s_red[warp] = s14;
             s_red[32 + warp] = s13;

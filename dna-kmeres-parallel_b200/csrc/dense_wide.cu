@@ -276,22 +276,17 @@ part_count7_kernel(uint32_t* __restrict__ table, const uint32_t* __restrict__ sl
         };
         for_each_record(count_rec);
         __syncthreads();
-        unsigned long long s0 = 0, s3 = 0, s6 = 0, asum = nrec;
+        uint32_t a0 = 0, a3 = 0, a6 = 0;  // per-warp sums fit 32 bits; one REDUX each
         for (int i = tid; i < 16384; i += 1024) {
-            s0 += nibsum(bins[i]);
-            s3 += nibsum(bins[W3 + i]);
+            a0 += nibsum(bins[i]);
+            a3 += nibsum(bins[W3 + i]);
         }
         for (int i = tid; i < 4096; i += 1024) {
             const uint32_t v = bins[W6 + i];
-            s6 += (v & 0xFFFFu) + (v >> 16);
+            a6 += (v & 0xFFFFu) + (v >> 16);
         }
-#pragma unroll
-        for (int dd = 16; dd >= 1; dd >>= 1) {
-            s0 += __shfl_down_sync(0xffffffffu, s0, dd);
-            s3 += __shfl_down_sync(0xffffffffu, s3, dd);
-            s6 += __shfl_down_sync(0xffffffffu, s6, dd);
-            asum += __shfl_down_sync(0xffffffffu, asum, dd);
-        }
+        const unsigned long long s0 = __reduce_add_sync(0xffffffffu, a0), s3 = __reduce_add_sync(0xffffffffu, a3),
+                                 s6 = __reduce_add_sync(0xffffffffu, a6), asum = __reduce_add_sync(0xffffffffu, nrec);
         if (lane == 0) {
             s_red[warp] = s0;
             s_red[32 + warp] = s3;

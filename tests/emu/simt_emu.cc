@@ -178,6 +178,12 @@ uint32_t warp_exchange(uint32_t mask, uint32_t v, int kind, int arg) {
         }
         case EMU_BALLOT:
             return W.ballot[p] & mask;
+        case EMU_REDUCE_ADD: {
+            uint32_t sum = 0;
+            for (int l = 0; l < 32; l++)
+                if (mask & (1u << l)) sum += W.vals[p][l];
+            return sum;
+        }
         default:
             return 0;
     }

@@ -152,7 +152,7 @@ static inline uint32_t __brev(uint32_t x) {
     return r;
 }
 
-enum { EMU_SHFL_IDX = 0, EMU_SHFL_DOWN = 1, EMU_SHFL_UP = 2, EMU_SHFL_XOR = 3, EMU_BALLOT = 4, EMU_SYNCWARP = 5 };
+enum { EMU_SHFL_IDX = 0, EMU_SHFL_DOWN = 1, EMU_SHFL_UP = 2, EMU_SHFL_XOR = 3, EMU_BALLOT = 4, EMU_SYNCWARP = 5, EMU_REDUCE_ADD = 6 };
 template <class T>
 static inline T emu_shfl(uint32_t mask, T v, int kind, int arg) {
     static_assert(sizeof(T) == 4 || sizeof(T) == 8, "shuffle of 32/64-bit values");
@@ -182,6 +182,7 @@ static inline T __shfl_xor_sync(uint32_t mask, T v, int m) { return emu_shfl(mas
 static inline uint32_t __ballot_sync(uint32_t mask, int pred) { return emu::warp_exchange(mask, pred ? 1u : 0u, EMU_BALLOT, 0); }
 static inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(uint32_t mask, int pred) { return (__ballot_sync(mask, pred) & mask) == mask; }
+static inline uint32_t __reduce_add_sync(uint32_t mask, uint32_t v) { return emu::warp_exchange(mask, v, EMU_REDUCE_ADD, 0); }
 static inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu::warp_exchange(mask, 0, EMU_SYNCWARP, 0); }
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __threadfence() { emu::maybe_preempt(); }
