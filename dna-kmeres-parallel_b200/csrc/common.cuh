@@ -144,6 +144,16 @@ __device__ __forceinline__ uint32_t kc_nzbytes4(uint32_t w) {
     return (h * 0x10204080u) >> 28;  // gather bits 0,8,16,24 -> 0..3
 }
 
+// 16 bad bits -> 32-bit mask with both bits of every bad base's 2-bit group set
+__device__ __forceinline__ uint32_t kc_spread_bad(uint32_t bad16) {
+    uint32_t x = bad16 & 0xFFFFu;          // bit j -> bits 2j, 2j+1
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+
 struct Decoded16 {
     uint32_t packed;  // 16 bases, 2 bits each, base j at bits [2j,2j+2)
     uint32_t bad;     // bit j set <=> base j is not ACGT (16 bits)

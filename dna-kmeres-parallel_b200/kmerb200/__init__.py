@@ -91,6 +91,11 @@ def lib():
         "kc_count_dense_range_async": (i32, [vp, vp, u64, u64, u64, i32, vp, i32, vp]),
         "kc_count_dense_host": (i32, [vp, vp, u64, i32, vp]),
         "kc_count_sparse": (i32, [vp, vp, u64, i32, i32, u64, C.POINTER(vp)]),
+        "kc_packed_bytes": (u64, [u64]),
+        "kc_badmask_bytes": (u64, [u64]),
+        "kc_pack_2bit": (i32, [vp, vp, u64, vp, vp, vp]),
+        "kc_unpack_2bit": (i32, [vp, vp, vp, u64, vp, vp]),
+        "kc_count_dense_packed": (i32, [vp, vp, vp, u64, i32, vp]),
         "kc_sparse_radix_plan": (i32, [vp, u64, i32, C.c_uint32, vp]),
         "kc_sparse_radix_scatter": (i32, [vp, vp, u64, vp, vp, vp]),
         "kc_sparse_radix_count": (i32, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
@@ -392,6 +397,32 @@ class Context:
         h = C.c_void_p()
         self._check(lib().kc_count_sparse(self._h, _ptr(d_data), nbytes, k, algo, capacity_hint, C.byref(h)))
         return Sparse(self, h)
+
+    # ---- 2-bit packed store ("next" row f4) ------------------------------------------------
+    def pack_2bit(self, d_data, nbytes):
+        """-> (packed uint8[(n+3)/4], badmask int32[(n+31)/32]) on this GPU"""
+        torch = self._torch()
+        dev = "cuda:%d" % self.device
+        packed = torch.empty(int(lib().kc_packed_bytes(nbytes)) + 4, dtype=torch.uint8, device=dev)
+        mask = torch.empty(int(lib().kc_badmask_bytes(nbytes)) // 4 + 1, dtype=torch.int32, device=dev)
+        self._check(lib().kc_pack_2bit(self._h, _ptr(d_data), nbytes, _ptr(packed), _ptr(mask), _stream_handle(None)))
+        torch.cuda.current_stream().synchronize()
+        return packed, mask
+
+    def unpack_2bit(self, packed, mask, nbases):
+        torch = self._torch()
+        out = torch.empty(nbases, dtype=torch.uint8, device="cuda:%d" % self.device)
+        self._check(lib().kc_unpack_2bit(self._h, _ptr(packed), _ptr(mask), nbases, _ptr(out), _stream_handle(None)))
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def count_dense_packed(self, packed, mask, nbases, k, table=None):
+        torch = self._torch()
+        torch.cuda.current_stream().synchronize()
+        if table is None:
+            table = torch.empty(num_kmers(k), dtype=torch.int32, device="cuda:%d" % self.device)
+        self._check(lib().kc_count_dense_packed(self._h, _ptr(packed), _ptr(mask), nbases, k, _ptr(table)))
+        return table
 
     # ---- stages of KC_SPARSE_RADIX (the multi-GPU path runs an all-to-all between them) ----
     def radix_plan(self, max_windows, k, world):

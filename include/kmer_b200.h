@@ -259,6 +259,28 @@ KC_API int kc_sparse_merge(kc_ctx* ctx, const uint64_t* d_keys, const uint32_t* 
 KC_API uint64_t kc_mix64(uint64_t code);
 
 /* ------------------------------------------------------------------ */
+/* "Next" row f4: the 2-bit packed sequence store sketched in the      */
+/* reference's comments (main.cu:78-86, utils.h:65-92: "AACG ->        */
+/* 00000110", four bases per byte, the first base in the two most      */
+/* significant bits, A=00 C=01 G=10 T=11), plus a validity bitmap so   */
+/* that N / separators / lower case keep resetting the window:         */
+/* bit i%32 of word i/32 (LSB first) is set iff byte i was not an      */
+/* upper-case ACGT; such bases pack as 00.  0.375 B/base at rest.      */
+/* ------------------------------------------------------------------ */
+KC_API uint64_t kc_packed_bytes(uint64_t nbases);   /* (n+3)/4        */
+KC_API uint64_t kc_badmask_bytes(uint64_t nbases);  /* (n+31)/32 * 4  */
+/* d_data 16-byte aligned (any cudaMalloc'ed buffer), d_packed 4-byte aligned */
+KC_API int kc_pack_2bit(kc_ctx* ctx, const char* d_data, uint64_t nbytes, void* d_packed,
+                        uint32_t* d_badmask, void* stream);
+/* inverse; invalid bases come back as 'N' (their identity is not stored)     */
+KC_API int kc_unpack_2bit(kc_ctx* ctx, const void* d_packed, const uint32_t* d_badmask,
+                          uint64_t nbases, char* d_data_out, void* stream);
+/* == kc_count_dense of the bytes the store was packed from (synchronous; d_table overwritten):
+ * 2^27-base chunks are unpacked into an ASCII scratch and counted by the ordinary dense path */
+KC_API int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32_t* d_badmask,
+                                 uint64_t nbases, int k, uint32_t* d_table);
+
+/* ------------------------------------------------------------------ */
 /* Count table dump.  Byte-identical to the (commented-out) dump at    */
 /* main.cu:301-309: "Sums:\n", per k-mer row "%d: " then "%d,\t" per   */
 /* sequence then "\n", and a final "\n".  h_sums is a HOST table       */

@@ -57,6 +57,13 @@ def lib():
         L.kc_gen_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.kc_count_dense_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_count_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.kc_packed_bytes.restype = C.c_uint64
+        L.kc_packed_bytes.argtypes = [C.c_uint64]
+        L.kc_badmask_bytes.restype = C.c_uint64
+        L.kc_badmask_bytes.argtypes = [C.c_uint64]
+        L.kc_pack_2bit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kc_unpack_2bit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kc_count_dense_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
         L.kc_sparse_radix_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -331,7 +338,49 @@ def case_dense_host(args):
     print("ok dense_host", *args)
 
 
-CASES = {"dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+def case_packed(args):
+    """f4: pack -> the reference sketch's layout (first base in the top two bits of each byte) + validity
+    bitmap; unpack is the inverse up to invalid -> 'N'; counting from the store == counting the bytes"""
+    k, n, seed = int(args[0]), int(args[1]), int(args[2])
+    O = _oracle()
+    data = make_input("dirty", n, seed, k)
+    m = min(5000, n - n // 3)  # a clean stretch, so that large k sees valid windows too
+    data[n // 3: n // 3 + m] = np.frombuffer(b"ACGT", dtype=np.uint8)[np.random.default_rng(seed).integers(0, 4, m)]
+    ctx = EmuContext()
+    L = ctx.L
+    base, p = ctx.upload(data)
+    pb, mb = int(L.kc_packed_bytes(n)), int(L.kc_badmask_bytes(n))
+    assert pb == (n + 3) // 4 and mb == (n + 31) // 32 * 4
+    d_p, d_m = ctx.alloc(pb), ctx.alloc(mb)
+    ctx.check(L.kc_pack_2bit(ctx.h, p, n, d_p, d_m, None))
+    packed = ctx.download(d_p, pb, np.uint8)
+    mask = ctx.download(d_m, mb, np.uint32)
+    code = np.full(256, -1, dtype=np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = code[data]
+    bad = c < 0
+    c2 = np.where(bad, 0, c).astype(np.uint8)
+    pad = np.zeros((-n) % 4, dtype=np.uint8)
+    q = np.concatenate([c2, pad]).reshape(-1, 4)
+    want_packed = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]    # "AACG -> 00000110" (main.cu:83)
+    assert (packed == want_packed).all(), "packed bytes differ"
+    bits = np.concatenate([bad, np.ones((-n) % 32, dtype=bool)]).reshape(-1, 32)   # bases past the end count as invalid
+    want_mask = (bits.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+    assert (mask == want_mask).all(), "validity bitmap differs"
+    d_o = ctx.alloc(n)
+    ctx.check(L.kc_unpack_2bit(ctx.h, d_p, d_m, n, d_o, None))
+    back = ctx.download(d_o, n, np.uint8)
+    assert (back == np.where(bad, ord("N"), data)).all(), "unpack is not the inverse"
+    t = ctx.alloc(4 << (2 * k))
+    ctx.check(L.kc_count_dense_packed(ctx.h, d_p, d_m, n, k, t))
+    want, _ = O.count_dense(data, k)
+    assert (ctx.download(t, 4 << (2 * k), np.uint32) == want).all(), "count from the packed store differs"
+    ctx.close()
+    print("ok packed", *args)
+
+
+CASES = {"packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

@@ -211,3 +211,12 @@ def test_sparse_radix_range_sharded_ranks_emulated(k, nreads, world):
         run_case("radix_sharded", k, nreads, world, 7 + world)
     finally:
         del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+def test_packed_store_on_emulator():
+    """f4: 2-bit packed store (layout of main.cu:78-86 + validity bitmap): pack, unpack, count in chunks"""
+    run_case("packed", 5, 100_003, 1)
+    run_case("packed", 12, 250_017, 2, KC_PACKED_CHUNK=30_000)
+    run_case("packed", 3, 1000, 3, KC_PACKED_CHUNK=64)
+    for n in (31, 3, 16, 17):
+        run_case("packed", 2, n, 6)

@@ -171,6 +171,39 @@ def test_partition_paired_count(ctx, kmerlib, oracle):
     assert int(t[0].item()) == (1 << 30) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 30) - 11
 
 
+def test_packed_store(ctx, kmerlib, oracle):
+    """f4: pack -> layout of main.cu:78-86 + validity bitmap; unpack inverse (invalid -> 'N'); counting
+    from the store equals counting the bytes (k = 5, 8, 12; the 200 Mbp case crosses a 2^27 chunk edge)"""
+    import torch
+    n = 5_000_003
+    data = oracle.gen_genome(0xB2000003, n, 5, 500, 12, 0, n).copy()
+    data[1000:1100] = np.frombuffer(b"acgtN\n\0|>x", dtype=np.uint8)[np.arange(100) % 10]
+    d = to_dev(data)
+    packed, mask = ctx.pack_2bit(d, n)
+    code = np.full(256, -1, dtype=np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = code[data]
+    bad = c < 0
+    q = np.concatenate([np.where(bad, 0, c).astype(np.uint8), np.zeros((-n) % 4, np.uint8)]).reshape(-1, 4)
+    want = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+    assert (packed[: want.size].cpu().numpy() == want).all()
+    back = ctx.unpack_2bit(packed, mask, n).cpu().numpy()
+    assert (back == np.where(bad, ord("N"), data)).all()
+    for k in (5, 8, 12):
+        t = ctx.count_dense_packed(packed, mask, n, k).cpu().numpy().view(np.uint32)
+        w, _ = oracle.count_dense(data, k)
+        assert (t == w).all(), k
+    L = 200_000_000
+    big = ctx.gen_genome(0xB2000003, L, 60, 600, 12, 0, L)
+    p2, m2 = ctx.pack_2bit(big, L)
+    a = ctx.count_dense_packed(p2, m2, L, 12)
+    b = torch.zeros_like(a)
+    ctx.count_dense_range(big, L, 0, L, 12, b)
+    torch.cuda.synchronize()
+    assert bool((a == b).all())
+
+
 def test_nccl_range_sharded_radix():
     """multi-GPU (>= 2 GPUs visible): scatter, all-to-all of the slabs, count per rank, vs the oracle"""
     import torch
