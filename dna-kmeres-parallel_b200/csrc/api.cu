@@ -267,19 +267,6 @@ int64_t kc_triangular_index(int64_t i, int64_t j, int64_t n) {
 // ---------------------------------------------------------------------------
 // FASTA loader (importSeqs main.cu:474-545, importSeqsNoNL main.cu:401-473)
 // ---------------------------------------------------------------------------
-struct kc_seqset {
-    std::vector<std::string> ids;
-    char* data = nullptr;           // sequences, each followed by '\0' (malloc'd, uninitialised tail)
-    size_t data_len = 0, data_cap = 0;
-    std::vector<int64_t> offsets;   // num_seqs + 1
-    ~kc_seqset() { free(data); }
-    uint32_t num_seqs = 0;
-    // device copies
-    kc_ctx* owner = nullptr;
-    char* d_data = nullptr;
-    int64_t* d_offsets = nullptr;
-};
-
 namespace {
 // The output image is written once, front to back: first-touch page faults are a large part
 // of the loader's time (4 KiB pages: 0.27 s per 400 MB here, and they do not scale with
@@ -633,7 +620,25 @@ void kc_seqset_free(kc_seqset* s) {
 uint32_t kc_seqset_num_seqs(const kc_seqset* s) { return s ? s->num_seqs : 0; }
 uint32_t kc_seqset_num_ids(const kc_seqset* s) { return s ? (uint32_t)s->ids.size() : 0; }
 uint64_t kc_seqset_nbytes(const kc_seqset* s) { return s ? s->data_len : 0; }
-const char* kc_seqset_data(const kc_seqset* s) { return s ? s->data : nullptr; }
+const char* kc_seqset_data(const kc_seqset* s) {
+    if (!s) return nullptr;
+    // a set parsed on the GPU (kc_import_seqs_device) fetches its host image on first use
+    if (!s->data && s->d_data && s->owner && s->data_len) {
+        kc_seqset* m = const_cast<kc_seqset*>(s);
+        DeviceGuard dg(m->owner->device);
+        char* h = (char*)malloc(m->data_len + 16);
+        if (!h) return nullptr;
+        if (cudaMemcpyAsync(h, m->d_data, m->data_len, cudaMemcpyDeviceToHost, m->owner->stream) != cudaSuccess ||
+            cudaStreamSynchronize(m->owner->stream) != cudaSuccess) {
+            cudaGetLastError();
+            free(h);
+            return nullptr;
+        }
+        m->data = h;
+        m->data_cap = m->data_len + 16;
+    }
+    return s->data;
+}
 const int64_t* kc_seqset_offsets(const kc_seqset* s) { return s ? s->offsets.data() : nullptr; }
 const char* kc_seqset_id(const kc_seqset* s, uint32_t i) {
     return (s && i < s->ids.size()) ? s->ids[i].c_str() : nullptr;

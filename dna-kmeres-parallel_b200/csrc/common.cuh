@@ -15,7 +15,10 @@
 #endif
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <string>
+#include <vector>
 
 #include "../../include/kmer_b200.h"
 
@@ -49,6 +52,21 @@ struct kc_ctx {
     bool timing = false;
     cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
     int timed_kernels = 0;
+};
+
+// what importSeqs leaves behind (main.cu:65-70,34-35): ids, the concatenated sequences, their offsets
+struct kc_seqset {
+    std::vector<std::string> ids;
+    char* data = nullptr;           // sequences, each followed by '\0' (malloc'd); fetched lazily when the
+                                    // set was parsed on the GPU (kc_seqset_data)
+    size_t data_len = 0, data_cap = 0;
+    std::vector<int64_t> offsets;   // num_seqs + 1
+    ~kc_seqset() { free(data); }
+    uint32_t num_seqs = 0;
+    // device copies
+    kc_ctx* owner = nullptr;
+    char* d_data = nullptr;
+    int64_t* d_offsets = nullptr;
 };
 
 // result of a sparse count: distinct codes ascending + their counts, both in device memory

@@ -91,6 +91,7 @@ def lib():
         "kc_count_dense_range_async": (i32, [vp, vp, u64, u64, u64, i32, vp, i32, vp]),
         "kc_count_dense_host": (i32, [vp, vp, u64, i32, vp]),
         "kc_count_sparse": (i32, [vp, vp, u64, i32, i32, u64, C.POINTER(vp)]),
+        "kc_import_seqs_device": (i32, [vp, vp, C.c_char_p, u64, i32, C.POINTER(vp)]),
         "kc_packed_bytes": (u64, [u64]),
         "kc_badmask_bytes": (u64, [u64]),
         "kc_pack_2bit": (i32, [vp, vp, u64, vp, vp, vp]),
@@ -232,6 +233,14 @@ class SeqSet:
         _check0(lib().kc_import_seqs_mem_threads(fasta, len(fasta), mode, nthreads, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def from_device(cls, ctx, d_raw, h_raw, nbytes, mode=IMPORT_BLANKLINE):
+        """parse a FASTA file image that already sits in device memory, on the GPU (f2); h_raw = the same
+        bytes on the host (for the id strings) or None"""
+        h = C.c_void_p()
+        ctx._check(lib().kc_import_seqs_device(ctx._h, _ptr(d_raw), h_raw, nbytes, mode, C.byref(h)))
+        return cls(h)
+
     @property
     def num_seqs(self):
         return int(lib().kc_seqset_num_seqs(self._h))
@@ -246,7 +255,8 @@ class SeqSet:
 
     @property
     def data(self):
-        return C.string_at(lib().kc_seqset_data(self._h), self.nbytes)
+        n = self.nbytes
+        return C.string_at(lib().kc_seqset_data(self._h), n) if n else b""
 
     @property
     def offsets(self):

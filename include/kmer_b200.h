@@ -128,6 +128,13 @@ KC_API int kc_import_seqs_mem(const char* fasta, size_t nbytes, int mode, long m
  * themselves for inputs of 32 MiB and more ("next" row f2: ingest at speed).           */
 KC_API int kc_import_seqs_mem_threads(const char* fasta, size_t nbytes, int mode, int nthreads,
                                       kc_seqset** out);
+/* Device-side form (f2): d_raw = the FASTA file image in DEVICE memory, parsed by three kernels (a
+ * seven-state byte transducer whose per-tile maps are composed by a scan); the set's device copies
+ * (kc_seqset_to_device) are in place on return, its host image is fetched on the first
+ * kc_seqset_data().  h_raw = the same bytes on the host, used only to cut the id strings (NULL: the
+ * ids stay empty).  Same result as kc_import_seqs_mem with max_seqs <= 0.                         */
+KC_API int kc_import_seqs_device(kc_ctx* ctx, const char* d_raw, const char* h_raw, uint64_t nbytes,
+                                 int mode, kc_seqset** out);
 KC_API void kc_seqset_free(kc_seqset* s);
 KC_API uint32_t kc_seqset_num_seqs(const kc_seqset* s);
 KC_API uint32_t kc_seqset_num_ids(const kc_seqset* s);

@@ -57,6 +57,21 @@ def lib():
         L.kc_gen_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.kc_count_dense_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_count_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.kc_import_seqs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        L.kc_import_seqs_mem.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_long, C.POINTER(C.c_void_p)]
+        L.kc_seqset_free.argtypes = [C.c_void_p]
+        L.kc_seqset_num_seqs.restype = C.c_uint32
+        L.kc_seqset_num_seqs.argtypes = [C.c_void_p]
+        L.kc_seqset_num_ids.restype = C.c_uint32
+        L.kc_seqset_num_ids.argtypes = [C.c_void_p]
+        L.kc_seqset_nbytes.restype = C.c_uint64
+        L.kc_seqset_nbytes.argtypes = [C.c_void_p]
+        L.kc_seqset_data.restype = C.c_void_p
+        L.kc_seqset_data.argtypes = [C.c_void_p]
+        L.kc_seqset_offsets.restype = C.c_void_p
+        L.kc_seqset_offsets.argtypes = [C.c_void_p]
+        L.kc_seqset_id.restype = C.c_char_p
+        L.kc_seqset_id.argtypes = [C.c_void_p, C.c_uint32]
         L.kc_packed_bytes.restype = C.c_uint64
         L.kc_packed_bytes.argtypes = [C.c_uint64]
         L.kc_badmask_bytes.restype = C.c_uint64
@@ -380,7 +395,51 @@ def case_packed(args):
     print("ok packed", *args)
 
 
-CASES = {"packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+def _seqset_tuple(L, h):
+    n = int(L.kc_seqset_num_seqs(h))
+    nb = int(L.kc_seqset_nbytes(h))
+    dp = L.kc_seqset_data(h)
+    data = C.string_at(dp, nb) if nb else b""
+    offs = np.ctypeslib.as_array(C.cast(L.kc_seqset_offsets(h), C.POINTER(C.c_int64)), shape=(n + 1,)).tolist()
+    ids = [L.kc_seqset_id(h, i) for i in range(int(L.kc_seqset_num_ids(h)))]
+    return n, data, offs, ids
+
+
+def case_ingest(args):
+    """f2, device side: kc_import_seqs_device (seven-state byte transducer, per-tile maps composed by a
+    scan) against the host loader kc_import_seqs_mem, on the reference-generated loader fixtures and on
+    random files — with tiles of 16 bytes, so that lines, headers and records span many tiles"""
+    import json
+    seed, ntrials = int(args[0]), int(args[1])
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_golden.json")))
+    texts = [c["fasta"].encode("latin-1") for c in golden["loader"]]
+    rng = np.random.default_rng(seed)
+    pieces = [b">h\n", b"ACGT\n", b"NNAC\n", b"\n", b"\r\n", b"acgt\n", b">x y\n", b"GG|TT\n", b"T", b"\n\n", b"CCC\r\n",
+              b"ACGTACGTACGTACGTACGTACGTACGTACGTACGT\n", b">\n", b"|\n", b"\r", b">"]
+    for _ in range(ntrials):
+        texts.append(b"".join(pieces[i] for i in rng.integers(0, len(pieces), size=int(rng.integers(0, 80)))))
+    # more tiles than the scan kernel has threads: every thread composes a RUN of tile maps
+    texts.append(b"".join(pieces[i] for i in rng.integers(0, len(pieces), size=9000)))
+    ctx = EmuContext()
+    L = ctx.L
+    for text in texts:
+        for mode in (0, 1):
+            want = C.c_void_p()
+            ctx.check(L.kc_import_seqs_mem(text, len(text), mode, 0, C.byref(want)))
+            base, p = ctx.upload(np.frombuffer(text, dtype=np.uint8)) if text else (None, None)
+            got = C.c_void_p()
+            ctx.check(L.kc_import_seqs_device(ctx.h, p, text, len(text), mode, C.byref(got)))
+            a, b = _seqset_tuple(L, want), _seqset_tuple(L, got)
+            assert a == b, (text, mode, a, b)
+            L.kc_seqset_free(want)
+            L.kc_seqset_free(got)
+            if base is not None:
+                ctx.free(base)
+    ctx.close()
+    print("ok ingest", *args, "files", len(texts))
+
+
+CASES = {"ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

@@ -220,3 +220,11 @@ def test_packed_store_on_emulator():
     run_case("packed", 3, 1000, 3, KC_PACKED_CHUNK=64)
     for n in (31, 3, 16, 17):
         run_case("packed", 2, n, 6)
+
+
+def test_gpu_fasta_parser_on_emulator():
+    """f2, device side: kc_import_seqs_device == the host loader on the reference-generated fixtures and
+    random files, with 16- and 5-byte tiles (lines, ids and records span tiles; > 1024 tiles in one file)"""
+    run_case("ingest", 1, 60, KC_INGEST_TILE=16)
+    run_case("ingest", 2, 40, KC_INGEST_TILE=5)
+    run_case("ingest", 3, 20)

@@ -204,6 +204,26 @@ def test_packed_store(ctx, kmerlib, oracle):
     assert bool((a == b).all())
 
 
+def test_gpu_fasta_parser(ctx, kmerlib, oracle, golden):
+    """f2, device side: raw FASTA bytes in HBM -> kc_import_seqs_device == the host loader; then the
+    per-sequence counts of the device-resident set == the oracle's"""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(30):
+        seq = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, int(rng.integers(1, 200_000)))].tobytes()
+        recs.append(b">chr%d test\n" % i + b"\n".join(seq[j:j + 70] for j in range(0, len(seq), 70)) + b"\n\n")
+    texts = [b"".join(recs)] + [c["fasta"].encode("latin-1") for c in golden["loader"]]
+    for text in texts:
+        for mode in (0, 1):
+            want = kmerlib.SeqSet.from_memory(text, mode, 0)
+            d_raw = to_dev(np.frombuffer(text, dtype=np.uint8)) if text else None
+            got = kmerlib.SeqSet.from_device(ctx, d_raw, text, len(text), mode)
+            assert got.num_seqs == want.num_seqs and got.ids == want.ids
+            assert got.offsets.tolist() == want.offsets.tolist() and got.data == want.data
+            got.close()
+            want.close()
+
+
 def test_nccl_range_sharded_radix():
     """multi-GPU (>= 2 GPUs visible): scatter, all-to-all of the slabs, count per rank, vs the oracle"""
     import torch
