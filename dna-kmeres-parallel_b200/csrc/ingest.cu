@@ -77,6 +77,25 @@ __host__ __device__ inline int fsm_step(int st, unsigned char c, int mode, Effec
     }
 }
 
+// bytes [b, e) of raw, in order; 128-bit loads wherever a 16-byte aligned block lies inside the range
+// (a thread walks its own tile: byte loads would cost one LSU wavefront per byte and lane)
+template <typename F>
+__device__ __forceinline__ void for_each_byte(const unsigned char* __restrict__ raw, uint64_t b, uint64_t e, F&& f) {
+    uint64_t p = b;
+    while (p < e) {
+        if ((((uintptr_t)(raw + p)) & 15) == 0 && p + 16 <= e) {
+            const uint4 v = *reinterpret_cast<const uint4*>(raw + p);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 16; i++) f((unsigned char)(w[i >> 2] >> (8 * (i & 3))), p + i);
+            p += 16;
+        } else {
+            f(raw[p], p);
+            p++;
+        }
+    }
+}
+
 struct TileMap {  // start state -> effect of the whole tile
     uint32_t bytes[NSTATE], recs[NSTATE], ids[NSTATE];
     uint8_t end[8];
@@ -93,33 +112,32 @@ ingest_map_kernel(const unsigned char* __restrict__ raw, uint64_t n, uint32_t ti
             st7[s] = s;
             by7[s] = rc7[s] = id7[s] = 0;
         }
-        uint64_t p = b;
         bool merged = false;  // past the first newline: every machine is in state 0, 1 or 2
-        for (; p < e && !merged; p++) {
-            const unsigned char c = raw[p];
-#pragma unroll
-            for (int s = 0; s < NSTATE; s++) {
-                Effect ef;
-                st7[s] = fsm_step(st7[s], c, mode, ef);
-                by7[s] += ef.copy + ef.close;
-                rc7[s] += ef.start;
-                id7[s] += ef.id;
-            }
-            merged = (c == '\n');
-        }
         int stc[3] = {0, 1, 2};
         uint32_t byc[3] = {0, 0, 0}, rcc[3] = {0, 0, 0}, idc[3] = {0, 0, 0};
-        for (; p < e; p++) {
-            const unsigned char c = raw[p];
+        auto feed = [&](unsigned char c, uint64_t) {
+            if (!merged) {
 #pragma unroll
-            for (int s = 0; s < 3; s++) {
-                Effect ef;
-                stc[s] = fsm_step(stc[s], c, mode, ef);
-                byc[s] += ef.copy + ef.close;
-                rcc[s] += ef.start;
-                idc[s] += ef.id;
+                for (int s = 0; s < NSTATE; s++) {
+                    Effect ef;
+                    st7[s] = fsm_step(st7[s], c, mode, ef);
+                    by7[s] += ef.copy + ef.close;
+                    rc7[s] += ef.start;
+                    id7[s] += ef.id;
+                }
+                merged = (c == '\n');
+            } else {
+#pragma unroll
+                for (int s = 0; s < 3; s++) {
+                    Effect ef;
+                    stc[s] = fsm_step(stc[s], c, mode, ef);
+                    byc[s] += ef.copy + ef.close;
+                    rcc[s] += ef.start;
+                    idc[s] += ef.id;
+                }
             }
-        }
+        };
+        for_each_byte(raw, b, e, feed);
         TileMap m;
 #pragma unroll
         for (int s = 0; s < NSTATE; s++) {
@@ -231,15 +249,31 @@ ingest_emit_kernel(const unsigned char* __restrict__ raw, uint64_t n, uint32_t t
         const TileStart ts = starts[t];
         int st = (int)ts.state;
         uint64_t o = ts.out_pos, rc = ts.rec, id = ts.id;
-        for (uint64_t p = b; p < e; p++) {
-            const unsigned char c = raw[p];
+        // output bytes are gathered into aligned 32-bit words (a byte store costs a wavefront per lane)
+        uint32_t word = 0, fill = 0;  // `fill` bytes of the word at o - fill are pending; o - fill is 4-byte aligned
+        auto put = [&](unsigned char ch) {
+            if (fill == 0 && (((uintptr_t)(data + o)) & 3)) {
+                data[o++] = (char)ch;  // head bytes up to the first aligned word
+                return;
+            }
+            word |= (uint32_t)ch << (8 * fill);
+            fill++;
+            o++;
+            if (fill == 4) {
+                *reinterpret_cast<uint32_t*>(data + o - 4) = word;
+                word = 0;
+                fill = 0;
+            }
+        };
+        for_each_byte(raw, b, e, [&](unsigned char c, uint64_t p) {
             Effect ef;
             st = fsm_step(st, c, mode, ef);
-            if (ef.close) data[o++] = '\0';  // the record's own '|' separator (main.cu:505,517), already NUL
+            if (ef.close) put(0);  // the record's own '|' separator (main.cu:505,517), already NUL
             if (ef.start) offsets[rc++] = (int64_t)o;
-            if (ef.copy) data[o++] = (c == '|') ? '\0' : (char)c;  // main.cu:538-541
+            if (ef.copy) put(c == '|' ? (unsigned char)0 : c);  // main.cu:538-541
             if (ef.id) id_pos[id++] = p;
-        }
+        });
+        for (uint32_t q = 0; q < fill; q++) data[o - fill + q] = (char)(word >> (8 * q));  // tail bytes
         if (e == n && (st == 2 || st == 5)) data[o] = '\0';  // the last record is closed by the end of the file
     }
 }
