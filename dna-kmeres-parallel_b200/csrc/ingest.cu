@@ -20,6 +20,11 @@
 //        positions of the id lines (the id strings are cut from the host's file image).
 // Output identical to kc_import_seqs_mem with max_seqs <= 0 (tests/test_emu_kernels.py compares them
 // on the reference fixtures and random files with tiles of 16 bytes).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "common.cuh"
 
 namespace {
@@ -375,4 +380,46 @@ extern "C" int kc_import_seqs_device(kc_ctx* ctx, const char* d_raw, const char*
     }
     *out = s;
     return KC_OK;
+}
+
+// File form: the file is mapped, copied to the device in 64 MiB pieces and parsed there; the id
+// strings come from the mapping.  Error text for a missing file as in the reference (main.cu:477-480).
+extern "C" int kc_import_seqs_gpu(kc_ctx* ctx, const char* path, int mode, kc_seqset** out) {
+    if (!ctx || !out || !path) return KC_ERR_INVALID;
+    *out = nullptr;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return kc_set_error(ctx, KC_ERR_IO, "Error opening: %s . Check your file or path.", path);
+    struct stat stt;
+    if (fstat(fd, &stt) != 0 || !S_ISREG(stt.st_mode)) {
+        close(fd);
+        return kc_set_error(ctx, KC_ERR_IO, "kc_import_seqs_gpu: %s is not a regular file", path);
+    }
+    const uint64_t n = (uint64_t)stt.st_size;
+    if (n == 0) {
+        close(fd);
+        return kc_import_seqs_device(ctx, nullptr, nullptr, 0, mode, out);
+    }
+    void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return kc_set_error(ctx, KC_ERR_IO, "kc_import_seqs_gpu: cannot map %s", path);
+    madvise(m, n, MADV_SEQUENTIAL);
+    DeviceGuard dg(ctx->device);
+    Dev raw;
+    int rc = KC_OK;
+    if (raw.alloc(n)) {
+        cudaGetLastError();
+        rc = kc_set_error(ctx, KC_ERR_NOMEM, "kc_import_seqs_gpu: no device memory for a %llu-byte file", (unsigned long long)n);
+    }
+    const uint64_t piece = 64ull << 20;
+    for (uint64_t b = 0; b < n && rc == KC_OK; b += piece) {
+        const uint64_t len = (b + piece < n) ? piece : n - b;
+        if (cudaMemcpyAsync((char*)raw.p + b, (const char*)m + b, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            rc = kc_set_error(ctx, KC_ERR_CUDA, "kc_import_seqs_gpu: copy to the device failed");
+        }
+    }
+    if (rc == KC_OK) rc = kc_import_seqs_device(ctx, (const char*)raw.p, (const char*)m, n, mode, out);
+    cudaStreamSynchronize(ctx->stream);
+    munmap(m, n);
+    return rc;
 }

@@ -92,6 +92,7 @@ def lib():
         "kc_count_dense_host": (i32, [vp, vp, u64, i32, vp]),
         "kc_count_sparse": (i32, [vp, vp, u64, i32, i32, u64, C.POINTER(vp)]),
         "kc_import_seqs_device": (i32, [vp, vp, C.c_char_p, u64, i32, C.POINTER(vp)]),
+        "kc_import_seqs_gpu": (i32, [vp, C.c_char_p, i32, C.POINTER(vp)]),
         "kc_packed_bytes": (u64, [u64]),
         "kc_badmask_bytes": (u64, [u64]),
         "kc_pack_2bit": (i32, [vp, vp, u64, vp, vp, vp]),
@@ -239,6 +240,13 @@ class SeqSet:
         bytes on the host (for the id strings) or None"""
         h = C.c_void_p()
         ctx._check(lib().kc_import_seqs_device(ctx._h, _ptr(d_raw), h_raw, nbytes, mode, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_file_gpu(cls, ctx, path, mode=IMPORT_BLANKLINE):
+        """the file goes to the device as it is and is parsed there (f2)"""
+        h = C.c_void_p()
+        ctx._check(lib().kc_import_seqs_gpu(ctx._h, path.encode(), mode, C.byref(h)))
         return cls(h)
 
     @property

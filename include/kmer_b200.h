@@ -135,6 +135,8 @@ KC_API int kc_import_seqs_mem_threads(const char* fasta, size_t nbytes, int mode
  * ids stay empty).  Same result as kc_import_seqs_mem with max_seqs <= 0.                         */
 KC_API int kc_import_seqs_device(kc_ctx* ctx, const char* d_raw, const char* h_raw, uint64_t nbytes,
                                  int mode, kc_seqset** out);
+/* file form: map the file, copy it to the device as it is, parse it there */
+KC_API int kc_import_seqs_gpu(kc_ctx* ctx, const char* path, int mode, kc_seqset** out);
 KC_API void kc_seqset_free(kc_seqset* s);
 KC_API uint32_t kc_seqset_num_seqs(const kc_seqset* s);
 KC_API uint32_t kc_seqset_num_ids(const kc_seqset* s);

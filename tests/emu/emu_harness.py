@@ -58,6 +58,7 @@ def lib():
         L.kc_count_dense_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_count_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_import_seqs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        L.kc_import_seqs_gpu.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.kc_import_seqs_mem.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_long, C.POINTER(C.c_void_p)]
         L.kc_seqset_free.argtypes = [C.c_void_p]
         L.kc_seqset_num_seqs.restype = C.c_uint32
@@ -435,6 +436,21 @@ def case_ingest(args):
             L.kc_seqset_free(got)
             if base is not None:
                 ctx.free(base)
+    # the file form, and its error text for a missing file
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".fasta") as f:
+        f.write(texts[-1])
+        f.flush()
+        for mode in (0, 1):
+            want, got = C.c_void_p(), C.c_void_p()
+            ctx.check(L.kc_import_seqs_mem(texts[-1], len(texts[-1]), mode, 0, C.byref(want)))
+            ctx.check(L.kc_import_seqs_gpu(ctx.h, f.name.encode(), mode, C.byref(got)))
+            assert _seqset_tuple(L, want) == _seqset_tuple(L, got)
+            L.kc_seqset_free(want)
+            L.kc_seqset_free(got)
+    got = C.c_void_p()
+    assert L.kc_import_seqs_gpu(ctx.h, b"/nonexistent/all_seqs.fasta", 0, C.byref(got)) == -3
+    assert b"Error opening" in L.kc_last_error(ctx.h)
     ctx.close()
     print("ok ingest", *args, "files", len(texts))
 
