@@ -4,22 +4,25 @@
 // "Next" row f3 of SURVEY.md §8; the GPU work goes through the C ABI.
 //
 //   examen_b200 <input.fasta> [-k K] [--nonl] [--max-seqs N] [--out parallel_results.csv]
-//               [--sums sums.txt]
+//               [--sums sums.txt] [--gpu-parse]
+// --gpu-parse: the FASTA file is copied to the device as it is and parsed there (no record limit)
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <memory>
 
 #include "kmer_b200.hpp"
 
 int main(int argc, char** argv) {
     std::string file, out = "parallel_results.csv", sums_path;
     int k = 3;
-    bool nonl = false;
+    bool nonl = false, gpu_parse = false;
     long max_seqs = 100;  // MAX_SEQS, main.cu:30
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-k") && i + 1 < argc) k = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--nonl")) nonl = true;
+        else if (!strcmp(argv[i], "--gpu-parse")) gpu_parse = true;
         else if (!strcmp(argv[i], "--max-seqs") && i + 1 < argc) max_seqs = atol(argv[++i]);
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
         else if (!strcmp(argv[i], "--sums") && i + 1 < argc) sums_path = argv[++i];
@@ -27,16 +30,20 @@ int main(int argc, char** argv) {
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (file.empty()) {
-        fprintf(stderr, "usage: %s <input.fasta> [-k K] [--nonl] [--max-seqs N] [--out csv] [--sums txt]\n", argv[0]);
+        fprintf(stderr, "usage: %s <input.fasta> [-k K] [--nonl] [--max-seqs N] [--out csv] [--sums txt] [--gpu-parse]\n", argv[0]);
         return 2;
     }
     try {
         std::cout << "K = " << k << std::endl;  // main.cu:145
-        kmerb200::Sequences seqs = nonl ? kmerb200::importSeqsNoNL(file, max_seqs) : kmerb200::importSeqs(file, max_seqs);
+        std::unique_ptr<kmerb200::Engine> engp;
+        if (gpu_parse) engp.reset(new kmerb200::Engine(0));  // otherwise the file is read first, as in the reference
+        kmerb200::Sequences seqs = gpu_parse ? kmerb200::importSeqsGpu(*engp, file, nonl)
+                                             : nonl ? kmerb200::importSeqsNoNL(file, max_seqs) : kmerb200::importSeqs(file, max_seqs);
         std::cout << "Size all seqs:" << seqs.size_all_seqs << std::endl;          // main.cu:166
         std::cout << seqs.numberOfSequenses << " sequences read ." << std::endl;  // main.cu:167
         printf("\n\aParallel:\n");                                                 // main.cu:170
-        kmerb200::Engine eng(0);
+        if (!engp) engp.reset(new kmerb200::Engine(0));
+        kmerb200::Engine& eng = *engp;
         auto t0 = std::chrono::steady_clock::now();
         int32_t* d_sums = nullptr;
         std::vector<int32_t> sums = eng.sumKmereCoincidences(seqs, k, &d_sums);

@@ -78,6 +78,11 @@ inline Sequences import_impl(const std::string& file, int mode, long max_seqs) {
 inline Sequences importSeqs(const std::string& inputFile, long max_seqs = 100) { return import_impl(inputFile, KC_IMPORT_BLANKLINE, max_seqs); }
 inline Sequences importSeqsNoNL(const std::string& inputFile, long max_seqs = 100) { return import_impl(inputFile, KC_IMPORT_NONL, max_seqs); }
 
+class Engine;
+// f2, device side: the file goes to the GPU as it is and is parsed there (kc_import_seqs_gpu); the
+// returned Sequences has no host image of `data` unless somebody asks kc_seqset_data for it
+inline Sequences importSeqsGpu(Engine& eng, const std::string& inputFile, bool nonl = false);
+
 class Engine {
   public:
     explicit Engine(int device = 0) { check(kc_ctx_create(device, &ctx_)); }
@@ -151,5 +156,16 @@ class Engine {
   private:
     kc_ctx* ctx_ = nullptr;
 };
+
+inline Sequences importSeqsGpu(Engine& eng, const std::string& inputFile, bool nonl) {
+    Sequences s;
+    check(kc_import_seqs_gpu(eng.ctx(), inputFile.c_str(), nonl ? KC_IMPORT_NONL : KC_IMPORT_BLANKLINE, &s.handle), eng.ctx());
+    s.numberOfSequenses = (int)kc_seqset_num_seqs(s.handle);
+    s.size_all_seqs = kc_seqset_nbytes(s.handle);
+    s.data = nullptr;  // stays on the device
+    s.indexes = kc_seqset_offsets(s.handle);
+    for (uint32_t i = 0; i < kc_seqset_num_ids(s.handle); i++) s.ids.emplace_back(kc_seqset_id(s.handle, i));
+    return s;
+}
 
 }  // namespace kmerb200

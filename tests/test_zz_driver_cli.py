@@ -41,3 +41,21 @@ def test_driver_matches_reference_distances(golden, oracle, tmp_path):
         offs = np.cumsum([0] + [len(s) + 1 for s in seqs])
         want, _ = oracle.count_per_seq(data, offs, k)
         assert sums.read_bytes() == oracle.dump_counts(want, k, len(seqs))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first B200 run pending (GPU-side FASTA parser, emulator-verified)")
+def test_driver_gpu_parse_matches_host_parse(golden, tmp_path):
+    """--gpu-parse: the same distances and sums as the host-parsed run"""
+    _build()
+    rng = np.random.default_rng(3)
+    seqs = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(30, 4000)))) for _ in range(12)]
+    fasta = tmp_path / "in.fasta"
+    fasta.write_bytes("".join(">s%d\n%s\n\n" % (i, "\n".join(s[j:j + 60] for j in range(0, len(s), 60))) for i, s in enumerate(seqs)).encode())
+    outs = []
+    for flag in ([], ["--gpu-parse"]):
+        out, sums = tmp_path / ("r%d.csv" % len(flag)), tmp_path / ("s%d.txt" % len(flag))
+        r = subprocess.run([EXE, str(fasta), "-k", "4", "--out", str(out), "--sums", str(sums)] + flag, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append((out.read_text(), sums.read_text()))
+    assert outs[0] == outs[1]
