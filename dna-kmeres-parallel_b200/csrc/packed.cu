@@ -8,7 +8,7 @@
 //   badmask : one bit per base, bit i%32 of 32-bit word i/32 (LSB first); set = byte i was not ACGT
 //   => 0.25 + 0.125 bytes per base at rest instead of 1.
 //
-// Counting from the store (kc_count_dense_packed) unpacks 2^27-base chunks into an ASCII scratch and
+// Counting from the store (kc_count_dense_packed) unpacks 2^30-base chunks into an ASCII scratch and
 // runs the ordinary dense path on each (windows that START in the chunk; the chunk carries a (k-1)-base
 // halo), so every verified kernel is reused and the result equals kc_count_dense of the original
 // bytes.  The counting kernels are bound by shared-memory atomics and decode, not by HBM, so a kernel
@@ -146,8 +146,11 @@ int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32_t* d_b
     if (nbases >= (uint64_t)k) {
         const uint64_t nwin = nbases - k + 1;
         static const uint64_t chunk_env = getenv("KC_PACKED_CHUNK") ? strtoull(getenv("KC_PACKED_CHUNK"), nullptr, 0) : 0;  // test aid
-        const uint64_t chunk = chunk_env ? (chunk_env + 31) / 32 * 32 : (1ull << 27);  // window starts per chunk, a multiple of 32
-        int rc = kc_scratch2_reserve(ctx, (size_t)(chunk + KC_MAX_DENSE_K + 64));
+        // window starts per chunk, a multiple of 32.  2^30: the partition path's fixed cost per call (~0.1 ms: 2048
+        // sub-table flushes) is paid once per Gbp, and 1 GiB of scratch is nothing on a 180 GB part
+        const uint64_t chunk = chunk_env ? (chunk_env + 31) / 32 * 32 : (1ull << 30);
+        const uint64_t need = (nwin < chunk ? nwin : chunk) + KC_MAX_DENSE_K + 64;
+        int rc = kc_scratch2_reserve(ctx, (size_t)need);
         if (rc) return rc;
         char* ascii = (char*)ctx->scratch2;
         for (uint64_t w0 = 0; w0 < nwin; w0 += chunk) {

@@ -285,7 +285,7 @@ KC_API int kc_pack_2bit(kc_ctx* ctx, const char* d_data, uint64_t nbytes, void* 
 KC_API int kc_unpack_2bit(kc_ctx* ctx, const void* d_packed, const uint32_t* d_badmask,
                           uint64_t nbases, char* d_data_out, void* stream);
 /* == kc_count_dense of the bytes the store was packed from (synchronous; d_table overwritten):
- * 2^27-base chunks are unpacked into an ASCII scratch and counted by the ordinary dense path */
+ * 2^30-base chunks are unpacked into an ASCII scratch and counted by the ordinary dense path */
 KC_API int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32_t* d_badmask,
                                  uint64_t nbases, int k, uint32_t* d_table);
 

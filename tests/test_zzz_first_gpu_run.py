@@ -173,7 +173,7 @@ def test_partition_paired_count(ctx, kmerlib, oracle):
 
 def test_packed_store(ctx, kmerlib, oracle):
     """f4: pack -> layout of main.cu:78-86 + validity bitmap; unpack inverse (invalid -> 'N'); counting
-    from the store equals counting the bytes (k = 5, 8, 12; the 200 Mbp case crosses a 2^27 chunk edge)"""
+    from the store equals counting the bytes (k = 5, 8, 12; the last case is 1.2 Gbp: it crosses the 2^30 chunk edge)"""
     import torch
     n = 5_000_003
     data = oracle.gen_genome(0xB2000003, n, 5, 500, 12, 0, n).copy()
@@ -194,7 +194,7 @@ def test_packed_store(ctx, kmerlib, oracle):
         t = ctx.count_dense_packed(packed, mask, n, k).cpu().numpy().view(np.uint32)
         w, _ = oracle.count_dense(data, k)
         assert (t == w).all(), k
-    L = 200_000_000
+    L = 1_200_000_000
     big = ctx.gen_genome(0xB2000003, L, 60, 600, 12, 0, L)
     p2, m2 = ctx.pack_2bit(big, L)
     a = ctx.count_dense_packed(p2, m2, L, 12)
