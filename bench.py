@@ -428,7 +428,10 @@ def main():
     p2 = float(np.mean([p[1] for p in passes]))
     bases_launch = e - b + k - 1
     if p2 > 0 and k == 8:  # shared-memory 16-bit bins + reduce of the per-CTA partials
-        kernels = {"dense_smem16_kernel": (p1, bases_launch), "smem16_reduce_kernel": (p2, 4 * nk)}
+        if args.algo == 3:  # checksum variant; the second interval covers its reduce + repair kernels
+            kernels = {"dense_smem16c_kernel": (p1, bases_launch), "smem16c_reduce_kernel+smem16_repair_kernel": (p2, 4 * nk)}
+        else:
+            kernels = {"dense_smem16_kernel": (p1, bases_launch), "smem16_reduce_kernel": (p2, 4 * nk)}
     elif p2 > 0:  # two-pass partition path (the count kernel has measured-later variants: --algo 5/6, KC_PART_PAIR)
         pm = {5: 1, 6: 2}.get(args.algo, int(os.environ.get("KC_PART_PAIR", "0") or 0)) if k == 12 else 0
         cname = {0: "part_count_kernel", 1: "part_count_pair12_kernel", 2: "part_count_trio12_kernel"}.get(pm, "part_count_kernel")
