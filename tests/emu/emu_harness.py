@@ -58,6 +58,7 @@ def lib():
         L.kc_count_dense_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_count_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_import_seqs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        L.kc_seqset_to_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.kc_import_seqs_gpu.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.kc_import_seqs_mem.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_long, C.POINTER(C.c_void_p)]
         L.kc_seqset_free.argtypes = [C.c_void_p]
@@ -432,6 +433,15 @@ def case_ingest(args):
             ctx.check(L.kc_import_seqs_device(ctx.h, p, text, len(text), mode, C.byref(got)))
             a, b = _seqset_tuple(L, want), _seqset_tuple(L, got)
             assert a == b, (text, mode, a, b)
+            if a[0] and len(text) > 5000:  # the device-resident copy feeds the per-sequence count directly
+                dd, do = C.c_void_p(), C.c_void_p()
+                ctx.check(L.kc_seqset_to_device(ctx.h, got, C.byref(dd), C.byref(do)))
+                d_sums = ctx.alloc(4 * 64 * a[0])
+                ctx.check(L.kc_count_per_seq(ctx.h, dd, do, a[0], 3, d_sums))
+                sums = ctx.download(d_sums, 4 * 64 * a[0], np.int32).reshape(64, a[0])
+                ws, _ = _oracle().count_per_seq(np.frombuffer(a[1], dtype=np.uint8), np.array(a[2], dtype=np.int64), 3)
+                assert (sums == ws).all(), "per-sequence counts of the GPU-parsed set differ"
+                ctx.free(d_sums)
             L.kc_seqset_free(want)
             L.kc_seqset_free(got)
             if base is not None:
