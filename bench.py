@@ -280,6 +280,54 @@ def leave(world):
     t.start()
 
 
+# Kernel variants that were written after round 1's GPU budget was spent.  They are
+# never the library's KC_DENSE_AUTO choice; the bench tries them the way an autotuner would: each in
+# its OWN process (a crash or a hang of a variant cannot touch this one), on the full workload, and a
+# variant is used for the timed run only if its table is bit-identical to the shipped path's (a
+# position-weighted fingerprint of all 4^k bins) and it is at least 3 % faster.  Every probe's time and
+# verdict goes into the result line (config.probe).
+PROBE_CANDIDATES = {12: [4, 5, 6, 7], 8: [3]}
+
+
+def probe_variants(args, k, local):
+    import subprocess
+    cands = PROBE_CANDIDATES.get(k, [])
+    if not cands:
+        return 0, None
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local), LOCAL_WORLD_SIZE="1")
+    for v in ("KC_PART_ABLATE", "KC_PART_PAIR"):
+        env.pop(v, None)
+    report = {}
+
+    def run(algo):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--algo", str(algo), "--steps", "5",
+               "--warmup", "3", "--no-e2e", "--no-cpu", "--probe"]
+        if args.length:
+            cmd += ["--length", str(args.length)]
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240, stdin=subprocess.DEVNULL)
+            if r.returncode != 0:
+                return {"ok": False, "why": "exit code %d" % r.returncode}
+            d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+            return {"ok": True, "ms": d["ms_per_step"], "fp": d["config"]["table_fingerprint"], "kernel_ms": d["roofline"]["kernel_ms"]}
+        except Exception as ex:  # timeout, no JSON, ...
+            return {"ok": False, "why": str(ex)[:120]}
+
+    base = run(0)
+    report["0"] = base
+    if not base.get("ok"):
+        return 0, report
+    best, best_ms = 0, base["ms"]
+    for a in cands:
+        res = run(a)
+        if res.get("ok"):
+            res["same_table"] = (res["fp"] == base["fp"])
+            if res["same_table"] and res["ms"] < 0.97 * base["ms"] and res["ms"] < best_ms:
+                best, best_ms = a, res["ms"]
+        report[str(a)] = res
+    return best, report
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,6 +348,8 @@ def main():
                     help="N>1: count the shard in S slices and overlap each slice's NCCL reduce with the next count "
                          "(measured slower than S=1 at N=2: 2.24 / 2.57 / 3.35 ms for S=1/2/4)")
     ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of a replayed CUDA graph")
+    ap.add_argument("--probe", action="store_true", help="internal: this run is a variant probe of a parent bench.py")
+    ap.add_argument("--no-probe", action="store_true", help="do not try the not-yet-default kernel variants (see probe_variants)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -321,10 +371,23 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    probe_report, base_fp = None, None
+    if rank == 0 and args.algo == 0 and not args.probe and not args.no_probe and not os.environ.get("KC_BENCH_NO_PROBE"):
+        try:
+            chosen, probe_report = probe_variants(args, WORKLOADS[args.workload]["k"], local)
+            if probe_report and probe_report.get("0", {}).get("ok"):
+                base_fp = probe_report["0"]["fp"]
+            args.algo = chosen
+        except Exception as ex:  # the probes are an extra: never let them cost the measurement
+            sys.stderr.write("bench: variant probes failed (%s); timing the shipped path\n" % ex)
+            args.algo = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        a = torch.tensor([args.algo], dtype=torch.int32, device=dev)
+        dist.broadcast(a, src=0)  # rank 0 probed; every rank runs the same kernels
+        args.algo = int(a.item())
     w = dict(WORKLOADS[args.workload])
     if args.length:
         w["L"] = args.length
@@ -364,53 +427,76 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    kmerb200.lib().kc_ctx_set_timing(ctx._h, 0)
-    for _ in range(args.warmup):
+    def fingerprint(t):  # position-weighted sum of all bins (int64, wraps): equal tables <=> equal with probability ~1
+        wgt = (torch.arange(t.numel(), dtype=torch.int64, device=t.device) % 65521) + 1
+        return int((t.to(torch.int64) * wgt).sum().item())
+
+    def timed():
+        kmerb200.lib().kc_ctx_set_timing(ctx._h, 0)
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        l0 = ctx.launch_count
         step()
-    barrier()
-    l0 = ctx.launch_count
-    step()
-    launches_per_step = ctx.launch_count - l0 + S  # + one zero-fill kernel per slice table
-    barrier()
-    # One step = zero-fill + ~8 launches (+ the NCCL reduce): captured once in a CUDA
-    # graph and replayed, so the timed region is not paced by Python/ctypes launches.
-    graph = None
-    # N > 1 keeps plain launches: a captured NCCL reduce replays fine (N=8: 1.02 ms/step) but the
-    # process then hung in teardown (graph + process group), which no timing gain is worth.
-    if not args.no_graph and world == 1:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            graph.replay()
-            barrier()
-        except Exception as ex:  # fall back to plain launches
-            sys.stderr.write("bench: CUDA graph capture failed (%s); timing plain launches\n" % ex)
-            graph = None
-            torch.cuda.synchronize()
-    run_step = graph.replay if graph is not None else step
-    sampler = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
-    ev0.record()
-    for _ in range(args.steps):
-        run_step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = launches_per_step * args.steps
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        launches_per_step = ctx.launch_count - l0 + S  # + one zero-fill kernel per slice table
+        barrier()
+        # One step = zero-fill + ~8 launches (+ the NCCL reduce): captured once in a CUDA
+        # graph and replayed, so the timed region is not paced by Python/ctypes launches.
+        graph = None
+        # N > 1 keeps plain launches: a captured NCCL reduce replays fine (N=8: 1.02 ms/step) but the
+        # process then hung in teardown (graph + process group), which no timing gain is worth.
+        if not args.no_graph and world == 1:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step()
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step()
+                graph.replay()
+                barrier()
+            except Exception as ex:  # fall back to plain launches
+                sys.stderr.write("bench: CUDA graph capture failed (%s); timing plain launches\n" % ex)
+                graph = None
+                torch.cuda.synchronize()
+        run_step = graph.replay if graph is not None else step
+        sampler = ClockSampler(local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        ev0.record()
+        for _ in range(args.steps):
+            run_step()
+        ev1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = launches_per_step * args.steps
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
+        value = L / (ms_step * 1e-3)
+        checksum = int(table.to(torch.int64).sum().item()) if rank == 0 else 0
+        fp = fingerprint(table) if rank == 0 else 0
+        return dict(ms_step=ms_step, value=value, launches=launches, clocks=clocks, checksum=checksum, graph=graph, fp=fp)
+
+    res = timed()
+    # a probed variant must reproduce the shipped path's table here as well (same full-sequence table at any
+    # N); otherwise the measurement is repeated with the shipped kernels
+    bad = torch.tensor([1 if (rank == 0 and args.algo != 0 and base_fp is not None and res["fp"] != base_fp) else 0],
+                       dtype=torch.int32, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = L / (ms_step * 1e-3)
-    checksum = int(table.to(torch.int64).sum().item()) if rank == 0 else 0
+        dist.broadcast(bad, src=0)
+    if int(bad.item()):
+        sys.stderr.write("bench: variant %d did not reproduce the shipped table in the timed run; timing the shipped path\n" % args.algo)
+        if probe_report is not None:
+            probe_report["rejected_in_timed_run"] = args.algo
+        args.algo = 0
+        res = timed()
+    ms_step, value, launches, clocks, checksum, graph, table_fp = (res["ms_step"], res["value"], res["launches"], res["clocks"],
+                                                                   res["checksum"], res["graph"], res["fp"])
 
     # ---- per-kernel times for the roofline (events on the launching stream) ----
     kmerb200.lib().kc_ctx_set_timing(ctx._h, 1)
@@ -567,7 +653,8 @@ def main():
                        "sharding": ("window ranges + %d-byte halo; ncclReduce of uint32[4^k] to rank 0%s"
                                     % (k - 1, "" if S == 1 else " in %d slices overlapped with counting" % S))
                        if world > 1 else "single GPU",
-                       "table_checksum": checksum},
+                       "table_checksum": checksum, "table_fingerprint": table_fp,
+                       "probe": probe_report},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "reference_config1": ref1,
         }
