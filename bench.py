@@ -287,6 +287,7 @@ def leave(world):
 # position-weighted fingerprint of all 4^k bins) and it is at least 3 % faster.  Every probe's time and
 # verdict goes into the result line (config.probe).
 PROBE_CANDIDATES = {12: [4, 5, 6, 7], 8: [3]}
+PROBE_SCRIPT = os.path.abspath(__file__)  # tests put a stand-in here
 
 
 def probe_variants(args, k, local):
@@ -299,33 +300,84 @@ def probe_variants(args, k, local):
         env.pop(v, None)
     report = {}
 
-    def run(algo):
-        cmd = [sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--algo", str(algo), "--steps", "5",
+    t_start = time.monotonic()
+    budget_s = float(os.environ.get("KC_BENCH_PROBE_BUDGET_S", "300"))  # all probes together
+
+    def run(algo, limit):
+        cmd = [sys.executable, PROBE_SCRIPT, "--workload", args.workload, "--algo", str(algo), "--steps", "5",
                "--warmup", "3", "--no-e2e", "--no-cpu", "--probe"]
         if args.length:
             cmd += ["--length", str(args.length)]
+        t0 = time.monotonic()
         try:
-            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240, stdin=subprocess.DEVNULL)
-            if r.returncode != 0:
-                return {"ok": False, "why": "exit code %d" % r.returncode}
-            d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
-            return {"ok": True, "ms": d["ms_per_step"], "fp": d["config"]["table_fingerprint"], "kernel_ms": d["roofline"]["kernel_ms"]}
-        except Exception as ex:  # timeout, no JSON, ...
-            return {"ok": False, "why": str(ex)[:120]}
+            # own session: a probe that has to be killed takes its children with it
+            p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                 stdin=subprocess.DEVNULL, start_new_session=True)
+            try:
+                out, _ = p.communicate(timeout=limit)
+            except subprocess.TimeoutExpired:
+                try:
+                    os.killpg(p.pid, 9)
+                except ProcessLookupError:
+                    pass
+                try:
+                    p.communicate(timeout=30)
+                except subprocess.TimeoutExpired:
+                    pass
+                return {"ok": False, "why": "no result within %.0f s (killed)" % limit, "wall_s": time.monotonic() - t0}
+            if p.returncode != 0:
+                return {"ok": False, "why": "exit code %d" % p.returncode, "wall_s": time.monotonic() - t0}
+            d = json.loads([ln for ln in out.splitlines() if ln.strip()][-1])
+            return {"ok": True, "ms": d["ms_per_step"], "fp": d["config"]["table_fingerprint"], "kernel_ms": d["roofline"]["kernel_ms"],
+                    "wall_s": time.monotonic() - t0}
+        except Exception as ex:  # no JSON, ...
+            return {"ok": False, "why": str(ex)[:120], "wall_s": time.monotonic() - t0}
 
-    base = run(0)
+    # The driver runs N = 1, 2, 4, 8 back to back on one box: the probes' verdict is kept in /tmp for an hour
+    # (keyed by workload, length and the library's build time) so that only the first run pays for them.
+    cache = None
+    try:
+        import kmerb200
+        key = "%s_%d_%d" % (args.workload, args.length, int(os.path.getmtime(kmerb200.LIB_PATH)))
+        cache = os.path.join("/tmp", "kc_bench_probe_%s.json" % key)
+        if os.path.exists(cache) and time.time() - os.path.getmtime(cache) < 3600:
+            with open(cache) as f:
+                c = json.load(f)
+            c["report"]["cached"] = cache
+            return int(c["best"]), c["report"]
+    except Exception:
+        pass
+
+    def done(best, report):
+        if cache:
+            try:
+                with open(cache + ".tmp", "w") as f:
+                    json.dump({"best": best, "report": report}, f)
+                os.replace(cache + ".tmp", cache)
+            except Exception:
+                pass
+        return best, report
+
+    base = run(0, 240)  # the first process on a fresh box also pages the image in (import torch: up to a minute)
     report["0"] = base
     if not base.get("ok"):
         return 0, report
     best, best_ms = 0, base["ms"]
+    # a variant does the same work as the shipped path: one that needs several times the shipped probe's wall
+    # time is hung or pathologically slow either way
+    limit = min(240.0, float(os.environ.get("KC_BENCH_PROBE_SLACK_S", "30")) + 3.0 * base["wall_s"])
     for a in cands:
-        res = run(a)
+        left = budget_s - (time.monotonic() - t_start)
+        if left < 20:
+            report[str(a)] = {"ok": False, "why": "not run: the probe budget of %.0f s is spent" % budget_s}
+            continue
+        res = run(a, min(limit, left))
         if res.get("ok"):
             res["same_table"] = (res["fp"] == base["fp"])
             if res["same_table"] and res["ms"] < 0.97 * base["ms"] and res["ms"] < best_ms:
                 best, best_ms = a, res["ms"]
         report[str(a)] = res
-    return best, report
+    return done(best, report)
 
 
 def main():

@@ -47,3 +47,44 @@ def test_reference_arm_time_box_shrinks_the_sample():
     assert r.returncode == 0, r.stderr[-2000:]
     d = _check_line(r.stdout, 1)
     assert d["config"]["bases_per_step"] < 268435456  # the calibration pass shrank it
+
+
+FAKE_PROBE = r"""
+import json, sys, time
+a = int(sys.argv[sys.argv.index("--algo") + 1])
+ms, fp = {0: (4.0, 111), 4: (3.95, 111), 5: (3.0, 222), 6: (3.2, 111), 7: (2.9, 111)}[a]
+if a == 7:
+    time.sleep(60)   # a variant that hangs
+if a == 4 and "--crash" in sys.argv:
+    sys.exit(3)
+print("noise on stdout")
+print(json.dumps({"ms_per_step": ms, "config": {"table_fingerprint": fp}, "roofline": {"kernel_ms": {"k": ms}}}))
+"""
+
+
+def test_probe_variants_decision(tmp_path, monkeypatch):
+    """the autotuner-style choice of bench.py: a variant is taken only if its table fingerprint equals the shipped
+    path's and it is >= 3 % faster; a hung probe is killed within its limit; the verdict is cached"""
+    import argparse
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    fake = tmp_path / "fake_probe.py"
+    fake.write_text(FAKE_PROBE)
+    monkeypatch.setattr(bench, "PROBE_SCRIPT", str(fake))
+    monkeypatch.setenv("KC_BENCH_PROBE_SLACK_S", "3")
+    args = argparse.Namespace(workload="config3", length=987654321)  # the length keys the cache file: unique to this test
+    import glob
+    for f in glob.glob("/tmp/kc_bench_probe_config3_987654321_*.json"):
+        os.remove(f)
+    t0 = time.monotonic()
+    best, rep = bench.probe_variants(args, 12, 0)
+    assert time.monotonic() - t0 < 30
+    assert best == 6, rep                      # 5 is faster but its table differs; 4 is < 3 % faster; 7 hangs
+    assert rep["0"]["ok"] and rep["5"]["same_table"] is False and rep["4"]["same_table"] is True
+    assert rep["7"]["ok"] is False and "killed" in rep["7"]["why"]
+    best2, rep2 = bench.probe_variants(args, 12, 0)
+    assert best2 == 6 and "cached" in rep2
+    for f in glob.glob("/tmp/kc_bench_probe_config3_987654321_*.json"):
+        os.remove(f)
+    assert bench.probe_variants(args, 5, 0) == (0, None)   # no candidates for this k

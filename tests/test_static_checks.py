@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILES = ["bench.py", "__graft_entry__.py", "dna-kmeres-parallel_b200/kmerb200/__init__.py",
          "dna-kmeres-parallel_b200/kmerb200/distributed.py", "tests/_nccl_worker.py", "tests/_nccl_radix_worker.py",
-         "tests/_gloo_worker.py", "tests/_gloo_radix_worker.py", "tests/test_gpu_parity.py", "tests/test_zzz_first_gpu_run.py",
+         "tests/_gloo_worker.py", "tests/_gloo_radix_worker.py", "tests/test_gpu_parity.py", "tests/test_zzz_first_gpu_run.py", "tests/_first_gpu_run_cases.py",
          "tests/test_multi_gpu.py", "tests/test_zz_driver_cli.py", "tools/nccl_reduce_bench.py", "tools/sanitize_smoke.py"]
 
 
@@ -33,3 +33,15 @@ def test_no_undefined_globals(rel):
 
     walk(top)
     assert not bad, bad
+
+
+def test_first_run_case_list_is_complete():
+    """tests/test_zzz_first_gpu_run.py runs the cases of tests/_first_gpu_run_cases.py by name, one process each"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("zzz_first", os.path.join(ROOT, "tests", "test_zzz_first_gpu_run.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert sorted(m.CASES) == sorted(m.case_names())
+    assert len(set(m.CASES)) == len(m.CASES)
+    # -k matches substrings: no case name may be contained in another
+    assert not [(a, b) for a in m.CASES for b in m.CASES if a != b and a in b]

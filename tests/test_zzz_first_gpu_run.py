@@ -1,238 +1,91 @@
-"""GPU parity tests of paths whose kernels have so far only met the oracle on the CPU
-emulator (tests/test_emu_kernels.py) — written while the round's GPU budget was spent.
-They run LAST (file name) and are marked xfail(strict=False): a pass shows as XPASS, a
-mismatch as XFAIL, and neither hides behind the verified tests above.  Remove the marker
-once a B200 run has been seen green."""
+"""First B200 run of the paths that have so far only met the oracle on the CPU emulator
+(tests/test_emu_kernels.py).  The cases live in tests/_first_gpu_run_cases.py; each one runs
+HERE in its own pytest process with a time limit: a kernel that has never been on a GPU may
+hang or fault, and neither may take the verified tests above (or this pytest process, or the
+CUDA context its session fixture holds) with it.  The file runs LAST (name) and is
+xfail(strict=False): a pass shows as XPASS, a mismatch / crash / timeout as XFAIL.  Remove the
+marker (and move the case into test_gpu_parity.py) once a B200 run has been seen green."""
 import os
+import signal
 import subprocess
 import sys
+import time
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES_FILE = os.path.join(ROOT, "tests", "_first_gpu_run_cases.py")
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first B200 run pending (verified on the CPU emulator only)")]
 
+CASE_TIMEOUT_S = 240     # one case; the slowest (1.2 Gbp packed store, 2^30-base poly-A) take well under a minute on a B200
+FILE_BUDGET_S = 900      # all cases together: a systematic hang must not eat the caller's time limit
+_state = {"t0": None, "gpu_lost": False}
 
-def to_dev(arr):
-    import torch
-    a = np.ascontiguousarray(arr, dtype=np.uint8)
-    buf = torch.zeros(a.size + 64, dtype=torch.uint8, device="cuda:0")
-    if a.size:
-        buf[: a.size] = torch.from_numpy(a.copy())
-    return buf
-
-
-@pytest.mark.parametrize("k", [13, 17, 18, 21, 25, 28, 31])
-def test_sparse_radix_vs_oracle(ctx, kmerlib, oracle, k):
-    """KC_SPARSE_RADIX (1024 x 1024 partitions, the shipped shape) on shallow-coverage reads;
-    NO_FALLBACK: the radix kernels themselves must produce the result."""
-    nreads = 30_000
-    reads = oracle.gen_reads(0xB2000004 + k, 4_000_000, 150, 200, 0, nreads)
-    wk, wc, _ = oracle.count_sparse(reads, k)
-    sp = ctx.count_sparse(to_dev(reads), reads.size, k, kmerlib.SPARSE_RADIX | kmerlib.SPARSE_NO_FALLBACK)
-    keys, counts = sp.to_host()
-    assert len(sp) == len(wk) and (keys == wk).all() and (counts == wc).all()
+CASES = [
+    "test_sparse_radix_vs_oracle",
+    "test_sparse_radix_deep_coverage_and_fallback",
+    "test_sparse_radix_equals_hash_at_scale",
+    "test_k8_checksum_variant",
+    "test_partition_deferred_retry",
+    "test_partition_two_increment_count",
+    "test_partition_wide_records",
+    "test_partition_paired_count",
+    "test_packed_store",
+    "test_gpu_fasta_parser",
+    "test_nccl_range_sharded_radix",
+]
 
 
-def test_sparse_radix_deep_coverage_and_fallback(ctx, kmerlib, oracle):
-    """deep coverage (counts >> 1) and an input that must overflow a leaf (one k-mer only):
-    with fallback allowed both give the oracle's result."""
-    reads = oracle.gen_reads(0xB2000004, 200_000, 150, 200, 0, 40_000)
-    poly = np.full(8_000_000, ord("A"), dtype=np.uint8)  # >= 4 M windows: the radix kernels run, overflow, and the hash path recounts
-    for data, k in ((reads, 21), (reads, 31), (poly, 21)):
-        wk, wc, _ = oracle.count_sparse(data, k)
-        keys, counts = ctx.count_sparse(to_dev(data), data.size, k, kmerlib.SPARSE_RADIX).to_host()
-        assert (keys == wk).all() and (counts == wc).all()
+def _run(cmd, timeout):
+    """run cmd in its own process group; on timeout the whole group is killed (torchrun grandchildren too)"""
+    p = subprocess.Popen(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         stdin=subprocess.DEVNULL, start_new_session=True)
+    try:
+        out, _ = p.communicate(timeout=timeout)
+        return p.returncode, out
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        try:
+            out, _ = p.communicate(timeout=30)
+        except subprocess.TimeoutExpired:
+            out = ""
+        return None, out or ""
 
 
-def test_sparse_radix_equals_hash_at_scale(ctx, kmerlib):
-    """no oracle at this size (20 M windows): the two GPU algorithms must agree exactly"""
-    nreads, k = 150_000, 21
-    reads = ctx.gen_reads(0xB2000004, 50_000_000, 150, 200, 0, nreads)
-    a = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_HASH)
-    b = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_RADIX | kmerlib.SPARSE_NO_FALLBACK)
-    ka, ca = a.to_host()
-    kb, cb = b.to_host()
-    assert len(a) == len(b) and (ka == kb).all() and (ca == cb).all()
-    assert int(ca.astype(np.int64).sum()) == nreads * (150 - k + 1)
+def _gpu_answers():
+    rc, _ = _run([sys.executable, "-c", "import torch; torch.zeros(1, device='cuda:0').item(); torch.cuda.synchronize()"], 120)
+    return rc == 0
 
 
-def _dense(ctx, kmerlib, data, k, algo):
-    import torch
-    table = torch.zeros(kmerlib.num_kmers(k), dtype=torch.int32, device="cuda:0")
-    d = to_dev(data)
-    ctx.count_dense_range(d, data.size, 0, data.size, k, table, algo=algo)
-    torch.cuda.synchronize()
-    return table.cpu().numpy().view(np.uint32)
+def case_names():
+    """the test functions of the cases file, by a text scan (no import: the static check below must hold on CPU)"""
+    names = []
+    with open(CASES_FILE) as f:
+        for ln in f:
+            if ln.startswith("def test_"):
+                names.append(ln[4:ln.index("(")])
+    return names
 
 
-def test_k8_checksum_variant(ctx, kmerlib, oracle):
-    """KC_DENSE_SMEM16C: uniform input (no CTA repaired), one-bin input (every CTA repaired), dirty bytes"""
-    n = 30_000_000
-    genome = oracle.gen_genome(0xB2000002, n, 30, 300, 8, 0, n)
-    poly = np.full(8_000_000, ord("A"), dtype=np.uint8)
-    for data in (genome, poly):
-        want, _ = oracle.count_dense(data, 8)
-        got = _dense(ctx, kmerlib, data, 8, kmerlib.DENSE_SMEM16C)
-        assert (got == want).all()
-
-
-def test_partition_deferred_retry(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_DEFER at k = 9..12 against the oracle, and against the shipped path at 1 Gbp"""
-    import torch
-    n = 40_000_000
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    for k in (9, 10, 11, 12):
-        want, _ = oracle.count_dense(genome, k)
-        assert (_dense(ctx, kmerlib, genome, k, kmerlib.DENSE_PARTITION_DEFER) == want).all()
-    L = 1 << 30
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_DEFER)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-
-
-def test_partition_two_increment_count(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_TRIO (k = 12) against the oracle, against the shipped path at 1 Gbp, and on
-    2^26 'A's (8-bit fields wrap in partition 0: checksum + 32-bit recount)"""
-    import torch
-    n = 40_000_000
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_TRIO) == want).all()
-    L = 1 << 30
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_TRIO)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-    del data, a, b
-    poly = torch.full((1 << 26,), ord("A"), dtype=torch.uint8, device="cuda:0")
-    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(poly, 1 << 26, 0, 1 << 26, 12, t, algo=kmerlib.DENSE_PARTITION_TRIO)
-    torch.cuda.synchronize()
-    assert int(t[0].item()) == (1 << 26) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 26) - 11
-
-
-def test_partition_wide_records(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_WIDE (k = 12, seven windows per record) against the oracle, against the shipped
-    path at 1 Gbp, and on 2^26 'A's (4-bit fields wrap: checksum + 32-bit recount)"""
-    import torch
-    n = 40_000_000
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_WIDE) == want).all()
-    L = 1 << 30
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_WIDE)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-    del data, a, b
-    poly = torch.full((1 << 26,), ord("A"), dtype=torch.uint8, device="cuda:0")
-    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(poly, 1 << 26, 0, 1 << 26, 12, t, algo=kmerlib.DENSE_PARTITION_WIDE)
-    torch.cuda.synchronize()
-    assert int(t[0].item()) == (1 << 26) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 26) - 11
-
-
-def test_partition_paired_count(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_PAIR (k = 12) against the oracle, and against the shipped path at 1 Gbp;
-    2^30 'A's: partition 0's regions hold ~127 K identical records (148 regions of ~860), one 16-bit
-    field wraps, the checksum fails and the 32-bit recount runs"""
-    import torch
-    n = 40_000_000
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_PAIR) == want).all()
-    L = 1 << 30
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_PAIR)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-    del data, a, b
-    poly = torch.full((1 << 30,), ord("A"), dtype=torch.uint8, device="cuda:0")
-    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(poly, 1 << 30, 0, 1 << 30, 12, t, algo=kmerlib.DENSE_PARTITION_PAIR)
-    torch.cuda.synchronize()
-    assert int(t[0].item()) == (1 << 30) - 11 and int(t.to(torch.int64).sum().item()) == (1 << 30) - 11
-
-
-def test_packed_store(ctx, kmerlib, oracle):
-    """f4: pack -> layout of main.cu:78-86 + validity bitmap; unpack inverse (invalid -> 'N'); counting
-    from the store equals counting the bytes (k = 5, 8, 12; the last case is 1.2 Gbp: it crosses the 2^30 chunk edge)"""
-    import torch
-    n = 5_000_003
-    data = oracle.gen_genome(0xB2000003, n, 5, 500, 12, 0, n).copy()
-    data[1000:1100] = np.frombuffer(b"acgtN\n\0|>x", dtype=np.uint8)[np.arange(100) % 10]
-    d = to_dev(data)
-    packed, mask = ctx.pack_2bit(d, n)
-    code = np.full(256, -1, dtype=np.int64)
-    for i, ch in enumerate(b"ACGT"):
-        code[ch] = i
-    c = code[data]
-    bad = c < 0
-    q = np.concatenate([np.where(bad, 0, c).astype(np.uint8), np.zeros((-n) % 4, np.uint8)]).reshape(-1, 4)
-    want = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
-    assert (packed[: want.size].cpu().numpy() == want).all()
-    back = ctx.unpack_2bit(packed, mask, n).cpu().numpy()
-    assert (back == np.where(bad, ord("N"), data)).all()
-    for k in (5, 8, 12):
-        t = ctx.count_dense_packed(packed, mask, n, k).cpu().numpy().view(np.uint32)
-        w, _ = oracle.count_dense(data, k)
-        assert (t == w).all(), k
-    L = 1_200_000_000
-    big = ctx.gen_genome(0xB2000003, L, 60, 600, 12, 0, L)
-    p2, m2 = ctx.pack_2bit(big, L)
-    a = ctx.count_dense_packed(p2, m2, L, 12)
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(big, L, 0, L, 12, b)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-
-
-def test_gpu_fasta_parser(ctx, kmerlib, oracle, golden):
-    """f2, device side: raw FASTA bytes in HBM -> kc_import_seqs_device == the host loader; then the
-    per-sequence counts of the device-resident set == the oracle's"""
-    rng = np.random.default_rng(5)
-    recs = []
-    for i in range(30):
-        seq = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, int(rng.integers(1, 200_000)))].tobytes()
-        recs.append(b">chr%d test\n" % i + b"\n".join(seq[j:j + 70] for j in range(0, len(seq), 70)) + b"\n\n")
-    texts = [b"".join(recs)] + [c["fasta"].encode("latin-1") for c in golden["loader"]]
-    for text in texts:
-        for mode in (0, 1):
-            want = kmerlib.SeqSet.from_memory(text, mode, 0)
-            d_raw = to_dev(np.frombuffer(text, dtype=np.uint8)) if text else None
-            got = kmerlib.SeqSet.from_device(ctx, d_raw, text, len(text), mode)
-            assert got.num_seqs == want.num_seqs and got.ids == want.ids
-            assert got.offsets.tolist() == want.offsets.tolist() and got.data == want.data
-            got.close()
-            want.close()
-
-
-def test_nccl_range_sharded_radix():
-    """multi-GPU (>= 2 GPUs visible): scatter, all-to-all of the slabs, count per rank, vs the oracle"""
-    import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs (tests/test_sharding_gloo.py covers the host logic with gloo + emulator kernels)")
-    world = 2 if n < 4 else 4
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
-           "--master-addr", "127.0.0.1", "--master-port", "29661", os.path.join(ROOT, "tests", "_nccl_radix_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "NCCL_RADIX_WORKER_OK world=%d" % world in r.stdout
+@pytest.mark.parametrize("case", CASES)
+def test_first_run(case):
+    if _state["t0"] is None:
+        _state["t0"] = time.monotonic()
+    if _state["gpu_lost"]:
+        pytest.fail("skipped: the GPU stopped answering after an earlier case")
+    left = FILE_BUDGET_S - (time.monotonic() - _state["t0"])
+    if left < 30:
+        pytest.fail("skipped: this file's %d s budget is spent" % FILE_BUDGET_S)
+    cmd = [sys.executable, "-m", "pytest", CASES_FILE, "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", case]
+    rc, out = _run(cmd, min(CASE_TIMEOUT_S, left))
+    if rc is None:
+        _state["gpu_lost"] = not _gpu_answers()
+        pytest.fail("%s: no result within the time limit (killed)%s\n%s"
+                    % (case, "; the GPU no longer answers" if _state["gpu_lost"] else "", out[-3000:]))
+    assert rc == 0, "%s: exit code %d\n%s" % (case, rc, out[-6000:])
+    assert " passed" in out or " skipped" in out, out[-2000:]
