@@ -380,6 +380,38 @@ def probe_variants(args, k, local):
     return done(best, report)
 
 
+def probe_e2e_packed(args, local):
+    """kc_count_dense_host_packed on the full workload in its own process (bounded, killed with its group on a hang)"""
+    import subprocess
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local), LOCAL_WORLD_SIZE="1")
+    cmd = [sys.executable, PROBE_SCRIPT, "--workload", args.workload, "--steps", str(args.steps), "--probe", "--probe-e2e"]
+    if args.length:
+        cmd += ["--length", str(args.length)]
+    limit = float(os.environ.get("KC_BENCH_E2E_PROBE_S", "180"))
+    t0 = time.monotonic()
+    try:
+        p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                             stdin=subprocess.DEVNULL, start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=limit)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(p.pid, 9)
+            except ProcessLookupError:
+                pass
+            try:
+                p.communicate(timeout=30)
+            except subprocess.TimeoutExpired:
+                pass
+            return {"ok": False, "why": "no result within %.0f s (killed)" % limit}
+        if p.returncode != 0:
+            return {"ok": False, "why": "exit code %d" % p.returncode, "wall_s": time.monotonic() - t0}
+        d = json.loads([ln for ln in out.splitlines() if ln.strip()][-1])
+        return {"ok": True, "ms": d["e2e_packed_ms"], "fp": d["fp"], "h2d_bytes": d["h2d_bytes"], "wall_s": time.monotonic() - t0}
+    except Exception as ex:
+        return {"ok": False, "why": str(ex)[:120]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -401,6 +433,7 @@ def main():
                          "(measured slower than S=1 at N=2: 2.24 / 2.57 / 3.35 ms for S=1/2/4)")
     ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of a replayed CUDA graph")
     ap.add_argument("--probe", action="store_true", help="internal: this run is a variant probe of a parent bench.py")
+    ap.add_argument("--probe-e2e", action="store_true", help="internal: measure kc_count_dense_host_packed for a parent bench.py")
     ap.add_argument("--no-probe", action="store_true", help="do not try the not-yet-default kernel variants (see probe_variants)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -482,6 +515,22 @@ def main():
     def fingerprint(t):  # position-weighted sum of all bins (int64, wraps): equal tables <=> equal with probability ~1
         wgt = (torch.arange(t.numel(), dtype=torch.int64, device=t.device) % 65521) + 1
         return int((t.to(torch.int64) * wgt).sum().item())
+
+    if args.probe_e2e:  # child of probe_e2e_packed(): the packed host path on the full workload, in its own process
+        host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        host.copy_(data)
+        h_table = torch.empty(nk, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        ctx.count_dense_host_packed(host, k, h_table)
+        fp = fingerprint(h_table.to(dev))
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            ctx.count_dense_host_packed(host, k, h_table)
+        dt = (time.perf_counter() - t0) / n_e2e
+        emit({"e2e_packed_ms": dt * 1e3, "fp": fp, "h2d_bytes": ctx.last_h2d_bytes, "steps": n_e2e})
+        leave(world)
+        return 0
 
     def timed():
         kmerb200.lib().kc_ctx_set_timing(ctx._h, 0)
@@ -637,6 +686,34 @@ def main():
                "api": "kc_count_dense_host" if world == 1 else "H2D + kc_count_dense_range_async + NCCL reduce + D2H"}
         if rank == 0 and world == 1:
             assert int(h_table.to(torch.int64).sum().item()) == checksum, "e2e table differs from resident-input table"
+        # The plain host path is bound by PCIe at 1 byte per base.  kc_count_dense_host_packed packs on the host cores
+        # first (0.375 B/base or less over PCIe); whether that wins depends on the cores this process may use, so it
+        # is measured: first in its own process (its kernels' first B200 run is pending), then —
+        # only if that process reproduced the resident-input table — here, and the faster of the two is reported.
+        if world == 1 and not args.no_probe and not os.environ.get("KC_BENCH_NO_PROBE"):
+            pk = probe_e2e_packed(args, local)
+            e2e["packed_probe"] = pk
+            if pk.get("ok") and pk.get("fp") == table_fp:
+                try:
+                    ctx.count_dense_host_packed(host, k, h_table)
+                    same = fingerprint(h_table.to(dev)) == table_fp
+                    t0 = time.perf_counter()
+                    for _ in range(n_e2e):
+                        ctx.count_dense_host_packed(host, k, h_table)
+                    torch.cuda.synchronize()
+                    dtp = (time.perf_counter() - t0) / n_e2e
+                    same = same and fingerprint(h_table.to(dev)) == table_fp
+                    pk["in_process_ms"] = dtp * 1e3
+                    pk["in_process_same_table"] = same
+                    if same and dtp < float(dt.item()):
+                        e2e = {"value": L / dtp, "unit": "bases/s", "h2d_bytes_per_step": ctx.last_h2d_bytes,
+                               "d2h_bytes_per_step": 4 * nk, "ms_per_step": dtp * 1e3, "steps": n_e2e,
+                               "api": "kc_count_dense_host_packed (host threads pack to 2 bits + validity bitmap, GPU unpacks and counts)",
+                               "plain": {"api": "kc_count_dense_host", "value": e2e["value"], "ms_per_step": e2e["ms_per_step"],
+                                         "h2d_bytes_per_step": e2e["h2d_bytes_per_step"]},
+                               "packed_probe": pk}
+                except Exception as ex:
+                    pk["in_process_error"] = str(ex)[:200]
         del host
 
     # ---- CPU baseline: the oracle port, 1 thread, bounded sample ---------------

@@ -1373,6 +1373,7 @@ extern "C" int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nby
         }
     }
     cudaEventDestroy(ev);
+    ctx->last_h2d_bytes = nbytes;
     KC_CUDA(ctx, cudaMemcpyAsync(h_table, d_table, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KC_OK;

@@ -14,7 +14,16 @@
 // bytes.  The counting kernels are bound by shared-memory atomics and decode, not by HBM, so a kernel
 // that scans the packed words directly would save little; the store is about HBM capacity (a 30 Gbp
 // read set is 11 GB packed).
+#include <sched.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
+
+// hostpack.cpp (plain g++): ASCII -> store layout on the host cores, one range per call
+extern "C" uint32_t kc_host_pack_range(const char* data, uint64_t n, uint8_t* packed, uint32_t* badmask, int force_scalar);
 
 namespace {
 
@@ -163,6 +172,249 @@ int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32_t* d_b
         }
     }
     KC_CUDA(ctx, cudaStreamSynchronize(st));
+    return KC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Counting from HOST memory through the packed form.  kc_count_dense_host moves 1 byte per base over
+// PCIe and is bound by it (3.1 GB: 57 ms, while the GPU counts them in 4 ms).  Here the host cores turn
+// the ASCII into the store's layout first (0.375 bytes per base), the GPU turns it back at HBM speed:
+//
+//   packer threads --items--> ring of pinned slots --H2D (copy stream)--> d_packed / d_mask
+//                                                   --event--> unpack_kernel --> d_ascii --> dense path
+//
+// * item = 2^20 bases, claimed from one atomic counter (in order, so the ring fills front to back);
+//   slot = 16 items = 4 MiB packed + 2 MiB mask; the ring holds 8 slots (48 MiB pinned, kept in the ctx).
+// * a packer may write slot s only when slot s - RING has left the host (`released`, published by the
+//   calling thread after cudaEventQuery of that slot's copy); the calling thread issues the copies of slot
+//   s once its 16 items are done.  No thread ever blocks inside the CUDA runtime.
+// * every COUNT_SLOTS slots (2^28 bases) the compute stream waits for the copies so far, unpacks those
+//   bases into the ASCII image and counts the windows that END inside it, exactly like kc_count_dense_host.
+// The result is kc_count_dense's: unpacking restores every valid byte and turns every invalid one into
+// 'N', which resets a window like the byte it replaces.
+namespace {
+
+constexpr int HP_ITEMS_PER_SLOT = 16;
+constexpr int HP_RING = 8;
+constexpr int HP_COUNT_SLOTS = 16;             // slots per unpack + count call
+// bases per packer item, a multiple of 32 (whole mask words).  KC_HOSTPACK_ITEM is a test aid: small items
+// drive a small input through many slots, ring wrap-arounds and count calls.
+static uint64_t hp_item() {
+    static const uint64_t v = [] {
+        const char* e = getenv("KC_HOSTPACK_ITEM");
+        uint64_t x = e ? strtoull(e, nullptr, 0) : 0;
+        x = (x + 31) / 32 * 32;
+        return x ? x : (1ull << 20);
+    }();
+    return v;
+}
+#define HP_ITEM hp_item()
+#define HP_SLOT (HP_ITEM * HP_ITEMS_PER_SLOT)
+#define HP_SLOT_BYTES ((size_t)(HP_SLOT / 4 + HP_SLOT / 8))
+
+int host_threads(int asked) {
+    if (asked > 0) return asked > 256 ? 256 : asked;
+    int n = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);
+    if (n < 1) n = (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    n -= 1;  // the calling thread drives the copies
+    if (n < 1) n = 1;
+    return n > 64 ? 64 : n;
+}
+
+struct HostPackPipe {
+    const char* h_data;
+    uint64_t n;
+    uint64_t nitems, nslots;
+    uint8_t* ring;
+    std::atomic<uint64_t> next_item{0};
+    std::atomic<uint64_t> released{0};  // slots [0, released) have left the host
+    std::atomic<int> stop{0};
+    std::atomic<int> done[HP_RING];
+    std::atomic<uint32_t> anybad[HP_RING];  // OR of the slot's mask words: 0 = the mask need not cross PCIe
+
+    uint64_t items_of(uint64_t slot) const {
+        const uint64_t first = slot * HP_ITEMS_PER_SLOT;
+        return nitems - first < (uint64_t)HP_ITEMS_PER_SLOT ? nitems - first : (uint64_t)HP_ITEMS_PER_SLOT;
+    }
+    void work() {
+        for (;;) {
+            const uint64_t it = next_item.fetch_add(1, std::memory_order_relaxed);
+            if (it >= nitems) return;
+            const uint64_t slot = it / HP_ITEMS_PER_SLOT;
+            while (slot >= released.load(std::memory_order_acquire) + HP_RING) {
+                if (stop.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            if (stop.load(std::memory_order_relaxed)) return;
+            uint8_t* base = ring + (size_t)(slot % HP_RING) * HP_SLOT_BYTES;
+            const uint64_t j = it % HP_ITEMS_PER_SLOT;
+            const uint64_t b = it * HP_ITEM;
+            const uint64_t len = n - b < HP_ITEM ? n - b : HP_ITEM;
+            const uint32_t any = kc_host_pack_range(h_data + b, len, base + j * (HP_ITEM / 4),
+                                                    reinterpret_cast<uint32_t*>(base + HP_SLOT / 4) + j * (HP_ITEM / 32), 0);
+            if (any) anybad[slot % HP_RING].fetch_or(any, std::memory_order_relaxed);
+            done[slot % HP_RING].fetch_add(1, std::memory_order_release);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask, int nthreads) {
+    if (nbytes == 0) return KC_OK;
+    if (!h_data || !h_packed || !h_badmask) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_pack_2bit_host: null pointer");
+    const bool scalar = nthreads < 0;  // test aid: -T = T threads, scalar body
+    if (scalar) nthreads = -nthreads;
+    const uint64_t nitems = (nbytes + HP_ITEM - 1) / HP_ITEM;
+    int T = host_threads(nthreads);
+    if ((uint64_t)T > nitems) T = (int)nitems;
+    std::atomic<uint64_t> next{0};
+    auto body = [&]() {
+        for (;;) {
+            const uint64_t it = next.fetch_add(1, std::memory_order_relaxed);
+            if (it >= nitems) return;
+            const uint64_t b = it * HP_ITEM;
+            const uint64_t len = nbytes - b < HP_ITEM ? nbytes - b : HP_ITEM;
+            kc_host_pack_range(h_data + b, len, (uint8_t*)h_packed + b / 4, h_badmask + b / 32, scalar ? 1 : 0);
+        }
+    };
+    std::vector<std::thread> th;
+    try {
+        for (int t = 1; t < T; t++) th.emplace_back(body);
+    } catch (...) {  // fewer threads than asked for: the ones that run (and this one) do all items
+    }
+    body();
+    for (auto& t : th) t.join();
+    return KC_OK;
+}
+
+int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table, int nthreads) {
+    if (!ctx) return KC_ERR_INVALID;
+    if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
+    if (!h_table || (!h_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
+    DeviceGuard dg(ctx->device);
+    const size_t table_bytes = sizeof(uint32_t) << (2 * k);
+    // device image: table | ASCII (rounded up to 256 B) | packed | mask
+    const size_t ascii_bytes = (size_t)((nbytes + 64 + 255) & ~(uint64_t)255);
+    const size_t packed_bytes = (size_t)(((nbytes + 3) / 4 + 255) & ~(uint64_t)255);
+    const size_t mask_bytes = (size_t)((nbytes + 31) / 32 * 4);
+    int rc = kc_scratch2_reserve(ctx, table_bytes + ascii_bytes + packed_bytes + mask_bytes + 256);
+    if (rc) return rc;
+    uint32_t* d_table = (uint32_t*)ctx->scratch2;
+    char* d_ascii = (char*)ctx->scratch2 + table_bytes;
+    uint8_t* d_packed = (uint8_t*)d_ascii + ascii_bytes;
+    uint32_t* d_mask = (uint32_t*)(d_packed + packed_bytes);
+    KC_CUDA(ctx, cudaMemsetAsync(d_table, 0, table_bytes, ctx->stream));
+    ctx->last_h2d_bytes = 0;
+    if (nbytes >= (uint64_t)k) {
+        const size_t ring_bytes = (size_t)HP_RING * HP_SLOT_BYTES;
+        if (ctx->pinned_bytes < ring_bytes) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr;
+            ctx->pinned_bytes = 0;
+            cudaError_t e = cudaHostAlloc(&ctx->pinned, ring_bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->pinned = nullptr;
+                return kc_set_error(ctx, KC_ERR_NOMEM, "cudaHostAlloc(%zu): %s", ring_bytes, cudaGetErrorString(e));
+            }
+            ctx->pinned_bytes = ring_bytes;
+        }
+        HostPackPipe pipe;
+        pipe.h_data = h_data;
+        pipe.n = nbytes;
+        pipe.nitems = (nbytes + HP_ITEM - 1) / HP_ITEM;
+        pipe.nslots = (pipe.nitems + HP_ITEMS_PER_SLOT - 1) / HP_ITEMS_PER_SLOT;
+        pipe.ring = (uint8_t*)ctx->pinned;
+        for (int i = 0; i < HP_RING; i++) {
+            pipe.done[i].store(0, std::memory_order_relaxed);
+            pipe.anybad[i].store(0, std::memory_order_relaxed);
+        }
+        cudaEvent_t ev[HP_RING];
+        int nev = 0;
+        cudaError_t ce = cudaSuccess;
+        for (; nev < HP_RING && ce == cudaSuccess; nev++) ce = cudaEventCreateWithFlags(&ev[nev], cudaEventDisableTiming);
+        if (ce != cudaSuccess) {
+            for (int i = 0; i + 1 < nev; i++) cudaEventDestroy(ev[i]);
+            return kc_set_error(ctx, KC_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce));
+        }
+        int T = host_threads(nthreads);
+        if ((uint64_t)T > pipe.nitems) T = (int)pipe.nitems;
+        std::vector<std::thread> th;
+        try {
+            for (int t = 0; t < T; t++) th.emplace_back([&pipe]() { pipe.work(); });
+        } catch (...) {
+        }
+        const uint64_t nwin = nbytes - k + 1;
+        uint64_t issued = 0, released = 0, unpacked = 0, counted = 0, h2d = 0;
+        rc = KC_OK;
+        if (th.empty()) rc = kc_set_error(ctx, KC_ERR_NOMEM, "kc_count_dense_host_packed: no packer thread could be started");
+        while (!rc && released < pipe.nslots) {
+            bool progress = false;
+            if (issued < pipe.nslots && issued < released + HP_RING &&
+                (uint64_t)pipe.done[issued % HP_RING].load(std::memory_order_acquire) == pipe.items_of(issued)) {
+                const int r = (int)(issued % HP_RING);
+                const uint32_t anybad = pipe.anybad[r].exchange(0, std::memory_order_relaxed);
+                pipe.done[r].store(0, std::memory_order_relaxed);  // before `released` lets anyone at this slot again
+                const uint64_t b = issued * HP_SLOT;
+                const uint64_t e = (b + HP_SLOT < nbytes) ? b + HP_SLOT : nbytes;
+                const uint8_t* src = pipe.ring + (size_t)r * HP_SLOT_BYTES;
+                ce = cudaMemcpyAsync(d_packed + b / 4, src, (size_t)((e - b + 3) / 4), cudaMemcpyHostToDevice, ctx->copy_stream);
+                // an all-valid slot (most of a genome) sends no mask: the device zeroes its words instead
+                if (ce == cudaSuccess && anybad)
+                    ce = cudaMemcpyAsync(d_mask + b / 32, src + HP_SLOT / 4, (size_t)((e - b + 31) / 32 * 4), cudaMemcpyHostToDevice,
+                                         ctx->copy_stream);
+                else if (ce == cudaSuccess)
+                    ce = cudaMemsetAsync(d_mask + b / 32, 0, (size_t)((e - b + 31) / 32 * 4), ctx->copy_stream);
+                h2d += (e - b + 3) / 4 + (anybad ? (e - b + 31) / 32 * 4 : 0);
+                if (ce == cudaSuccess) ce = cudaEventRecord(ev[r], ctx->copy_stream);
+                issued++;
+                if (ce == cudaSuccess && (issued % HP_COUNT_SLOTS == 0 || issued == pipe.nslots)) {
+                    // bases [unpacked, e) are on their way: unpack and count behind them
+                    ce = cudaStreamWaitEvent(ctx->stream, ev[r], 0);
+                    if (ce == cudaSuccess) {
+                        rc = unpack_range(ctx, d_packed, d_mask, unpacked, e - unpacked, d_ascii + unpacked, ctx->stream);
+                        unpacked = e;
+                        uint64_t upto = (e >= (uint64_t)k) ? e - k + 1 : 0;  // windows that end before byte e
+                        if (upto > nwin) upto = nwin;
+                        if (!rc && upto > counted) {
+                            rc = kc_count_dense_range_async(ctx, d_ascii, e, counted, upto, k, d_table, KC_DENSE_AUTO, ctx->stream);
+                            counted = upto;
+                        }
+                    }
+                }
+                if (ce != cudaSuccess) rc = kc_set_error(ctx, KC_ERR_CUDA, "host staging failed: %s", cudaGetErrorString(ce));
+                progress = true;
+            }
+            if (!rc && released < issued) {
+                ce = cudaEventQuery(ev[released % HP_RING]);
+                if (ce == cudaSuccess) {
+                    released++;
+                    pipe.released.store(released, std::memory_order_release);
+                    progress = true;
+                } else if (ce != cudaErrorNotReady) {
+                    rc = kc_set_error(ctx, KC_ERR_CUDA, "host staging failed: %s", cudaGetErrorString(ce));
+                }
+            }
+            if (!progress) std::this_thread::yield();
+        }
+        pipe.stop.store(1, std::memory_order_relaxed);
+        pipe.next_item.store(pipe.nitems, std::memory_order_relaxed);
+        for (auto& t : th) t.join();
+        if (rc) cudaStreamSynchronize(ctx->copy_stream);  // the ring must not be reused under a copy in flight
+        for (int i = 0; i < HP_RING; i++) cudaEventDestroy(ev[i]);
+        if (rc) return rc;
+        ctx->last_h2d_bytes = h2d;
+    }
+    KC_CUDA(ctx, cudaMemcpyAsync(h_table, d_table, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KC_OK;
 }
 

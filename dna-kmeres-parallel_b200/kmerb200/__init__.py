@@ -59,6 +59,7 @@ def lib():
         "kc_ctx_device": (i32, [vp]),
         "kc_ctx_sm_count": (i32, [vp]),
         "kc_ctx_launch_count": (u64, [vp]),
+        "kc_ctx_last_h2d_bytes": (u64, [vp]),
         "kc_ctx_synchronize": (i32, [vp]),
         "kc_ctx_set_timing": (i32, [vp, i32]),
         "kc_ctx_pass_times": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -98,6 +99,9 @@ def lib():
         "kc_pack_2bit": (i32, [vp, vp, u64, vp, vp, vp]),
         "kc_unpack_2bit": (i32, [vp, vp, vp, u64, vp, vp]),
         "kc_count_dense_packed": (i32, [vp, vp, vp, u64, i32, vp]),
+        "kc_pack_2bit_host": (i32, [vp, u64, vp, vp, i32]),
+        "kc_host_pack_simd": (i32, []),
+        "kc_count_dense_host_packed": (i32, [vp, vp, u64, i32, vp, i32]),
         "kc_sparse_radix_plan": (i32, [vp, u64, i32, C.c_uint32, vp]),
         "kc_sparse_radix_scatter": (i32, [vp, vp, u64, vp, vp, vp]),
         "kc_sparse_radix_count": (i32, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
@@ -196,6 +200,17 @@ def dump_counts(path, sums, k, num_seqs):
 def dump_distances(path, dist):
     dist = np.ascontiguousarray(dist, dtype=np.float32)
     _check0(lib().kc_dump_distances(path.encode() if path else None, dist.ctypes.data, dist.size))
+
+
+def pack_2bit_host(h_data, nthreads=0):
+    """host-side packer of the 2-bit store (numpy uint8 in) -> (packed uint8[(n+3)/4], badmask uint32[(n+31)/32]);
+    nthreads < 0: |nthreads| threads with the scalar body (tests)"""
+    a = np.ascontiguousarray(h_data, dtype=np.uint8)
+    n = a.size
+    packed = np.zeros(int(lib().kc_packed_bytes(n)), dtype=np.uint8)
+    mask = np.zeros(int(lib().kc_badmask_bytes(n)) // 4, dtype=np.uint32)
+    _check0(lib().kc_pack_2bit_host(_ptr(a), n, _ptr(packed), _ptr(mask), nthreads))
+    return packed, mask
 
 
 def pass_times(ctx):
@@ -364,6 +379,11 @@ class Context:
     def launch_count(self):
         return int(lib().kc_ctx_launch_count(self._h))
 
+    @property
+    def last_h2d_bytes(self):
+        """bytes the last count_dense_host[_packed] call copied host -> device"""
+        return int(lib().kc_ctx_last_h2d_bytes(self._h))
+
     def synchronize(self):
         self._check(lib().kc_ctx_synchronize(self._h))
 
@@ -398,6 +418,14 @@ class Context:
         if h_table is None:
             h_table = np.empty(num_kmers(k), dtype=np.uint32)
         self._check(lib().kc_count_dense_host(self._h, _ptr(h_data), n, k, _ptr(h_table)))
+        return h_table
+
+    def count_dense_host_packed(self, h_data, k, h_table=None, nthreads=0):
+        """count_dense_host through the packed form: host threads pack (0.375 B/base over PCIe), the GPU unpacks and counts"""
+        n = h_data.numel() if hasattr(h_data, "numel") else h_data.size
+        if h_table is None:
+            h_table = np.empty(num_kmers(k), dtype=np.uint32)
+        self._check(lib().kc_count_dense_host_packed(self._h, _ptr(h_data), n, k, _ptr(h_table), nthreads))
         return h_table
 
     def count_per_seq(self, d_data, d_offsets, num_seqs, k, sums=None, stream=None, sync=True):

@@ -68,6 +68,8 @@ KC_API int kc_ctx_device(const kc_ctx* ctx);
 KC_API int kc_ctx_sm_count(const kc_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench "gpu_launches") */
 KC_API uint64_t kc_ctx_launch_count(const kc_ctx* ctx);
+/* bytes the last kc_count_dense_host[_packed] call of this ctx copied host -> device */
+KC_API uint64_t kc_ctx_last_h2d_bytes(const kc_ctx* ctx);
 /* block until everything enqueued through this ctx has finished */
 KC_API int kc_ctx_synchronize(kc_ctx* ctx);
 /* Measurement aid: when enabled, the dense entry points bracket their kernels
@@ -288,6 +290,19 @@ KC_API int kc_unpack_2bit(kc_ctx* ctx, const void* d_packed, const uint32_t* d_b
  * 2^30-base chunks are unpacked into an ASCII scratch and counted by the ordinary dense path */
 KC_API int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32_t* d_badmask,
                                  uint64_t nbases, int k, uint32_t* d_table);
+/* The same conversion on the HOST cores (format conversion only; counting has no CPU path): h_data ->
+ * h_packed[(n+3)/4], h_badmask[(n+31)/32]; bit-identical to kc_pack_2bit's output.  nthreads 0 = one per
+ * core this process may run on (at most 64).  AVX2 body when the host has it (kc_host_pack_simd() == 1). */
+KC_API int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask,
+                             int nthreads);
+KC_API int kc_host_pack_simd(void);
+/* kc_count_dense_host (main.cu:287-299: the reference's count step starts from host/managed memory)
+ * for hosts with cores to spare: packer threads turn the ASCII into the store's layout slot by slot
+ * (pinned ring), the slots cross PCIe at 0.375 bytes per base instead of 1, the GPU unpacks them at HBM
+ * speed and counts behind the copies.  Same result as kc_count_dense_host / kc_count_dense.  nthreads =
+ * packer threads (0 = cores available to the process - 1, at most 64).                               */
+KC_API int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k,
+                                      uint32_t* h_table, int nthreads);
 
 /* ------------------------------------------------------------------ */
 /* Count table dump.  Byte-identical to the (commented-out) dump at    */

@@ -203,6 +203,36 @@ def test_packed_store(ctx, kmerlib, oracle):
     assert bool((a == b).all())
 
 
+def test_host_packed_count(ctx, kmerlib, oracle):
+    """kc_count_dense_host_packed (host threads pack, 0.375 B/base or less over PCIe, GPU unpacks and counts behind
+    the copies) == the oracle at 40 Mbp (k = 12, 8, 3; pinned and pageable input), == kc_count_dense_host and the
+    resident-input table at 1.2 Gbp; dirty bytes; the bytes sent are the packed bytes + the mask words of the
+    slots that hold an invalid byte"""
+    import torch
+    n = 40_000_000
+    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n).copy()
+    genome[12345:12400] = np.frombuffer(b"acgtN\n\0|>x\xff", dtype=np.uint8)[np.arange(55) % 11]
+    pinned = torch.from_numpy(genome).pin_memory()
+    for k in (12, 8, 3):
+        want, _ = oracle.count_dense(genome, k)
+        for src in (pinned, genome):
+            got = ctx.count_dense_host_packed(src, k)
+            assert (got == want).all(), k
+        assert (n + 3) // 4 <= ctx.last_h2d_bytes <= (n + 3) // 4 + (n + 31) // 32 * 4
+    assert ctx.last_h2d_bytes < 0.33 * n   # most 16 Mbase slots of this input hold no invalid byte
+    assert (ctx.count_dense_host_packed(genome[:7], 12) == 0).all()
+    L = 1_200_000_000
+    big = ctx.gen_genome(0xB2000003, L, 60, 600, 12, 0, L)
+    host = torch.empty(L, dtype=torch.uint8, pin_memory=True)
+    host.copy_(big)
+    a = ctx.count_dense_host_packed(host, 12, nthreads=0)
+    b = ctx.count_dense_host(host, 12)
+    c = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    ctx.count_dense_range(big, L, 0, L, 12, c)
+    torch.cuda.synchronize()
+    assert (a == b).all() and (a == c.cpu().numpy().view(np.uint32)).all()
+
+
 def test_gpu_fasta_parser(ctx, kmerlib, oracle, golden):
     """f2, device side: raw FASTA bytes in HBM -> kc_import_seqs_device == the host loader; then the
     per-sequence counts of the device-resident set == the oracle's"""

@@ -81,6 +81,10 @@ def lib():
         L.kc_pack_2bit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_unpack_2bit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.kc_count_dense_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.kc_ctx_last_h2d_bytes.restype = C.c_uint64
+        L.kc_ctx_last_h2d_bytes.argtypes = [C.c_void_p]
+        L.kc_pack_2bit_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.kc_count_dense_host_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
         L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
         L.kc_sparse_radix_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -355,6 +359,33 @@ def case_dense_host(args):
     print("ok dense_host", *args)
 
 
+def case_dense_host_packed(args):
+    """kc_count_dense_host_packed: host threads pack into the pinned ring, slots are copied, unpacked and
+    counted behind the copies; KC_HOSTPACK_ITEM (env) makes the items small enough for ring wrap-arounds"""
+    k, n, seed, kind, nthreads = int(args[0]), int(args[1]), int(args[2]), args[3], int(args[4])
+    O = _oracle()
+    data = make_input(kind, n, seed, k)
+    ctx = EmuContext()
+    want, _ = O.count_dense(data, k)
+    for rep in range(2):  # the second call reuses the ring and the device image
+        table = np.full(4 ** k, 0xDEADBEEF, dtype=np.uint32)
+        ctx.check(ctx.L.kc_count_dense_host_packed(ctx.h, data.ctypes.data if n else None, n, k, table.ctypes.data, nthreads))
+        assert (table == want).all(), "kc_count_dense_host_packed differs"
+        sent = int(ctx.L.kc_ctx_last_h2d_bytes(ctx.h))
+        if n >= k:  # the packed bytes + the mask words of the slots that hold an invalid byte (or the end of the input)
+            item = (int(os.environ.get("KC_HOSTPACK_ITEM", "0")) + 31) // 32 * 32 or (1 << 20)
+            slot = 16 * item
+            valid = np.isin(data, np.frombuffer(b"ACGT", dtype=np.uint8))
+            expect = (n + 3) // 4
+            for b in range(0, n, slot):
+                e = min(b + slot, n)
+                if not valid[b:e].all() or (e - b) % 32:
+                    expect += (e - b + 31) // 32 * 4
+            assert sent == expect, (sent, expect)
+    ctx.close()
+    print("ok dense_host_packed", *args)
+
+
 def case_packed(args):
     """f4: pack -> the reference sketch's layout (first base in the top two bits of each byte) + validity
     bitmap; unpack is the inverse up to invalid -> 'N'; counting from the store == counting the bytes"""
@@ -385,6 +416,12 @@ def case_packed(args):
     bits = np.concatenate([bad, np.ones((-n) % 32, dtype=bool)]).reshape(-1, 32)   # bases past the end count as invalid
     want_mask = (bits.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
     assert (mask == want_mask).all(), "validity bitmap differs"
+    # the host-side packer (hostpack.cpp: AVX2 body, scalar body, several threads) writes the same store
+    for nthreads in (1, 3, -1, -2):
+        hp = np.full(pb, 0xEE, dtype=np.uint8)
+        hm = np.full(mb // 4, 0xEEEEEEEE, dtype=np.uint32)
+        ctx.check(L.kc_pack_2bit_host(data.ctypes.data, n, hp.ctypes.data, hm.ctypes.data, nthreads))
+        assert (hp == packed).all() and (hm == mask).all(), "host packer differs from pack_kernel (nthreads=%d)" % nthreads
     d_o = ctx.alloc(n)
     ctx.check(L.kc_unpack_2bit(ctx.h, d_p, d_m, n, d_o, None))
     back = ctx.download(d_o, n, np.uint8)
@@ -465,7 +502,7 @@ def case_ingest(args):
     print("ok ingest", *args, "files", len(texts))
 
 
-CASES = {"ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+CASES = {"dense_host_packed": case_dense_host_packed, "ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

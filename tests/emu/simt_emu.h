@@ -236,7 +236,7 @@ static inline size_t __cvta_generic_to_shared(const void* p) {
 
 // ---- CUDA runtime stand-ins ------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorNotReady = 600 };
 typedef struct emu_stream* cudaStream_t;
 typedef struct emu_event* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
@@ -298,6 +298,7 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
 }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }  // everything is synchronous here
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
     *ms = 0.f;
     return cudaSuccess;

@@ -222,6 +222,18 @@ def test_packed_store_on_emulator():
         run_case("packed", 2, n, 6)
 
 
+def test_host_packed_count_on_emulator():
+    """kc_count_dense_host_packed: packer threads -> pinned ring -> H2D -> unpack -> count behind the copies.
+    64-base items: a 200 K input goes through ~200 slots (25 ring wrap-arounds) and 13 count calls"""
+    run_case("dense_host_packed", 5, 200_003, 1, "dirty", 3, KC_HOSTPACK_ITEM=64)
+    run_case("dense_host_packed", 12, 300_000, 2, "genome", 2, KC_HOSTPACK_ITEM=96)
+    run_case("dense_host_packed", 8, 70_001, 3, "genome", 1, KC_HOSTPACK_ITEM=32)
+    run_case("dense_host_packed", 4, 5_000_000, 4, "dirty", 0)            # production item size, auto threads
+    run_case("dense_host_packed", 6, 100_000, 6, "polyA", 2, KC_HOSTPACK_ITEM=64)   # no invalid byte: no mask words sent
+    for n in (0, 1, 3, 4, 31, 32, 33):
+        run_case("dense_host_packed", 3, n, 5, "dirty", 2, KC_HOSTPACK_ITEM=32)
+
+
 def test_gpu_fasta_parser_on_emulator():
     """f2, device side: kc_import_seqs_device == the host loader on the reference-generated fixtures and
     random files, with 16- and 5-byte tiles (lines, ids and records span tiles; > 1024 tiles in one file)"""

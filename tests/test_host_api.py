@@ -216,3 +216,39 @@ def test_no_gpu_fails_loudly(kmerlib):
     assert L.kc_count_dense(None, None, 0, 3, None) == kmerlib.KC_ERR_INVALID
     assert L.kc_count_per_seq(None, None, None, 0, 3, None) == kmerlib.KC_ERR_INVALID
     assert L.kc_count_sparse(None, None, 0, 21, 0, 0, None) == kmerlib.KC_ERR_INVALID
+    assert L.kc_count_dense_host_packed(None, None, 0, 3, None, 0) == kmerlib.KC_ERR_INVALID
+
+
+def _store_reference(data):
+    """the 2-bit store of include/kmer_b200.h in numpy: packed bytes (first base on top, main.cu:83) + validity bitmap"""
+    n = data.size
+    code = np.full(256, -1, dtype=np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = code[data]
+    bad = c < 0
+    q = np.concatenate([np.where(bad, 0, c).astype(np.uint8), np.zeros((-n) % 4, np.uint8)]).reshape(-1, 4)
+    packed = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+    bits = np.concatenate([bad, np.ones((-n) % 32, dtype=bool)]).reshape(-1, 32)
+    mask = (bits.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+    return packed.astype(np.uint8), mask
+
+
+def test_pack_2bit_host_matches_store_layout(kmerlib):
+    """kc_pack_2bit_host (format conversion on the host cores, no ctx): every byte value, lengths around the
+    32-base word and the 2^20-base item edges, AVX2 and scalar bodies, 1..5 threads"""
+    rng = np.random.default_rng(11)
+    assert kmerlib.lib().kc_host_pack_simd() in (0, 1)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for n in (1, 3, 4, 5, 31, 32, 33, 63, 64, 65, 4096 + 17, (1 << 20) - 1, (1 << 20) + 33, 3 * (1 << 20) + 5):
+        data = acgt[rng.integers(0, 4, n)].copy()
+        dirty = rng.random(n) < 0.02
+        data[dirty] = rng.integers(0, 256, int(dirty.sum())).astype(np.uint8)
+        if n >= 256:
+            data[:256] = np.arange(256, dtype=np.uint8)
+        wp, wm = _store_reference(data)
+        for nthreads in (1, 5, -1, -3):
+            p, m = kmerlib.pack_2bit_host(data, nthreads)
+            assert (p == wp).all() and (m == wm).all(), (n, nthreads)
+    p, m = kmerlib.pack_2bit_host(np.zeros(0, dtype=np.uint8))
+    assert p.size == 0 and m.size == 0

@@ -33,6 +33,7 @@ CASES = [
     "test_partition_wide_records",
     "test_partition_paired_count",
     "test_packed_store",
+    "test_host_packed_count",
     "test_gpu_fasta_parser",
     "test_nccl_range_sharded_radix",
 ]
