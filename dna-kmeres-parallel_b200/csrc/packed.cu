@@ -17,6 +17,7 @@
 #include <sched.h>
 
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -215,12 +216,26 @@ static uint64_t hp_item() {
 #define HP_SLOT_BYTES ((size_t)(HP_SLOT / 4 + HP_SLOT / 8))
 
 int host_threads(int asked) {
+    if (asked <= 0) {  // KC_HOSTPACK_THREADS: measurement aid for the automatic choice
+        static const int env = getenv("KC_HOSTPACK_THREADS") ? atoi(getenv("KC_HOSTPACK_THREADS")) : 0;
+        asked = env;
+    }
     if (asked > 0) return asked > 256 ? 256 : asked;
     int n = 0;
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);
     if (n < 1) n = (int)std::thread::hardware_concurrency();
     if (n < 1) n = 1;
+    // a container may be allowed less CPU time than the cores it can be scheduled on (cgroup v2 cpu.max =
+    // "<quota> <period>" or "max <period>"): threads beyond the quota only get throttled
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        long long quota = 0, period = 0;
+        if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0) {
+            const int q = (int)((quota + period - 1) / period);
+            if (q >= 1 && q < n) n = q;
+        }
+        fclose(f);
+    }
     n -= 1;  // the calling thread drives the copies
     if (n < 1) n = 1;
     return n > 64 ? 64 : n;
@@ -246,9 +261,11 @@ struct HostPackPipe {
             const uint64_t it = next_item.fetch_add(1, std::memory_order_relaxed);
             if (it >= nitems) return;
             const uint64_t slot = it / HP_ITEMS_PER_SLOT;
-            while (slot >= released.load(std::memory_order_acquire) + HP_RING) {
+            for (int spins = 0; slot >= released.load(std::memory_order_acquire) + HP_RING; spins++) {
                 if (stop.load(std::memory_order_relaxed)) return;
-                std::this_thread::yield();
+                // the ring is full = the bus is the limit (the wanted state): a slot takes ~75 us to leave
+                if (spins < 64) std::this_thread::yield();
+                else std::this_thread::sleep_for(std::chrono::microseconds(40));
             }
             if (stop.load(std::memory_order_relaxed)) return;
             uint8_t* base = ring + (size_t)(slot % HP_RING) * HP_SLOT_BYTES;

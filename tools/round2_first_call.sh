@@ -61,3 +61,9 @@ make -s -C tools microbench3 2>/dev/null; timeout 120 tools/microbench3 > $O/r02
 echo "== 4. default bench line (with e2e + cpu baseline)"
 timeout 600 python bench.py > $O/r02_bench_n1.log 2> $O/r02_bench_n1.err; echo "bench rc=$?"; cut -c1-600 $O/r02_bench_n1.log
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_ref.log 2> $O/r02_bench_ref.err; echo "reference arm rc=$?"; cut -c1-300 $O/r02_bench_ref.log
+echo "== 5. host -> GPU through the packed form: packer-thread sweep (the default bench line above already chose between plain and packed)"
+for T in 8 16 32 64 128; do
+  KC_HOSTPACK_THREADS=$T timeout 300 python bench.py --probe --probe-e2e --steps 5 > $O/r02_e2e_packed_t$T.log 2> $O/r02_e2e_packed_t$T.err
+  echo "threads=$T $(cut -c1-200 $O/r02_e2e_packed_t$T.log)"
+done
+nproc; cat /sys/fs/cgroup/cpu.max 2>/dev/null; lscpu | head -20
