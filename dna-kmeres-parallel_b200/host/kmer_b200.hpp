@@ -109,9 +109,14 @@ class Engine {
     }
 
     // aggregate dense table of a host byte buffer (any non-ACGT byte splits windows)
-    std::vector<uint32_t> countDense(const char* h_data, uint64_t nbytes, int k) {
+    // packer_threads < 0: plain copy (1 byte per base over PCIe); >= 0: the host cores pack first
+    // (kc_count_dense_host_packed, <= 0.375 bytes per base over PCIe; 0 = as many threads as the process may use)
+    std::vector<uint32_t> countDense(const char* h_data, uint64_t nbytes, int k, int packer_threads = -1) {
         std::vector<uint32_t> table((size_t)kc_num_kmers(k));
-        check(kc_count_dense_host(ctx_, h_data, nbytes, k, table.data()), ctx_);
+        if (packer_threads < 0)
+            check(kc_count_dense_host(ctx_, h_data, nbytes, k, table.data()), ctx_);
+        else
+            check(kc_count_dense_host_packed(ctx_, h_data, nbytes, k, table.data(), packer_threads), ctx_);
         return table;
     }
 
