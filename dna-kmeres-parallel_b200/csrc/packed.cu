@@ -416,7 +416,9 @@ int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
                     released++;
                     pipe.released.store(released, std::memory_order_release);
                     progress = true;
-                } else if (ce != cudaErrorNotReady) {
+                } else if (ce == cudaErrorNotReady) {
+                    cudaGetLastError();  // "not ready" is recorded as the thread's last error: the next launch check must not see it
+                } else {
                     rc = kc_set_error(ctx, KC_ERR_CUDA, "host staging failed: %s", cudaGetErrorString(ce));
                 }
             }

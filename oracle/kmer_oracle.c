@@ -11,7 +11,7 @@
  *   (a) the reference's OWN permutation() + permutationsCountAll() +
  *       importSeqs() + sequentialKmerCount2(), compiled unmodified from
  *       /root/reference by oracle/build_ref.sh into oracle/_ref/ (k = 3..6), and
- *   (b) the golden vectors of SURVEY.md §8c / tests/golden/*.json that were
+ *   (b) the golden vectors of SURVEY.md §8c / tests/golden/ (JSON fixtures) that were
  *       generated from (a) by tests/golden/make_golden.py.
  * For k > 6 (the reference cannot be compiled: kernels.h:21 overflows constant
  * memory) the same code path is used with a larger k; nothing else changes.
