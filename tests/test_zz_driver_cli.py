@@ -55,7 +55,8 @@ def test_driver_gpu_parse_matches_host_parse(golden, tmp_path):
     outs = []
     for flag in ([], ["--gpu-parse"]):
         out, sums = tmp_path / ("r%d.csv" % len(flag)), tmp_path / ("s%d.txt" % len(flag))
-        r = subprocess.run([EXE, str(fasta), "-k", "4", "--out", str(out), "--sums", str(sums)] + flag, capture_output=True, text=True)
+        r = subprocess.run([EXE, str(fasta), "-k", "4", "--out", str(out), "--sums", str(sums)] + flag, capture_output=True, text=True,
+                           timeout=180)  # a never-run kernel may hang: bounded, and the run is its own process
         assert r.returncode == 0, r.stderr
         outs.append((out.read_text(), sums.read_text()))
     assert outs[0] == outs[1]
