@@ -290,6 +290,12 @@ PROBE_CANDIDATES = {12: [4, 5, 6, 7], 8: [3]}
 PROBE_SCRIPT = os.path.abspath(__file__)  # tests put a stand-in here
 
 
+def probe_cache_path(args):
+    import kmerb200
+    key = "%s_%d_%d" % (args.workload, args.length, int(os.path.getmtime(kmerb200.LIB_PATH)))
+    return os.path.join("/tmp", "kc_bench_probe_%s.json" % key)
+
+
 def probe_variants(args, k, local):
     import subprocess
     cands = PROBE_CANDIDATES.get(k, [])
@@ -337,9 +343,7 @@ def probe_variants(args, k, local):
     # (keyed by workload, length and the library's build time) so that only the first run pays for them.
     cache = None
     try:
-        import kmerb200
-        key = "%s_%d_%d" % (args.workload, args.length, int(os.path.getmtime(kmerb200.LIB_PATH)))
-        cache = os.path.join("/tmp", "kc_bench_probe_%s.json" % key)
+        cache = probe_cache_path(args)
         if os.path.exists(cache) and time.time() - os.path.getmtime(cache) < 3600:
             with open(cache) as f:
                 c = json.load(f)
@@ -594,6 +598,12 @@ def main():
         sys.stderr.write("bench: variant %d did not reproduce the shipped table in the timed run; timing the shipped path\n" % args.algo)
         if probe_report is not None:
             probe_report["rejected_in_timed_run"] = args.algo
+            if rank == 0:  # later runs on this box must not pick it again
+                try:
+                    with open(probe_cache_path(args), "w") as f:
+                        json.dump({"best": 0, "report": probe_report}, f)
+                except Exception:
+                    pass
         args.algo = 0
         res = timed()
     ms_step, value, launches, clocks, checksum, graph, table_fp = (res["ms_step"], res["value"], res["launches"], res["clocks"],
