@@ -724,6 +724,48 @@ def main():
                                "packed_probe": pk}
                 except Exception as ex:
                     pk["in_process_error"] = str(ex)[:200]
+        # N > 1, opt-in (KC_BENCH_E2E_PACKED_N=1) until a B200 has run it: every rank feeds its shard through the packed
+        # path into its device table, then the same NCCL reduce + D2H; the ranks share the host's cores.
+        if world > 1 and os.environ.get("KC_BENCH_E2E_PACKED_N"):
+            nth = max(1, ((os.cpu_count() or 2) - world) // world)
+
+            def packed_step():
+                ctx.count_dense_host_packed_dev(host, k, table, nthreads=nth)  # all windows of this rank's bytes = its shard
+                dist.reduce(table, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    h_table.copy_(table, non_blocking=True)
+                torch.cuda.synchronize()
+            ok = 1
+            try:
+                packed_step()
+                if rank == 0 and fingerprint(table) != table_fp:
+                    ok = 0
+            except Exception as ex:
+                sys.stderr.write("bench: packed e2e failed on rank %d: %s\n" % (rank, ex))
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(n_e2e):
+                    packed_step()
+                barrier()
+                dtp = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+                dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+                sent = torch.tensor([ctx.last_h2d_bytes], dtype=torch.int64, device=dev)
+                dist.all_reduce(sent, op=dist.ReduceOp.SUM)
+                plain = {"api": e2e["api"], "value": e2e["value"], "ms_per_step": e2e["ms_per_step"],
+                         "h2d_bytes_per_step": e2e["h2d_bytes_per_step"]}
+                if float(dtp.item()) < float(dt.item()):
+                    e2e = {"value": L / float(dtp.item()), "unit": "bases/s", "h2d_bytes_per_step": int(sent.item()),
+                           "d2h_bytes_per_step": 4 * nk, "ms_per_step": float(dtp.item()) * 1e3, "steps": n_e2e,
+                           "api": "kc_count_dense_host_packed_dev (%d packer threads per rank) + NCCL reduce + D2H" % nth,
+                           "plain": plain}
+                else:
+                    e2e["packed"] = {"ms_per_step": float(dtp.item()) * 1e3, "threads_per_rank": nth}
+            else:
+                e2e["packed"] = {"ok": False}
         del host
 
     # ---- CPU baseline: the oracle port, 1 thread, bounded sample ---------------

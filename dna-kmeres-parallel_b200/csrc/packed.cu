@@ -312,10 +312,15 @@ int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint3
     return KC_OK;
 }
 
-int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table, int nthreads) {
+}  // extern "C"
+
+// h_table != NULL: the table ends in host memory (d_user NULL);  d_user != NULL: it is counted into the caller's
+// device table (overwritten) and stays there
+static int host_packed_count(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table, uint32_t* d_user,
+                             int nthreads) {
     if (!ctx) return KC_ERR_INVALID;
     if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
-    if (!h_table || (!h_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
+    if ((!h_table && !d_user) || (!h_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     DeviceGuard dg(ctx->device);
     const size_t table_bytes = sizeof(uint32_t) << (2 * k);
     // device image: table | ASCII (rounded up to 256 B) | packed | mask
@@ -324,7 +329,7 @@ int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
     const size_t mask_bytes = (size_t)((nbytes + 31) / 32 * 4);
     int rc = kc_scratch2_reserve(ctx, table_bytes + ascii_bytes + packed_bytes + mask_bytes + 256);
     if (rc) return rc;
-    uint32_t* d_table = (uint32_t*)ctx->scratch2;
+    uint32_t* d_table = d_user ? d_user : (uint32_t*)ctx->scratch2;
     char* d_ascii = (char*)ctx->scratch2 + table_bytes;
     uint8_t* d_packed = (uint8_t*)d_ascii + ascii_bytes;
     uint32_t* d_mask = (uint32_t*)(d_packed + packed_bytes);
@@ -432,9 +437,21 @@ int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
         if (rc) return rc;
         ctx->last_h2d_bytes = h2d;
     }
-    KC_CUDA(ctx, cudaMemcpyAsync(h_table, d_table, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_table) KC_CUDA(ctx, cudaMemcpyAsync(h_table, d_table, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KC_OK;
+}
+
+extern "C" {
+
+int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table, int nthreads) {
+    if (ctx && !h_table) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
+    return host_packed_count(ctx, h_data, nbytes, k, h_table, nullptr, nthreads);
+}
+
+int kc_count_dense_host_packed_dev(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* d_table, int nthreads) {
+    if (ctx && !d_table) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
+    return host_packed_count(ctx, h_data, nbytes, k, nullptr, d_table, nthreads);
 }
 
 }  // extern "C"

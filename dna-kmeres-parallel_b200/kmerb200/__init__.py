@@ -102,6 +102,7 @@ def lib():
         "kc_pack_2bit_host": (i32, [vp, u64, vp, vp, i32]),
         "kc_host_pack_simd": (i32, []),
         "kc_count_dense_host_packed": (i32, [vp, vp, u64, i32, vp, i32]),
+        "kc_count_dense_host_packed_dev": (i32, [vp, vp, u64, i32, vp, i32]),
         "kc_sparse_radix_plan": (i32, [vp, u64, i32, C.c_uint32, vp]),
         "kc_sparse_radix_scatter": (i32, [vp, vp, u64, vp, vp, vp]),
         "kc_sparse_radix_count": (i32, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
@@ -427,6 +428,12 @@ class Context:
             h_table = np.empty(num_kmers(k), dtype=np.uint32)
         self._check(lib().kc_count_dense_host_packed(self._h, _ptr(h_data), n, k, _ptr(h_table), nthreads))
         return h_table
+
+    def count_dense_host_packed_dev(self, h_data, k, d_table, nthreads=0):
+        """count_dense_host_packed into a device table (overwritten), synchronous"""
+        n = h_data.numel() if hasattr(h_data, "numel") else h_data.size
+        self._check(lib().kc_count_dense_host_packed_dev(self._h, _ptr(h_data), n, k, _ptr(d_table), nthreads))
+        return d_table
 
     def count_per_seq(self, d_data, d_offsets, num_seqs, k, sums=None, stream=None, sync=True):
         torch = self._torch()

@@ -303,6 +303,10 @@ KC_API int kc_host_pack_simd(void);
  * packer threads (0 = cores available to the process - 1, at most 64).                               */
 KC_API int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k,
                                       uint32_t* h_table, int nthreads);
+/* the same, counted into the caller's DEVICE table (overwritten; synchronous) — for callers that go on
+ * with the table on the GPU: the multi-GPU reduce of a rank's shard, the distance step                */
+KC_API int kc_count_dense_host_packed_dev(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k,
+                                          uint32_t* d_table, int nthreads);
 
 /* ------------------------------------------------------------------ */
 /* Count table dump.  Byte-identical to the (commented-out) dump at    */

@@ -85,6 +85,7 @@ def lib():
         L.kc_ctx_last_h2d_bytes.argtypes = [C.c_void_p]
         L.kc_pack_2bit_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         L.kc_count_dense_host_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
+        L.kc_count_dense_host_packed_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
         L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
         L.kc_sparse_radix_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -382,6 +383,10 @@ def case_dense_host_packed(args):
                 if not valid[b:e].all() or (e - b) % 32:
                     expect += (e - b + 31) // 32 * 4
             assert sent == expect, (sent, expect)
+    t = ctx.alloc(4 << (2 * k))   # the device-table variant overwrites whatever the table held
+    ctx.check(ctx.L.kc_memset_d(ctx.h, t, 0x5A, 4 << (2 * k)))
+    ctx.check(ctx.L.kc_count_dense_host_packed_dev(ctx.h, data.ctypes.data if n else None, n, k, t, nthreads))
+    assert (ctx.download(t, 4 << (2 * k), np.uint32) == want).all(), "kc_count_dense_host_packed_dev differs"
     ctx.close()
     print("ok dense_host_packed", *args)
 

@@ -16,3 +16,13 @@ for A in hash radix; do
   timeout 600 $R --master-port 29742 bench.py --gpus $N --workload config4 --reads 20000000 --sparse-algo $A --steps 1 --warmup 1 > $O/r02_c4_n${N}_$A.log 2> $O/r02_c4_n${N}_$A.err
   echo "config4 N=$N $A rc=$?"; cut -c1-400 $O/r02_c4_n${N}_$A.log; tail -2 $O/r02_c4_n${N}_$A.err
 done
+echo "== 4. dense bench at N=$N with the packed host path in e2e (opt-in until seen green)"
+KC_BENCH_E2E_PACKED_N=1 timeout 300 $R --master-port 29743 bench.py --gpus $N --steps 20 --warmup 3 > $O/r02_dense_n${N}_packed.log 2> $O/r02_dense_n${N}_packed.err; echo "rc=$?"
+python - <<PY
+import json
+try:
+    d = json.load(open("$O/r02_dense_n${N}_packed.log"))
+    print("e2e:", json.dumps(d["e2e"])[:500])
+except Exception as e:
+    print("no line:", e)
+PY
