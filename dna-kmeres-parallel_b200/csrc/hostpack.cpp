@@ -7,7 +7,7 @@
 //
 // Why it exists: counting from HOST memory is bound by PCIe (1 byte per base, ~55 GB/s), not by the
 // GPU (770 Gbases/s).  Packing on the host cores first sends 0.375 bytes per base; the GPU unpacks at
-// HBM speed.  Plain g++ (no CUDA): AVX2 body chosen at run time, scalar body otherwise and for tails.
+// HBM speed.  Plain g++ (no CUDA): AVX-512BW or AVX2 body chosen at run time, scalar body otherwise and for tails.
 #include <stdint.h>
 #include <string.h>
 
@@ -106,15 +106,40 @@ __attribute__((target("avx2"))) uint32_t pack_avx2(const uint8_t* s, uint64_t nw
     }
     return any;
 }
+
+// 64 bases per iteration, the same two nibble-indexed shuffles: the validity compare lands in a mask register
+// (= the bitmap word pair, inverted), the code shuffle is zero-masked by it, and vpmovdb gathers the 16 result
+// bytes in order.
+__attribute__((target("avx512f,avx512bw"))) uint32_t pack_avx512(const uint8_t* s, uint64_t npairs, uint8_t* packed, uint32_t* mask) {
+    const __m512i letter = _mm512_broadcast_i32x4(_mm_setr_epi8((char)0xFF, 0x41, (char)0xFF, 0x43, 0x54, (char)0xFF, (char)0xFF, 0x47,
+                                                                (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF,
+                                                                (char)0xFF, (char)0xFF));
+    const __m512i codes = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 0, 0, 1, 3, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i m1 = _mm512_set1_epi16(0x0104);
+    const __m512i m2 = _mm512_set1_epi32(0x00010010);
+    uint64_t any = 0;
+    for (uint64_t w = 0; w < npairs; w++) {
+        const __m512i x = _mm512_loadu_si512(s + (w << 6));
+        const __mmask64 valid = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(letter, x), x);
+        const __m512i code = _mm512_maskz_shuffle_epi8(valid, codes, x);
+        const __m512i u = _mm512_madd_epi16(_mm512_maddubs_epi16(code, m1), m2);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(packed + (w << 4)), _mm512_cvtepi32_epi8(u));
+        const uint64_t bad = ~(uint64_t)valid;
+        memcpy(mask + (w << 1), &bad, 8);
+        any |= bad;
+    }
+    return (uint32_t)(any | (any >> 32));
+}
 #endif
 
 }  // namespace
 
 extern "C" {
 
-// 1 = the AVX2 body is used on this host
+// 0 = scalar body, 1 = AVX2, 2 = AVX-512BW on this host
 __attribute__((visibility("default"))) int kc_host_pack_simd(void) {
 #if defined(__x86_64__)
+    if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) return 2;
     return __builtin_cpu_supports("avx2") ? 1 : 0;
 #else
     return 0;
@@ -123,17 +148,23 @@ __attribute__((visibility("default"))) int kc_host_pack_simd(void) {
 
 // One range, one thread: bases data[0, n) -> packed[0, (n+3)/4) and badmask[0, (n+31)/32).  A caller that
 // splits a sequence cuts it at multiples of 32 bases (whole mask words, whole packed bytes).
-// force_scalar != 0 takes the scalar body (tests compare the two).  Returns the OR of the mask words (0 = all valid).
+// force_scalar: 0 = the best body this host has (AVX-512BW, AVX2, scalar), 1 = scalar, 2 = AVX2 (tests compare them).  Returns the OR of the mask words (0 = all valid).
 __attribute__((visibility("hidden"))) uint32_t kc_host_pack_range(const char* data, uint64_t n, uint8_t* packed, uint32_t* badmask,
                                                                 int force_scalar) {
     const uint8_t* s = reinterpret_cast<const uint8_t*>(data);
     uint64_t done = 0;
     uint32_t any = 0;
 #if defined(__x86_64__)
-    if (!force_scalar && __builtin_cpu_supports("avx2")) {
-        const uint64_t nwords = n >> 5;
-        any = pack_avx2(s, nwords, packed, badmask);
-        done = nwords << 5;
+    // force_scalar: 0 = best body of this host, 1 = scalar, 2 = AVX2 even where AVX-512 exists (tests)
+    if (force_scalar != 1 && force_scalar != 2 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) {
+        const uint64_t npairs = n >> 6;
+        any = pack_avx512(s, npairs, packed, badmask);
+        done = npairs << 6;
+    }
+    if (force_scalar != 1 && __builtin_cpu_supports("avx2")) {
+        const uint64_t nwords = (n - done) >> 5;
+        any |= pack_avx2(s + done, nwords, packed + (done >> 2), badmask + (done >> 5));
+        done += nwords << 5;
     }
 #endif
     if (done < n) any |= pack_scalar(s + done, n - done, packed + (done >> 2), badmask + (done >> 5));

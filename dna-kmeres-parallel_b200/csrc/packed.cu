@@ -284,32 +284,35 @@ struct HostPackPipe {
 
 extern "C" {
 
-int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask, int nthreads) {
+int kc_pack_2bit_host_body(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask, int nthreads, int body) {
     if (nbytes == 0) return KC_OK;
     if (!h_data || !h_packed || !h_badmask) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_pack_2bit_host: null pointer");
-    const bool scalar = nthreads < 0;  // test aid: -T = T threads, scalar body
-    if (scalar) nthreads = -nthreads;
+    if (body < 0 || body > 2) return kc_set_error(nullptr, KC_ERR_INVALID, "kc_pack_2bit_host_body: body must be 0, 1 or 2");
     const uint64_t nitems = (nbytes + HP_ITEM - 1) / HP_ITEM;
     int T = host_threads(nthreads);
     if ((uint64_t)T > nitems) T = (int)nitems;
     std::atomic<uint64_t> next{0};
-    auto body = [&]() {
+    auto work = [&]() {
         for (;;) {
             const uint64_t it = next.fetch_add(1, std::memory_order_relaxed);
             if (it >= nitems) return;
             const uint64_t b = it * HP_ITEM;
             const uint64_t len = nbytes - b < HP_ITEM ? nbytes - b : HP_ITEM;
-            kc_host_pack_range(h_data + b, len, (uint8_t*)h_packed + b / 4, h_badmask + b / 32, scalar ? 1 : 0);
+            kc_host_pack_range(h_data + b, len, (uint8_t*)h_packed + b / 4, h_badmask + b / 32, body);
         }
     };
     std::vector<std::thread> th;
     try {
-        for (int t = 1; t < T; t++) th.emplace_back(body);
+        for (int t = 1; t < T; t++) th.emplace_back(work);
     } catch (...) {  // fewer threads than asked for: the ones that run (and this one) do all items
     }
-    body();
+    work();
     for (auto& t : th) t.join();
     return KC_OK;
+}
+
+int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask, int nthreads) {
+    return kc_pack_2bit_host_body(h_data, nbytes, h_packed, h_badmask, nthreads, 0);
 }
 
 }  // extern "C"

@@ -100,6 +100,7 @@ def lib():
         "kc_unpack_2bit": (i32, [vp, vp, vp, u64, vp, vp]),
         "kc_count_dense_packed": (i32, [vp, vp, vp, u64, i32, vp]),
         "kc_pack_2bit_host": (i32, [vp, u64, vp, vp, i32]),
+        "kc_pack_2bit_host_body": (i32, [vp, u64, vp, vp, i32, i32]),
         "kc_host_pack_simd": (i32, []),
         "kc_count_dense_host_packed": (i32, [vp, vp, u64, i32, vp, i32]),
         "kc_count_dense_host_packed_dev": (i32, [vp, vp, u64, i32, vp, i32]),
@@ -203,14 +204,14 @@ def dump_distances(path, dist):
     _check0(lib().kc_dump_distances(path.encode() if path else None, dist.ctypes.data, dist.size))
 
 
-def pack_2bit_host(h_data, nthreads=0):
+def pack_2bit_host(h_data, nthreads=0, body=0):
     """host-side packer of the 2-bit store (numpy uint8 in) -> (packed uint8[(n+3)/4], badmask uint32[(n+31)/32]);
-    nthreads < 0: |nthreads| threads with the scalar body (tests)"""
+    body: 0 = the best loop body of this host, 1 = scalar, 2 = AVX2 (tests compare them)"""
     a = np.ascontiguousarray(h_data, dtype=np.uint8)
     n = a.size
     packed = np.zeros(int(lib().kc_packed_bytes(n)), dtype=np.uint8)
     mask = np.zeros(int(lib().kc_badmask_bytes(n)) // 4, dtype=np.uint32)
-    _check0(lib().kc_pack_2bit_host(_ptr(a), n, _ptr(packed), _ptr(mask), nthreads))
+    _check0(lib().kc_pack_2bit_host_body(_ptr(a), n, _ptr(packed), _ptr(mask), nthreads, body))
     return packed, mask
 
 

@@ -292,10 +292,13 @@ KC_API int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32
                                  uint64_t nbases, int k, uint32_t* d_table);
 /* The same conversion on the HOST cores (format conversion only; counting has no CPU path): h_data ->
  * h_packed[(n+3)/4], h_badmask[(n+31)/32]; bit-identical to kc_pack_2bit's output.  nthreads 0 = one per
- * core this process may run on (at most 64).  AVX2 body when the host has it (kc_host_pack_simd() == 1). */
+ * core this process may run on (at most 64).  AVX-512BW or AVX2 body when the host has it (kc_host_pack_simd()). */
 KC_API int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask,
                              int nthreads);
-KC_API int kc_host_pack_simd(void);
+KC_API int kc_host_pack_simd(void);   /* body kc_pack_2bit_host uses here: 0 scalar, 1 AVX2, 2 AVX-512BW */
+/* diagnostic / test aid: the same with a chosen loop body (0 = best available, 1 = scalar, 2 = AVX2 if present) */
+KC_API int kc_pack_2bit_host_body(const char* h_data, uint64_t nbytes, void* h_packed,
+                                  uint32_t* h_badmask, int nthreads, int body);
 /* kc_count_dense_host (main.cu:287-299: the reference's count step starts from host/managed memory)
  * for hosts with cores to spare: packer threads turn the ASCII into the store's layout slot by slot
  * (pinned ring), the slots cross PCIe at 0.375 bytes per base instead of 1, the GPU unpacks them at HBM

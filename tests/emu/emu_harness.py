@@ -83,7 +83,7 @@ def lib():
         L.kc_count_dense_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.kc_ctx_last_h2d_bytes.restype = C.c_uint64
         L.kc_ctx_last_h2d_bytes.argtypes = [C.c_void_p]
-        L.kc_pack_2bit_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.kc_pack_2bit_host_body.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.kc_count_dense_host_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
         L.kc_count_dense_host_packed_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
         L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
@@ -421,12 +421,12 @@ def case_packed(args):
     bits = np.concatenate([bad, np.ones((-n) % 32, dtype=bool)]).reshape(-1, 32)   # bases past the end count as invalid
     want_mask = (bits.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
     assert (mask == want_mask).all(), "validity bitmap differs"
-    # the host-side packer (hostpack.cpp: AVX2 body, scalar body, several threads) writes the same store
-    for nthreads in (1, 3, -1, -2):
+    # the host-side packer (hostpack.cpp: AVX-512 / AVX2 / scalar bodies, several threads) writes the same store
+    for nthreads, body in ((1, 0), (3, 0), (1, 1), (2, 2)):
         hp = np.full(pb, 0xEE, dtype=np.uint8)
         hm = np.full(mb // 4, 0xEEEEEEEE, dtype=np.uint32)
-        ctx.check(L.kc_pack_2bit_host(data.ctypes.data, n, hp.ctypes.data, hm.ctypes.data, nthreads))
-        assert (hp == packed).all() and (hm == mask).all(), "host packer differs from pack_kernel (nthreads=%d)" % nthreads
+        ctx.check(L.kc_pack_2bit_host_body(data.ctypes.data, n, hp.ctypes.data, hm.ctypes.data, nthreads, body))
+        assert (hp == packed).all() and (hm == mask).all(), "host packer differs from pack_kernel (threads %d, body %d)" % (nthreads, body)
     d_o = ctx.alloc(n)
     ctx.check(L.kc_unpack_2bit(ctx.h, d_p, d_m, n, d_o, None))
     back = ctx.download(d_o, n, np.uint8)

@@ -236,9 +236,9 @@ def _store_reference(data):
 
 def test_pack_2bit_host_matches_store_layout(kmerlib):
     """kc_pack_2bit_host (format conversion on the host cores, no ctx): every byte value, lengths around the
-    32-base word and the 2^20-base item edges, AVX2 and scalar bodies, 1..5 threads"""
+    32-base word and the 2^20-base item edges, AVX-512 / AVX2 / scalar bodies, 1..5 threads"""
     rng = np.random.default_rng(11)
-    assert kmerlib.lib().kc_host_pack_simd() in (0, 1)
+    assert kmerlib.lib().kc_host_pack_simd() in (0, 1, 2)
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
     for n in (1, 3, 4, 5, 31, 32, 33, 63, 64, 65, 4096 + 17, (1 << 20) - 1, (1 << 20) + 33, 3 * (1 << 20) + 5):
         data = acgt[rng.integers(0, 4, n)].copy()
@@ -247,8 +247,8 @@ def test_pack_2bit_host_matches_store_layout(kmerlib):
         if n >= 256:
             data[:256] = np.arange(256, dtype=np.uint8)
         wp, wm = _store_reference(data)
-        for nthreads in (1, 5, -1, -3):
-            p, m = kmerlib.pack_2bit_host(data, nthreads)
-            assert (p == wp).all() and (m == wm).all(), (n, nthreads)
+        for nthreads, body in ((1, 0), (5, 0), (1, 1), (3, 1), (1, 2), (2, 2)):
+            p, m = kmerlib.pack_2bit_host(data, nthreads, body)
+            assert (p == wp).all() and (m == wm).all(), (n, nthreads, body)
     p, m = kmerlib.pack_2bit_host(np.zeros(0, dtype=np.uint8))
     assert p.size == 0 and m.size == 0
