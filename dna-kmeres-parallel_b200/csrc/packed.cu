@@ -181,39 +181,97 @@ int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32_t* d_b
 // ---------------------------------------------------------------------------------------------------
 // Counting from HOST memory through the packed form.  kc_count_dense_host moves 1 byte per base over
 // PCIe and is bound by it (3.1 GB: 57 ms, while the GPU counts them in 4 ms).  Here the host cores turn
-// the ASCII into the store's layout first (0.375 bytes per base), the GPU turns it back at HBM speed:
+// the ASCII into the store's layout first, the GPU turns it back at HBM speed:
 //
-//   packer threads --items--> ring of pinned slots --H2D (copy stream)--> d_packed / d_mask
-//                                                   --event--> unpack_kernel --> d_ascii --> dense path
+//   packer threads --items--> ring of pinned slots --H2D (copy stream)--> d_packed, mask stage / d_mask
+//                                  --event--> mask_expand_kernel, unpack_kernel --> d_ascii --> dense path
 //
 // * item = 2^20 bases, claimed from one atomic counter (in order, so the ring fills front to back);
-//   slot = 16 items = 4 MiB packed + 2 MiB mask; the ring holds 8 slots (48 MiB pinned, kept in the ctx).
+//   slot = 16 items = 4 MiB packed + 2 MiB mask; the ring holds 8 slots (pinned, kept in the ctx).
+// * the validity bitmap crosses the bus SPARSE: a packer notes which 4 KiB blocks (32 K bases) of its item's
+//   bitmap hold a set bit; the thread that finishes a slot moves the dirty blocks to the front of the slot's
+//   mask area, and the slot sends [header: dirty-block map][dirty blocks] in one copy to a stage area on the
+//   device, where mask_expand_kernel rebuilds the bitmap (clean blocks are zeroed there).  A slot with more
+//   than a quarter of its blocks dirty sends its bitmap as it is.  A genome with an N every ~300 K bases costs
+//   0.25 + ~0.02 bytes per base on the bus instead of 0.375.
 // * a packer may write slot s only when slot s - RING has left the host (`released`, published by the
 //   calling thread after cudaEventQuery of that slot's copy); the calling thread issues the copies of slot
-//   s once its 16 items are done.  No thread ever blocks inside the CUDA runtime.
-// * every COUNT_SLOTS slots (2^28 bases) the compute stream waits for the copies so far, unpacks those
-//   bases into the ASCII image and counts the windows that END inside it, exactly like kc_count_dense_host.
+//   s once it is finished.  No thread ever blocks inside the CUDA runtime.
+// * every COUNT_SLOTS slots (2^28 bases) the compute stream waits for the copies so far, rebuilds bitmap and
+//   ASCII image of those bases and counts the windows that END inside it, exactly like kc_count_dense_host.
 // The result is kc_count_dense's: unpacking restores every valid byte and turns every invalid one into
 // 'N', which resets a window like the byte it replaces.
 namespace {
 
 constexpr int HP_ITEMS_PER_SLOT = 16;
 constexpr int HP_RING = 8;
-constexpr int HP_COUNT_SLOTS = 16;             // slots per unpack + count call
-// bases per packer item, a multiple of 32 (whole mask words).  KC_HOSTPACK_ITEM is a test aid: small items
-// drive a small input through many slots, ring wrap-arounds and count calls.
-static uint64_t hp_item() {
-    static const uint64_t v = [] {
+constexpr int HP_COUNT_SLOTS = 16;             // slots per expand + unpack + count call
+constexpr int HP_HDR_WORDS = 64;               // slot header: [0,16) dirty-block map per item, [16] mode, [17] dirty blocks
+constexpr uint32_t HP_MODE_SPARSE = 0, HP_MODE_FULL = 1;
+
+// Shape of the pipeline.  item = bases per packer item; a bitmap block = 1/32 of an item's bitmap (at least one
+// word).  KC_HOSTPACK_ITEM is a test aid: small items drive a small input through many slots, ring wrap-arounds
+// and count calls (values <= 1024 bases are rounded up to a multiple of 32, larger ones to a multiple of 1024).
+struct HpShape {
+    uint64_t item;            // bases per item
+    uint32_t block_words;     // bitmap words per block
+    uint32_t bpi;             // blocks per item (<= 32)
+    uint64_t slot;            // bases per slot
+    uint32_t blocks_per_slot;
+    uint32_t max_sparse;      // a slot with more dirty blocks goes as a full bitmap
+    size_t off_hdr, off_mask, slot_bytes;   // ring slot layout: [packed][header][bitmap]
+    size_t stage_stride;      // device stage per slot: header + max_sparse blocks
+};
+static const HpShape& hp_shape() {
+    static const HpShape v = [] {
         const char* e = getenv("KC_HOSTPACK_ITEM");
         uint64_t x = e ? strtoull(e, nullptr, 0) : 0;
-        x = (x + 31) / 32 * 32;
-        return x ? x : (1ull << 20);
+        if (!x) x = 1ull << 20;
+        x = x <= 1024 ? (x + 31) / 32 * 32 : (x + 1023) / 1024 * 1024;
+        HpShape h;
+        h.item = x;
+        const uint64_t item_words = x / 32;
+        h.block_words = item_words <= 32 ? 1u : (uint32_t)(item_words / 32);
+        h.bpi = (uint32_t)(item_words / h.block_words);
+        h.slot = x * HP_ITEMS_PER_SLOT;
+        h.blocks_per_slot = h.bpi * HP_ITEMS_PER_SLOT;
+        h.max_sparse = h.blocks_per_slot / 4;
+        h.off_hdr = (size_t)(h.slot / 4);
+        h.off_mask = h.off_hdr + HP_HDR_WORDS * 4;
+        h.slot_bytes = h.off_mask + (size_t)(h.slot / 8);
+        h.stage_stride = (HP_HDR_WORDS + (size_t)h.max_sparse * h.block_words) * 4;
+        return h;
     }();
     return v;
 }
-#define HP_ITEM hp_item()
-#define HP_SLOT (HP_ITEM * HP_ITEMS_PER_SLOT)
-#define HP_SLOT_BYTES ((size_t)(HP_SLOT / 4 + HP_SLOT / 8))
+#define HP_ITEM (hp_shape().item)
+
+// Rebuild the bitmap words of the slots [slot0, slot0 + gridDim.x) from their stage records: CTA (s, j) does
+// item j of slot s.  A FULL slot's bitmap was copied to its place directly.
+__global__ void __launch_bounds__(256)
+mask_expand_kernel(const uint32_t* __restrict__ stage, uint64_t stage_stride_words, uint64_t slot0, uint32_t block_words, uint32_t bpi,
+                   uint64_t total_words, uint32_t* __restrict__ d_mask) {
+    const uint64_t slot = slot0 + blockIdx.x;
+    const uint32_t* hdr = stage + slot * stage_stride_words;
+    if (hdr[16] != HP_MODE_SPARSE) return;
+    const uint32_t j = blockIdx.y;
+    uint32_t before = 0;  // dirty blocks of the items in front of this one
+    for (uint32_t q = 0; q < j; q++) before += __popc(hdr[q]);
+    const uint32_t map = hdr[j];
+    const uint32_t* blocks = hdr + HP_HDR_WORDS;
+    const uint64_t item_words = (uint64_t)block_words * bpi;
+    const uint64_t w0 = (slot * HP_ITEMS_PER_SLOT + j) * item_words;  // first bitmap word of the item
+    for (uint64_t w = threadIdx.x; w < item_words; w += blockDim.x) {
+        if (w0 + w >= total_words) break;
+        const uint32_t blk = (uint32_t)w / block_words, off = (uint32_t)w % block_words;  // w < 2^15 words per item
+        uint32_t v = 0;
+        if ((map >> blk) & 1u) {
+            const uint32_t rank = before + __popc(map & ((1u << blk) - 1u));
+            v = blocks[(uint64_t)rank * block_words + off];
+        }
+        d_mask[w0 + w] = v;
+    }
+}
 
 int host_threads(int asked) {
     if (asked <= 0) {  // KC_HOSTPACK_THREADS: measurement aid for the automatic choice
@@ -242,6 +300,7 @@ int host_threads(int asked) {
 }
 
 struct HostPackPipe {
+    const HpShape& S = hp_shape();
     const char* h_data;
     uint64_t n;
     uint64_t nitems, nslots;
@@ -249,12 +308,32 @@ struct HostPackPipe {
     std::atomic<uint64_t> next_item{0};
     std::atomic<uint64_t> released{0};  // slots [0, released) have left the host
     std::atomic<int> stop{0};
-    std::atomic<int> done[HP_RING];
-    std::atomic<uint32_t> anybad[HP_RING];  // OR of the slot's mask words: 0 = the mask need not cross PCIe
+    std::atomic<int> done[HP_RING];     // items packed
+    std::atomic<int> ready[HP_RING];    // 1 = header written, dirty blocks compacted: the slot may be copied
 
     uint64_t items_of(uint64_t slot) const {
         const uint64_t first = slot * HP_ITEMS_PER_SLOT;
         return nitems - first < (uint64_t)HP_ITEMS_PER_SLOT ? nitems - first : (uint64_t)HP_ITEMS_PER_SLOT;
+    }
+    // the thread that packed the last item of a slot: count the dirty blocks, move them to the front
+    void finish_slot(uint8_t* base, uint64_t items) {
+        uint32_t* hdr = reinterpret_cast<uint32_t*>(base + S.off_hdr);
+        uint32_t* mask = reinterpret_cast<uint32_t*>(base + S.off_mask);
+        for (uint64_t j = items; j < (uint64_t)HP_ITEMS_PER_SLOT; j++) hdr[j] = 0;  // the last slot: no such items (the ring slot may hold an older map)
+        uint32_t dirty = 0;
+        for (int j = 0; j < HP_ITEMS_PER_SLOT; j++) dirty += (uint32_t)__builtin_popcount(hdr[j]);
+        hdr[17] = dirty;
+        if (dirty > S.max_sparse) {
+            hdr[16] = HP_MODE_FULL;
+            return;
+        }
+        hdr[16] = HP_MODE_SPARSE;
+        uint32_t outb = 0;
+        for (uint32_t blk = 0; blk < S.blocks_per_slot && outb < dirty; blk++) {
+            if (!((hdr[blk / S.bpi] >> (blk % S.bpi)) & 1u)) continue;
+            if (outb != blk) memmove(mask + (size_t)outb * S.block_words, mask + (size_t)blk * S.block_words, (size_t)S.block_words * 4);
+            outb++;
+        }
     }
     void work() {
         for (;;) {
@@ -268,14 +347,26 @@ struct HostPackPipe {
                 else std::this_thread::sleep_for(std::chrono::microseconds(40));
             }
             if (stop.load(std::memory_order_relaxed)) return;
-            uint8_t* base = ring + (size_t)(slot % HP_RING) * HP_SLOT_BYTES;
+            const int r = (int)(slot % HP_RING);
+            uint8_t* base = ring + (size_t)r * S.slot_bytes;
             const uint64_t j = it % HP_ITEMS_PER_SLOT;
-            const uint64_t b = it * HP_ITEM;
-            const uint64_t len = n - b < HP_ITEM ? n - b : HP_ITEM;
-            const uint32_t any = kc_host_pack_range(h_data + b, len, base + j * (HP_ITEM / 4),
-                                                    reinterpret_cast<uint32_t*>(base + HP_SLOT / 4) + j * (HP_ITEM / 32), 0);
-            if (any) anybad[slot % HP_RING].fetch_or(any, std::memory_order_relaxed);
-            done[slot % HP_RING].fetch_add(1, std::memory_order_release);
+            const uint64_t b = it * S.item;
+            const uint64_t len = n - b < S.item ? n - b : S.item;
+            uint8_t* packed = base + j * (S.item / 4);
+            uint32_t* mask = reinterpret_cast<uint32_t*>(base + S.off_mask) + j * (S.item / 32);
+            const uint64_t block_bases = (uint64_t)S.block_words * 32;
+            uint32_t map = 0;
+            for (uint32_t blk = 0; (uint64_t)blk * block_bases < len; blk++) {
+                const uint64_t o = (uint64_t)blk * block_bases;
+                const uint64_t l = len - o < block_bases ? len - o : block_bases;
+                if (kc_host_pack_range(h_data + b + o, l, packed + o / 4, mask + o / 32, 0)) map |= 1u << blk;
+            }
+            reinterpret_cast<uint32_t*>(base + S.off_hdr)[j] = map;
+            // acq_rel: the finisher sees every item's bytes and map; its own are ordered before the flag
+            if ((uint64_t)done[r].fetch_add(1, std::memory_order_acq_rel) + 1 == items_of(slot)) {
+                finish_slot(base, items_of(slot));
+                ready[r].store(1, std::memory_order_release);
+            }
         }
     }
 };
@@ -329,17 +420,23 @@ static int host_packed_count(kc_ctx* ctx, const char* h_data, uint64_t nbytes, i
     // device image: table | ASCII (rounded up to 256 B) | packed | mask
     const size_t ascii_bytes = (size_t)((nbytes + 64 + 255) & ~(uint64_t)255);
     const size_t packed_bytes = (size_t)(((nbytes + 3) / 4 + 255) & ~(uint64_t)255);
-    const size_t mask_bytes = (size_t)((nbytes + 31) / 32 * 4);
-    int rc = kc_scratch2_reserve(ctx, table_bytes + ascii_bytes + packed_bytes + mask_bytes + 256);
+    const size_t mask_bytes = (size_t)(((nbytes + 31) / 32 * 4 + 255) & ~(uint64_t)255);
+    const HpShape& S = hp_shape();
+    const uint64_t nitems_all = (nbytes + S.item - 1) / S.item;
+    const uint64_t nslots_all = (nitems_all + HP_ITEMS_PER_SLOT - 1) / HP_ITEMS_PER_SLOT;
+    const size_t stage_bytes = (size_t)nslots_all * S.stage_stride;
+    int rc = kc_scratch2_reserve(ctx, table_bytes + ascii_bytes + packed_bytes + mask_bytes + stage_bytes + 256);
     if (rc) return rc;
     uint32_t* d_table = d_user ? d_user : (uint32_t*)ctx->scratch2;
     char* d_ascii = (char*)ctx->scratch2 + table_bytes;
     uint8_t* d_packed = (uint8_t*)d_ascii + ascii_bytes;
     uint32_t* d_mask = (uint32_t*)(d_packed + packed_bytes);
+    uint32_t* d_stage = (uint32_t*)((uint8_t*)d_mask + mask_bytes);
+    const uint64_t total_words = (nbytes + 31) / 32;
     KC_CUDA(ctx, cudaMemsetAsync(d_table, 0, table_bytes, ctx->stream));
     ctx->last_h2d_bytes = 0;
     if (nbytes >= (uint64_t)k) {
-        const size_t ring_bytes = (size_t)HP_RING * HP_SLOT_BYTES;
+        const size_t ring_bytes = (size_t)HP_RING * S.slot_bytes;
         if (ctx->pinned_bytes < ring_bytes) {
             if (ctx->pinned) cudaFreeHost(ctx->pinned);
             ctx->pinned = nullptr;
@@ -355,12 +452,12 @@ static int host_packed_count(kc_ctx* ctx, const char* h_data, uint64_t nbytes, i
         HostPackPipe pipe;
         pipe.h_data = h_data;
         pipe.n = nbytes;
-        pipe.nitems = (nbytes + HP_ITEM - 1) / HP_ITEM;
-        pipe.nslots = (pipe.nitems + HP_ITEMS_PER_SLOT - 1) / HP_ITEMS_PER_SLOT;
+        pipe.nitems = nitems_all;
+        pipe.nslots = nslots_all;
         pipe.ring = (uint8_t*)ctx->pinned;
         for (int i = 0; i < HP_RING; i++) {
             pipe.done[i].store(0, std::memory_order_relaxed);
-            pipe.anybad[i].store(0, std::memory_order_relaxed);
+            pipe.ready[i].store(0, std::memory_order_relaxed);
         }
         cudaEvent_t ev[HP_RING];
         int nev = 0;
@@ -383,27 +480,36 @@ static int host_packed_count(kc_ctx* ctx, const char* h_data, uint64_t nbytes, i
         if (th.empty()) rc = kc_set_error(ctx, KC_ERR_NOMEM, "kc_count_dense_host_packed: no packer thread could be started");
         while (!rc && released < pipe.nslots) {
             bool progress = false;
-            if (issued < pipe.nslots && issued < released + HP_RING &&
-                (uint64_t)pipe.done[issued % HP_RING].load(std::memory_order_acquire) == pipe.items_of(issued)) {
+            if (issued < pipe.nslots && issued < released + HP_RING && pipe.ready[issued % HP_RING].load(std::memory_order_acquire)) {
                 const int r = (int)(issued % HP_RING);
-                const uint32_t anybad = pipe.anybad[r].exchange(0, std::memory_order_relaxed);
-                pipe.done[r].store(0, std::memory_order_relaxed);  // before `released` lets anyone at this slot again
-                const uint64_t b = issued * HP_SLOT;
-                const uint64_t e = (b + HP_SLOT < nbytes) ? b + HP_SLOT : nbytes;
-                const uint8_t* src = pipe.ring + (size_t)r * HP_SLOT_BYTES;
+                pipe.ready[r].store(0, std::memory_order_relaxed);  // both before `released` lets anyone at this slot again
+                pipe.done[r].store(0, std::memory_order_relaxed);
+                const uint64_t b = issued * S.slot;
+                const uint64_t e = (b + S.slot < nbytes) ? b + S.slot : nbytes;
+                const uint8_t* src = pipe.ring + (size_t)r * S.slot_bytes;
+                const uint32_t* hdr = reinterpret_cast<const uint32_t*>(src + S.off_hdr);
+                const bool sparse = hdr[16] == HP_MODE_SPARSE;
+                // [header][dirty blocks] -> the slot's stage record (a FULL slot: the header alone)
+                const size_t rec_bytes = (HP_HDR_WORDS + (sparse ? (size_t)hdr[17] * S.block_words : 0)) * 4;
+                const size_t full_bytes = (size_t)((e - b + 31) / 32 * 4);
                 ce = cudaMemcpyAsync(d_packed + b / 4, src, (size_t)((e - b + 3) / 4), cudaMemcpyHostToDevice, ctx->copy_stream);
-                // an all-valid slot (most of a genome) sends no mask: the device zeroes its words instead
-                if (ce == cudaSuccess && anybad)
-                    ce = cudaMemcpyAsync(d_mask + b / 32, src + HP_SLOT / 4, (size_t)((e - b + 31) / 32 * 4), cudaMemcpyHostToDevice,
-                                         ctx->copy_stream);
-                else if (ce == cudaSuccess)
-                    ce = cudaMemsetAsync(d_mask + b / 32, 0, (size_t)((e - b + 31) / 32 * 4), ctx->copy_stream);
-                h2d += (e - b + 3) / 4 + (anybad ? (e - b + 31) / 32 * 4 : 0);
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyAsync((uint8_t*)d_stage + issued * S.stage_stride, hdr, rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+                if (ce == cudaSuccess && !sparse)
+                    ce = cudaMemcpyAsync(d_mask + b / 32, src + S.off_mask, full_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+                h2d += (e - b + 3) / 4 + rec_bytes + (sparse ? 0 : full_bytes);
                 if (ce == cudaSuccess) ce = cudaEventRecord(ev[r], ctx->copy_stream);
                 issued++;
                 if (ce == cudaSuccess && (issued % HP_COUNT_SLOTS == 0 || issued == pipe.nslots)) {
-                    // bases [unpacked, e) are on their way: unpack and count behind them
+                    // bases [unpacked, e) are on their way: rebuild their bitmap and ASCII image behind the copies, count
                     ce = cudaStreamWaitEvent(ctx->stream, ev[r], 0);
+                    if (ce == cudaSuccess) {
+                        const uint64_t slot0 = unpacked / S.slot;
+                        KC_LAUNCH(mask_expand_kernel, dim3((unsigned)(issued - slot0), HP_ITEMS_PER_SLOT), 256, 0, ctx->stream, d_stage,
+                                  (uint64_t)(S.stage_stride / 4), slot0, S.block_words, S.bpi, total_words, d_mask);
+                        ctx->launches++;
+                        ce = cudaGetLastError();
+                    }
                     if (ce == cudaSuccess) {
                         rc = unpack_range(ctx, d_packed, d_mask, unpacked, e - unpacked, d_ascii + unpacked, ctx->stream);
                         unpacked = e;

@@ -190,6 +190,13 @@ def make_input(kind, n, seed, k):
         return O.gen_genome(seed, n, 3, 40, k, 0, n)
     if kind == "polyA":
         return np.full(n, ord("A"), dtype=np.uint8)
+    if kind.startswith("sparseN"):  # random ACGT with an invalid byte about every <period> bases
+        period = int(kind[7:])
+        rng = np.random.default_rng(seed)
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+        pos = np.flatnonzero(rng.random(n) < 1.0 / period)
+        a[pos] = np.frombuffer(b"N\n\0a", dtype=np.uint8)[rng.integers(0, 4, pos.size)]
+        return a
     if kind == "skew":  # 90 % of the windows fall into a few partitions
         rng = np.random.default_rng(seed)
         a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
@@ -373,15 +380,20 @@ def case_dense_host_packed(args):
         ctx.check(ctx.L.kc_count_dense_host_packed(ctx.h, data.ctypes.data if n else None, n, k, table.ctypes.data, nthreads))
         assert (table == want).all(), "kc_count_dense_host_packed differs"
         sent = int(ctx.L.kc_ctx_last_h2d_bytes(ctx.h))
-        if n >= k:  # the packed bytes + the mask words of the slots that hold an invalid byte (or the end of the input)
-            item = (int(os.environ.get("KC_HOSTPACK_ITEM", "0")) + 31) // 32 * 32 or (1 << 20)
-            slot = 16 * item
+        if n >= k:  # per slot: packed bytes + 256-byte header + its dirty bitmap blocks (sparse) or its whole bitmap (full)
+            item = int(os.environ.get("KC_HOSTPACK_ITEM", "0")) or (1 << 20)
+            item = (item + 31) // 32 * 32 if item <= 1024 else (item + 1023) // 1024 * 1024
+            item_words = item // 32
+            block_words = 1 if item_words <= 32 else item_words // 32
+            bpi = item_words // block_words
+            slot, block = 16 * item, 32 * block_words
             valid = np.isin(data, np.frombuffer(b"ACGT", dtype=np.uint8))
-            expect = (n + 3) // 4
+            expect = 0
             for b in range(0, n, slot):
                 e = min(b + slot, n)
-                if not valid[b:e].all() or (e - b) % 32:
-                    expect += (e - b + 31) // 32 * 4
+                dirty = sum(1 for o in range(b, e, block) if not valid[o:min(o + block, e)].all() or (min(o + block, e) - o) % 32)
+                expect += (e - b + 3) // 4 + 256
+                expect += dirty * block_words * 4 if dirty <= (16 * bpi) // 4 else (e - b + 31) // 32 * 4
             assert sent == expect, (sent, expect)
     t = ctx.alloc(4 << (2 * k))   # the device-table variant overwrites whatever the table held
     ctx.check(ctx.L.kc_memset_d(ctx.h, t, 0x5A, 4 << (2 * k)))

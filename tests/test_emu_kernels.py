@@ -230,6 +230,12 @@ def test_host_packed_count_on_emulator():
     run_case("dense_host_packed", 8, 70_001, 3, "genome", 1, KC_HOSTPACK_ITEM=32)
     run_case("dense_host_packed", 4, 5_000_000, 4, "dirty", 0)            # production item size, auto threads
     run_case("dense_host_packed", 6, 100_000, 6, "polyA", 2, KC_HOSTPACK_ITEM=64)   # no invalid byte: no mask words sent
+    # sparse bitmap transfer: a few dirty blocks per slot (compaction on the host, rank lookup in mask_expand_kernel),
+    # at 1-word blocks (item 64), 2-word blocks (item 2048) and mixed sparse / full slots
+    run_case("dense_host_packed", 7, 150_000, 7, "sparseN300", 3, KC_HOSTPACK_ITEM=64)
+    run_case("dense_host_packed", 7, 150_000, 8, "sparseN5000", 2, KC_HOSTPACK_ITEM=64)
+    run_case("dense_host_packed", 9, 600_000, 9, "sparseN2000", 3, KC_HOSTPACK_ITEM=2048)
+    run_case("dense_host_packed", 5, 200_000, 10, "sparseN100", 2, KC_HOSTPACK_ITEM=96)
     for n in (0, 1, 3, 4, 31, 32, 33):
         run_case("dense_host_packed", 3, n, 5, "dirty", 2, KC_HOSTPACK_ITEM=32)
 
