@@ -43,6 +43,8 @@ WORKLOADS = {
     "genome_k11": dict(L=3_100_000_000, k=11, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=11"),
     "genome_k8": dict(L=3_100_000_000, k=8, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=8"),
     "genome_k6": dict(L=3_100_000_000, k=6, long_runs=1000, short_runs=10000, seed=0xB2000003, desc="3.1 Gbp genome, k=6"),
+    # not a measurement: the size tests/emu/bench_dryrun.py pushes through this file's GPU arm on the CPU emulator
+    "tiny_k12": dict(L=600_000, k=12, long_runs=2, short_runs=20, seed=0xB2000003, desc="600 Kbp, k=12 (dry-run aid, not a benchmark)"),
 }
 SPARSE_WORKLOADS = {
     # name: (reads at full scale, read length, genome length, k, seed) — SURVEY §8d configs 4 and 5
@@ -299,6 +301,8 @@ def probe_cache_path(args):
 def probe_variants(args, k, local):
     import subprocess
     cands = PROBE_CANDIDATES.get(k, [])
+    if os.environ.get("KC_BENCH_PROBE_CANDIDATES"):  # measurement / test aid: "4,7"
+        cands = [int(x) for x in os.environ["KC_BENCH_PROBE_CANDIDATES"].split(",") if x.strip()]
     if not cands:
         return 0, None
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local), LOCAL_WORLD_SIZE="1")

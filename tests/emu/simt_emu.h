@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <sys/mman.h>
 
 #include <algorithm>
@@ -288,7 +289,7 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSucce
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
-    *e = (cudaEvent_t)malloc(8);
+    *e = (cudaEvent_t)calloc(1, 8);
     return cudaSuccess;
 }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
@@ -296,11 +297,18 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
     free(e);
     return cudaSuccess;
 }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+// an event holds the wall-clock time of its record (everything is synchronous here), so that host code
+// that branches on elapsed times (bench.py's per-kernel table) takes the same branches as on a GPU
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    *reinterpret_cast<double*>(e) = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    return cudaSuccess;
+}
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }  // everything is synchronous here
-static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
-    *ms = 0.f;
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = (float)(*reinterpret_cast<double*>(b) - *reinterpret_cast<double*>(a));
     return cudaSuccess;
 }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }

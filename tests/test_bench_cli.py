@@ -88,3 +88,66 @@ def test_probe_variants_decision(tmp_path, monkeypatch):
     for f in glob.glob("/tmp/kc_bench_probe_config3_987654321_*.json"):
         os.remove(f)
     assert bench.probe_variants(args, 5, 0) == (0, None)   # no candidates for this k
+
+
+DRYRUN = os.path.join(ROOT, "tests", "emu", "bench_dryrun.py")
+GPU_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"}
+
+
+def _one_line(out):
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1, out[-2000:]
+    return json.loads(lines[0])
+
+
+def test_gpu_arm_dry_run_single(tmp_path):
+    """bench.py's GPU arm — variant probes in child processes, timed region, roofline, e2e through both host
+    paths, CPU baseline with its parity check, the reference-code config-1 line — executed on the CPU: the
+    emulator build of the kernels in the place of the library, torch's CUDA surface replaced by stand-ins
+    (tests/emu/bench_dryrun.py).  Checks the Python and the contract of the line, not any number."""
+    import glob
+    for f in glob.glob("/tmp/kc_bench_probe_tiny_k12_*.json"):
+        os.remove(f)
+    env = dict(os.environ, KC_EMU_SMS="4", KC_BENCH_PROBE_CANDIDATES="4")
+    r = subprocess.run([sys.executable, DRYRUN, "--workload", "tiny_k12", "--steps", "1", "--cpu-sample", "300000"], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = _one_line(r.stdout)
+    assert GPU_KEYS <= set(d), sorted(GPU_KEYS - set(d))
+    assert d["metric"] == "bases/sec" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"]
+    rf = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"} <= set(rf) and rf["bound"] == "hbm" and rf["unit"] == "GB/s"
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["parity_on_sample"] == "bit-exact" and "sample" in cb
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "api"} <= set(e) and e["value"] > 0
+    # the packed host path ran in its own process, reproduced the table, and ran again here
+    pk = e.get("packed_probe") or e["plain"]
+    assert e["packed_probe"]["ok"] and e["packed_probe"]["fp"] == d["config"]["table_fingerprint"] and pk
+    assert e["packed_probe"]["in_process_same_table"] is True
+    # the variant probe ran, produced the shipped table, and was not taken (it is slower on the emulator) or was
+    pr = d["config"]["probe"]
+    assert pr["0"]["ok"] and pr["4"]["ok"] and pr["4"]["same_table"] is True
+    assert set(pr["4"]["kernel_ms"]) == {"part_scatter_kernel", "part_count_kernel"}
+    assert d["reference_config1"]["parity"] == "bit-exact"
+    for f in glob.glob("/tmp/kc_bench_probe_tiny_k12_*.json"):
+        os.remove(f)
+
+
+def test_gpu_arm_dry_run_two_ranks():
+    """the same through torchrun with two ranks (collectives over gloo): one line, from rank 0, the full-sequence
+    table of the single-rank run, and both processes leave"""
+    env = dict(os.environ, KC_EMU_SMS="4", OMP_NUM_THREADS="1", KC_BENCH_E2E_PACKED_N="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29673", DRYRUN, "--gpus", "2", "--workload", "tiny_k12", "--steps", "1", "--no-probe"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = _one_line(r.stdout)
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["cpu_baseline"] is None
+    one = subprocess.run([sys.executable, DRYRUN, "--workload", "tiny_k12", "--steps", "1", "--no-probe", "--no-e2e", "--no-cpu"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert one.returncode == 0, one.stderr[-3000:]
+    assert _one_line(one.stdout)["config"]["table_fingerprint"] == d["config"]["table_fingerprint"]
+    assert "packed" in d["e2e"] or "plain" in d["e2e"]   # the opt-in packed path of N > 1 ran on every rank
