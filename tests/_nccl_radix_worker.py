@@ -23,7 +23,9 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     ctx = kmerb200.Context(local)
-    for k, nreads in ((21, 200_000), (31, 100_000)):
+    # KC_NCCL_RADIX_CASES="21:600,31:500": smaller cases for the CPU dry run of this file (tests/test_sharding_gloo.py)
+    cases = [tuple(int(x) for x in c.split(":")) for c in os.environ.get("KC_NCCL_RADIX_CASES", "21:200000,31:100000").split(",")]
+    for k, nreads in cases:
         r0, r1 = D.shard_reads(nreads, rank, world)
         reads = ctx.gen_reads(0xB2000004, 20_000_000, 150, 200, r0, r1 - r0)
         sp = D.count_sparse_sharded_gpu(ctx, reads, (r1 - r0) * 151, k, kmerb200.SPARSE_RADIX | kmerb200.SPARSE_NO_FALLBACK)

@@ -29,6 +29,19 @@ def test_world2_gloo_radix():
     assert "GLOO_RADIX_WORKER_OK world=2" in r.stdout
 
 
+def test_nccl_radix_worker_dry_run():
+    """the GPU worker of the range-sharded radix path itself (tests/_nccl_radix_worker.py: kmerb200.Context's
+    radix_plan / scatter / count methods, count_sparse_sharded_gpu's dispatch and overflow vote), unmodified,
+    on the CPU: emulator library + torch CUDA stand-ins + gloo (tests/emu/run_under_shim.py), small cases"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29658", os.path.join(ROOT, "tests", "emu", "run_under_shim.py"),
+           os.path.join(ROOT, "tests", "_nccl_radix_worker.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="1", KC_SPARSE_RADIX_SHAPE="small", KC_EMU_SMS="4", KC_NCCL_RADIX_CASES="21:600,31:500")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "NCCL_RADIX_WORKER_OK world=2" in r.stdout
+
+
 def test_mix64_np_matches_engine(kmerlib, oracle):
     from kmerb200 import distributed as D
     xs = np.array([0, 1, 0xDEADBEEF, (1 << 62) - 1, 12345678901234567], dtype=np.uint64)
