@@ -288,7 +288,7 @@ def leave(world):
 # variant is used for the timed run only if its table is bit-identical to the shipped path's (a
 # position-weighted fingerprint of all 4^k bins) and it is at least 3 % faster.  Every probe's time and
 # verdict goes into the result line (config.probe).
-PROBE_CANDIDATES = {12: [4, 5, 6, 7], 8: [3]}
+PROBE_CANDIDATES = {12: [4, 5, 6, 7, 8, 9], 8: [3]}
 PROBE_SCRIPT = os.path.abspath(__file__)  # tests put a stand-in here
 
 
@@ -430,7 +430,7 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="sparse workloads: number of reads (0 = full scale)")
     ap.add_argument("--sparse-algo", default="hash", choices=["hash", "sort", "radix"])
     ap.add_argument("--capacity-hint", type=int, default=0, help="sparse hash: expected distinct k-mers")
-    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition, 3 k=8 checksum variant, 4 partition with deferred retry, 5 partition with paired count (k=12), 6 partition with 14-mer + 13-mer count (k=12), 7 partition with seven windows per record (k=12)")
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition, 3 k=8 checksum variant, 4 partition with deferred retry, 5 partition with paired count (k=12), 6 partition with 14-mer + 13-mer count (k=12), 7 partition with seven windows per record (k=12), 8 = 4 + 5, 9 = 4 + 6")
     ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="bases of the CPU-baseline sample")
     ap.add_argument("--ref-sample", type=int, default=1 << 30, help="bases per step of the reference arm")
@@ -634,7 +634,7 @@ def main():
         else:
             kernels = {"dense_smem16_kernel": (p1, bases_launch), "smem16_reduce_kernel": (p2, 4 * nk)}
     elif p2 > 0:  # two-pass partition path (the count kernel has measured-later variants: --algo 5/6, KC_PART_PAIR)
-        pm = {5: 1, 6: 2}.get(args.algo, int(os.environ.get("KC_PART_PAIR", "0") or 0)) if k == 12 else 0
+        pm = {5: 1, 6: 2, 8: 1, 9: 2}.get(args.algo, int(os.environ.get("KC_PART_PAIR", "0") or 0)) if k == 12 else 0
         cname = {0: "part_count_kernel", 1: "part_count_pair12_kernel", 2: "part_count_trio12_kernel"}.get(pm, "part_count_kernel")
         sname = "part_scatter_kernel"
         if args.algo == 7:
@@ -830,7 +830,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "bases": L, "kmers_per_sec": (L - k + 1) / (ms_step * 1e-3),
-                       "algo": {0: "auto", 1: "direct", 2: "partition", 3: "smem16-checksum", 4: "partition-deferred-retry", 5: "partition-paired-count", 6: "partition-two-increment-count", 7: "partition-wide-records"}[args.algo],
+                       "algo": {0: "auto", 1: "direct", 2: "partition", 3: "smem16-checksum", 4: "partition-deferred-retry", 5: "partition-paired-count", 6: "partition-two-increment-count", 7: "partition-wide-records",
+                                8: "partition-deferred-retry+paired-count", 9: "partition-deferred-retry+two-increment-count"}[args.algo],
                        "launch": "CUDA graph replay" if graph is not None else "plain launches",
                        "l2": ("input %.2f GB per GPU (+ as much scratch written per step) exceeds the 126 MB L2: "
                               "no flush needed" % (nb / 1e9)) if nb > 252e6 else

@@ -1255,7 +1255,7 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (!d_table || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION && algo != KC_DENSE_SMEM16C &&
         algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR && algo != KC_DENSE_PARTITION_TRIO &&
-        algo != KC_DENSE_PARTITION_WIDE)
+        algo != KC_DENSE_PARTITION_WIDE && algo != KC_DENSE_PARTITION_DEFER_PAIR && algo != KC_DENSE_PARTITION_DEFER_TRIO)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown dense algo %d", algo);
     if (algo == KC_DENSE_SMEM16C) {
         if (k != 8) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_SMEM16C is the k = 8 path (k=%d)", k);
@@ -1273,8 +1273,10 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         if (win_begin >= win_end) return KC_OK;
         return kc_dense_partition_wide(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream);
     }
-    const bool defer = (algo == KC_DENSE_PARTITION_DEFER);
-    const int pair = (algo == KC_DENSE_PARTITION_PAIR) ? 1 : (algo == KC_DENSE_PARTITION_TRIO) ? 2 : 0;
+    const bool defer = (algo == KC_DENSE_PARTITION_DEFER || algo == KC_DENSE_PARTITION_DEFER_PAIR || algo == KC_DENSE_PARTITION_DEFER_TRIO);
+    const int pair = (algo == KC_DENSE_PARTITION_PAIR || algo == KC_DENSE_PARTITION_DEFER_PAIR)   ? 1
+                     : (algo == KC_DENSE_PARTITION_TRIO || algo == KC_DENSE_PARTITION_DEFER_TRIO) ? 2
+                                                                                                  : 0;
     if (pair && k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_PAIR/TRIO are built for k = 12 (k=%d)", k);
     if (defer || pair) algo = KC_DENSE_PARTITION;
     DeviceGuard dg(ctx->device);

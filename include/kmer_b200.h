@@ -197,6 +197,8 @@ KC_API int kc_count_dense_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes
                                       pass 1; pass 2 counts two 14-mers (4-bit fields) + one 12-mer   */
 #define KC_DENSE_PARTITION_TRIO 6  /* k = 12: one 14-mer (8-bit fields) + one 13-mer per record:
                                       2 shared increments instead of 5                           */
+#define KC_DENSE_PARTITION_DEFER_PAIR 8  /* k = 12: the scatter of 4 with the count of 5 */
+#define KC_DENSE_PARTITION_DEFER_TRIO 9  /* k = 12: the scatter of 4 with the count of 6 */
 KC_API int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
                                       uint64_t win_begin, uint64_t win_end, int k,
                                       uint32_t* d_table, int algo, void* stream);

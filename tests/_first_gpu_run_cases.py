@@ -131,6 +131,25 @@ def test_partition_two_increment_count(ctx, kmerlib, oracle):
     assert int(t[0].item()) == P - 11 and int(t.to(torch.int64).sum().item()) == P - 11
 
 
+def test_partition_combined_variants(ctx, kmerlib, oracle):
+    """algo 8 / 9 (k = 12): the deferred-retry scatter with the paired / two-increment count, against the oracle
+    and against the shipped path at 1 Gbp"""
+    import torch
+    n = sz(40_000_000)
+    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
+    want, _ = oracle.count_dense(genome, 12)
+    L = sz(1 << 30)
+    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
+    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
+    for algo in (kmerlib.DENSE_PARTITION_DEFER_PAIR, kmerlib.DENSE_PARTITION_DEFER_TRIO):
+        assert (_dense(ctx, kmerlib, genome, 12, algo) == want).all(), algo
+        b = torch.zeros_like(a)
+        ctx.count_dense_range(data, L, 0, L, 12, b, algo=algo)
+        torch.cuda.synchronize()
+        assert bool((a == b).all()), algo
+
+
 def test_partition_wide_records(ctx, kmerlib, oracle):
     """KC_DENSE_PARTITION_WIDE (k = 12, seven windows per record) against the oracle, against the shipped
     path at 1 Gbp, and on 2^26 'A's (4-bit fields wrap: checksum + 32-bit recount)"""

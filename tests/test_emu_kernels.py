@@ -107,6 +107,15 @@ def test_partition_two_increment_count_variant():
     assert st[7] == 2048, st   # partition 0, twice (whole table + window sub-range), 1024 threads each
 
 
+def test_partition_combined_variants():
+    """algo 8 / 9: the deferred-retry scatter (4) with the paired (5) / two-increment (6) count — host dispatch only,
+    the kernels are the ones of the tests above"""
+    for algo in (8, 9):
+        run_case("dense", 12, 300_000, algo, "dirty", 5, 7)
+        st = emu_stats(run_case("dense", 12, 300_000, algo, "skew", 6, 2, seed=3, sms=2, shift=1))
+        assert st[1] > 0, st   # the deferred retry ran
+
+
 def test_partition_wide_record_variant():
     """KC_DENSE_PARTITION_WIDE (algo 7, k = 12): seven windows per record (18 bases; the slab record omits
     the 11 key bits), pass 2 with two 4-bit 14-mer tables + one 16-bit 12-mer table.  Random schedule on
@@ -257,4 +266,4 @@ def test_first_gpu_run_cases_on_emulator():
                         os.path.join(ROOT, "tests", "_first_gpu_run_cases.py"), "-m", "gpu", "-q", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert "17 passed, 1 skipped" in r.stdout
+    assert "18 passed, 1 skipped" in r.stdout

@@ -30,6 +30,7 @@ CASES = [
     "test_k8_checksum_variant",
     "test_partition_deferred_retry",
     "test_partition_two_increment_count",
+    "test_partition_combined_variants",
     "test_partition_wide_records",
     "test_partition_paired_count",
     "test_packed_store",
