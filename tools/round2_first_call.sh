@@ -8,8 +8,8 @@ mkdir -p gpurun_out
 O=gpurun_out
 echo "== 1. GPU parity tests (the first-run-pending file is last, xfail(strict=False), every case in its own time-limited process)"
 timeout 1500 python -m pytest tests -m gpu -q -x -rxX > $O/r02_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 $O/r02_pytest.log
-echo "== 2. dense k=12: shipped (--algo 0) vs deferred-retry scatter (--algo 4) vs paired count (--algo 5) vs 14-mer + 13-mer count (--algo 6) vs seven windows per record (--algo 7); KC_PART_PAIR=1|2 combines a count variant with any scatter variant"
-for A in 0 4 5 6 7; do
+echo "== 2. dense k=12: shipped (--algo 0) vs deferred-retry scatter (--algo 4) vs paired count (--algo 5) vs 14-mer + 13-mer count (--algo 6) vs seven windows per record (--algo 7) vs the combinations 4+5 (--algo 8) and 4+6 (--algo 9); KC_PART_PAIR=1|2 combines a count variant with any scatter variant"
+for A in 0 4 5 6 7 8 9; do
   timeout 300 python bench.py --algo $A --steps 20 --warmup 3 --no-e2e --no-cpu > $O/r02_dense_abl$A.log 2> $O/r02_dense_abl$A.err
   python - <<PY
 import json
