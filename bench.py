@@ -706,6 +706,9 @@ def main():
         # only if that process reproduced the resident-input table — here, and the faster of the two is reported.
         if world == 1 and not args.no_probe and not os.environ.get("KC_BENCH_NO_PROBE"):
             pk = probe_e2e_packed(args, local)
+            pk["packer_threads"] = int(kmerb200.lib().kc_host_pack_threads(0))
+            pk["packer_body"] = {0: "scalar", 1: "avx2", 2: "avx512bw"}.get(int(kmerb200.lib().kc_host_pack_simd()), "?")
+            pk["host_cpus"] = os.cpu_count()
             e2e["packed_probe"] = pk
             if pk.get("ok") and pk.get("fp") == table_fp:
                 try:

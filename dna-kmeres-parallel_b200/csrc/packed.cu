@@ -402,6 +402,8 @@ int kc_pack_2bit_host_body(const char* h_data, uint64_t nbytes, void* h_packed, 
     return KC_OK;
 }
 
+int kc_host_pack_threads(int nthreads) { return host_threads(nthreads); }
+
 int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask, int nthreads) {
     return kc_pack_2bit_host_body(h_data, nbytes, h_packed, h_badmask, nthreads, 0);
 }

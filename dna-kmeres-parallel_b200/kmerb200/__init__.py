@@ -103,6 +103,7 @@ def lib():
         "kc_pack_2bit_host": (i32, [vp, u64, vp, vp, i32]),
         "kc_pack_2bit_host_body": (i32, [vp, u64, vp, vp, i32, i32]),
         "kc_host_pack_simd": (i32, []),
+        "kc_host_pack_threads": (i32, [i32]),
         "kc_count_dense_host_packed": (i32, [vp, vp, u64, i32, vp, i32]),
         "kc_count_dense_host_packed_dev": (i32, [vp, vp, u64, i32, vp, i32]),
         "kc_sparse_radix_plan": (i32, [vp, u64, i32, C.c_uint32, vp]),

@@ -297,6 +297,8 @@ KC_API int kc_count_dense_packed(kc_ctx* ctx, const void* d_packed, const uint32
  * core this process may run on (at most 64).  AVX-512BW or AVX2 body when the host has it (kc_host_pack_simd()). */
 KC_API int kc_pack_2bit_host(const char* h_data, uint64_t nbytes, void* h_packed, uint32_t* h_badmask,
                              int nthreads);
+KC_API int kc_host_pack_threads(int nthreads);   /* packer threads a call with this `nthreads` argument uses
+                                                    (0: cores the process may run on - 1, cgroup quota, at most 64) */
 KC_API int kc_host_pack_simd(void);   /* body kc_pack_2bit_host uses here: 0 scalar, 1 AVX2, 2 AVX-512BW */
 /* diagnostic / test aid: the same with a chosen loop body (0 = best available, 1 = scalar, 2 = AVX2 if present) */
 KC_API int kc_pack_2bit_host_body(const char* h_data, uint64_t nbytes, void* h_packed,
