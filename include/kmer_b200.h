@@ -307,7 +307,8 @@ KC_API int kc_pack_2bit_host_body(const char* h_data, uint64_t nbytes, void* h_p
  * for hosts with cores to spare: packer threads turn the ASCII into the store's layout slot by slot
  * (pinned ring), the slots cross PCIe at 0.25 bytes per base + the 4 KiB bitmap blocks that hold an invalid
  * byte (at most 0.375 in all) instead of 1, the GPU rebuilds bitmap and bytes at HBM speed and counts behind
- * the copies.  Same result as kc_count_dense_host / kc_count_dense.  nthreads =
+ * the copies.  h_data need not be pinned (the packer threads read it; only the library's own ring is).
+ * Same result as kc_count_dense_host / kc_count_dense.  nthreads =
  * packer threads (0 = cores available to the process - 1, at most 64).                               */
 KC_API int kc_count_dense_host_packed(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k,
                                       uint32_t* h_table, int nthreads);
