@@ -290,6 +290,7 @@ def leave(world):
 # verdict goes into the result line (config.probe).
 PROBE_CANDIDATES = {12: [4, 5, 6, 7, 8, 9], 8: [3]}
 PROBE_SCRIPT = os.path.abspath(__file__)  # tests put a stand-in here
+E2E_PACKED_OK = "/tmp/kc_bench_e2e_packed_ok"  # written by an N = 1 run whose packed host path reproduced the table
 
 
 def probe_cache_path(args):
@@ -722,6 +723,12 @@ def main():
                     same = same and fingerprint(h_table.to(dev)) == table_fp
                     pk["in_process_ms"] = dtp * 1e3
                     pk["in_process_same_table"] = same
+                    if same:  # this box has run the packed path correctly: the N > 1 runs that follow may use it
+                        try:
+                            with open(E2E_PACKED_OK, "w") as f:
+                                f.write("%d\n" % int(os.path.getmtime(kmerb200.LIB_PATH)))
+                        except Exception:
+                            pass
                     if same and dtp < float(dt.item()):
                         e2e = {"value": L / dtp, "unit": "bases/s", "h2d_bytes_per_step": ctx.last_h2d_bytes,
                                "d2h_bytes_per_step": 4 * nk, "ms_per_step": dtp * 1e3, "steps": n_e2e,
@@ -731,9 +738,25 @@ def main():
                                "packed_probe": pk}
                 except Exception as ex:
                     pk["in_process_error"] = str(ex)[:200]
-        # N > 1, opt-in (KC_BENCH_E2E_PACKED_N=1) until a B200 has run it: every rank feeds its shard through the packed
-        # path into its device table, then the same NCCL reduce + D2H; the ranks share the host's cores.
-        if world > 1 and os.environ.get("KC_BENCH_E2E_PACKED_N"):
+        # N > 1: every rank feeds its shard through the packed path into its device table, then the same NCCL reduce + D2H;
+        # the ranks share the host's cores.  Only if an N = 1 run on this box has just proven the packed path (the driver runs
+        # N = 1, 2, 4, 8 back to back) or KC_BENCH_E2E_PACKED_N=1 asks for it; the faster of plain and packed is reported.
+        use_packed_n = 0
+        if world > 1 and rank == 0:
+            if os.environ.get("KC_BENCH_E2E_PACKED_N"):
+                use_packed_n = 1
+            elif not (os.environ.get("KC_BENCH_NO_PROBE") or args.no_probe):
+                try:  # proven on this box by an N = 1 run of the same library within the hour?
+                    with open(E2E_PACKED_OK) as f:
+                        use_packed_n = int(int(f.read().strip()) == int(os.path.getmtime(kmerb200.LIB_PATH)) and
+                                           time.time() - os.path.getmtime(E2E_PACKED_OK) < 3600)
+                except Exception:
+                    use_packed_n = 0
+        if world > 1:
+            u = torch.tensor([use_packed_n], dtype=torch.int32, device=dev)
+            dist.broadcast(u, src=0)
+            use_packed_n = int(u.item())
+        if world > 1 and use_packed_n:
             nth = max(1, ((os.cpu_count() or 2) - world) // world)
 
             def packed_step():
