@@ -738,65 +738,6 @@ def main():
                                "packed_probe": pk}
                 except Exception as ex:
                     pk["in_process_error"] = str(ex)[:200]
-        # N > 1: every rank feeds its shard through the packed path into its device table, then the same NCCL reduce + D2H;
-        # the ranks share the host's cores.  Only if an N = 1 run on this box has just proven the packed path (the driver runs
-        # N = 1, 2, 4, 8 back to back) or KC_BENCH_E2E_PACKED_N=1 asks for it; the faster of plain and packed is reported.
-        use_packed_n = 0
-        if world > 1 and rank == 0:
-            if os.environ.get("KC_BENCH_E2E_PACKED_N"):
-                use_packed_n = 1
-            elif not (os.environ.get("KC_BENCH_NO_PROBE") or args.no_probe):
-                try:  # proven on this box by an N = 1 run of the same library within the hour?
-                    with open(E2E_PACKED_OK) as f:
-                        use_packed_n = int(int(f.read().strip()) == int(os.path.getmtime(kmerb200.LIB_PATH)) and
-                                           time.time() - os.path.getmtime(E2E_PACKED_OK) < 3600)
-                except Exception:
-                    use_packed_n = 0
-        if world > 1:
-            u = torch.tensor([use_packed_n], dtype=torch.int32, device=dev)
-            dist.broadcast(u, src=0)
-            use_packed_n = int(u.item())
-        if world > 1 and use_packed_n:
-            nth = max(1, ((os.cpu_count() or 2) - world) // world)
-
-            def packed_step():
-                ctx.count_dense_host_packed_dev(host, k, table, nthreads=nth)  # all windows of this rank's bytes = its shard
-                dist.reduce(table, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    h_table.copy_(table, non_blocking=True)
-                torch.cuda.synchronize()
-            ok = 1
-            try:
-                packed_step()
-                if rank == 0 and fingerprint(table) != table_fp:
-                    ok = 0
-            except Exception as ex:
-                sys.stderr.write("bench: packed e2e failed on rank %d: %s\n" % (rank, ex))
-                ok = 0
-            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()):
-                barrier()
-                t0 = time.perf_counter()
-                for _ in range(n_e2e):
-                    packed_step()
-                barrier()
-                dtp = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-                dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
-                sent = torch.tensor([ctx.last_h2d_bytes], dtype=torch.int64, device=dev)
-                dist.all_reduce(sent, op=dist.ReduceOp.SUM)
-                plain = {"api": e2e["api"], "value": e2e["value"], "ms_per_step": e2e["ms_per_step"],
-                         "h2d_bytes_per_step": e2e["h2d_bytes_per_step"]}
-                if float(dtp.item()) < float(dt.item()):
-                    e2e = {"value": L / float(dtp.item()), "unit": "bases/s", "h2d_bytes_per_step": int(sent.item()),
-                           "d2h_bytes_per_step": 4 * nk, "ms_per_step": float(dtp.item()) * 1e3, "steps": n_e2e,
-                           "api": "kc_count_dense_host_packed_dev (%d packer threads per rank) + NCCL reduce + D2H" % nth,
-                           "plain": plain}
-                else:
-                    e2e["packed"] = {"ms_per_step": float(dtp.item()) * 1e3, "threads_per_rank": nth}
-            else:
-                e2e["packed"] = {"ok": False}
-        del host
 
     # ---- CPU baseline: the oracle port, 1 thread, bounded sample ---------------
     cpu = None
@@ -850,7 +791,7 @@ def main():
         except Exception as ex:  # the reference library is optional (built only where /root/reference exists)
             ref1 = {"unavailable": str(ex)[:200]}
 
-    if rank == 0:
+    def make_line(e2e):
         line = {
             "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -870,7 +811,84 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "reference_config1": ref1,
         }
-        emit(line)
+        return line
+
+    emitted = threading.Lock()
+
+    def emit_once(e2e_val):  # the ONE line, whoever gets here first (the end of main, or the watchdog below)
+        if emitted.acquire(blocking=False) and rank == 0:
+            emit(make_line(e2e_val))
+
+    # N > 1: every rank feeds its shard through the packed path into its device table, then the same NCCL reduce + D2H;
+    # the ranks share the host's cores.  Only if an N = 1 run on this box has just proven the packed path (the driver runs
+    # N = 1, 2, 4, 8 back to back) or KC_BENCH_E2E_PACKED_N=1 asks for it; the faster of plain and packed is reported.
+    use_packed_n = 0
+    if world > 1 and rank == 0 and e2e is not None:
+        if os.environ.get("KC_BENCH_E2E_PACKED_N"):
+            use_packed_n = 1
+        elif not (os.environ.get("KC_BENCH_NO_PROBE") or args.no_probe):
+            try:  # proven on this box by an N = 1 run of the same library within the hour?
+                with open(E2E_PACKED_OK) as f:
+                    use_packed_n = int(int(f.read().strip()) == int(os.path.getmtime(kmerb200.LIB_PATH)) and
+                                       time.time() - os.path.getmtime(E2E_PACKED_OK) < 3600)
+            except Exception:
+                use_packed_n = 0
+    if world > 1:
+        u = torch.tensor([use_packed_n], dtype=torch.int32, device=dev)
+        dist.broadcast(u, src=0)
+        use_packed_n = int(u.item())
+    if world > 1 and use_packed_n:
+        nth = max(1, ((os.cpu_count() or 2) - world) // world)
+        # everything else of the line is known: if this extra stalls (its first multi-rank run on a B200 is here), every
+        # rank's watchdog leaves after 150 s and rank 0 prints the line with the plain e2e first
+        e2e_plain = dict(e2e, packed={"ok": False, "why": "no result within the watchdog's time"})
+        wd_s = float(os.environ.get("KC_BENCH_E2E_WATCHDOG_S", "150"))
+        wd = threading.Timer(wd_s, lambda: (emit_once(e2e_plain), sys.stdout.flush(), os._exit(0)))
+        wd.daemon = True
+        wd.start()
+
+        def packed_step():
+            if os.environ.get("KC_BENCH_TEST_STALL") and rank == world - 1:  # test hook for the watchdog
+                time.sleep(3600)
+            ctx.count_dense_host_packed_dev(host, k, table, nthreads=nth)  # all windows of this rank's bytes = its shard
+            dist.reduce(table, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                h_table.copy_(table, non_blocking=True)
+            torch.cuda.synchronize()
+        ok = 1
+        try:
+            packed_step()
+            if rank == 0 and fingerprint(table) != table_fp:
+                ok = 0
+        except Exception as ex:
+            sys.stderr.write("bench: packed e2e failed on rank %d: %s\n" % (rank, ex))
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                packed_step()
+            barrier()
+            dtp = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+            sent = torch.tensor([ctx.last_h2d_bytes], dtype=torch.int64, device=dev)
+            dist.all_reduce(sent, op=dist.ReduceOp.SUM)
+            plain = {"api": e2e["api"], "value": e2e["value"], "ms_per_step": e2e["ms_per_step"],
+                     "h2d_bytes_per_step": e2e["h2d_bytes_per_step"]}
+            if float(dtp.item()) < float(dt.item()):
+                e2e = {"value": L / float(dtp.item()), "unit": "bases/s", "h2d_bytes_per_step": int(sent.item()),
+                       "d2h_bytes_per_step": 4 * nk, "ms_per_step": float(dtp.item()) * 1e3, "steps": n_e2e,
+                       "api": "kc_count_dense_host_packed_dev (%d packer threads per rank) + NCCL reduce + D2H" % nth,
+                       "plain": plain}
+            else:
+                e2e["packed"] = {"ms_per_step": float(dtp.item()) * 1e3, "threads_per_rank": nth}
+        else:
+            e2e["packed"] = {"ok": False}
+    if world > 1 and use_packed_n:
+        wd.cancel()
+    emit_once(e2e)
     leave(world)
     graph = None
     ctx.close()

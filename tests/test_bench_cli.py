@@ -151,3 +151,17 @@ def test_gpu_arm_dry_run_two_ranks():
     assert one.returncode == 0, one.stderr[-3000:]
     assert _one_line(one.stdout)["config"]["table_fingerprint"] == d["config"]["table_fingerprint"]
     assert "packed" in d["e2e"] or "plain" in d["e2e"]   # the opt-in packed path of N > 1 ran on every rank
+
+
+def test_gpu_arm_dry_run_two_ranks_watchdog():
+    """an extra of the N > 1 line (the packed host path in e2e) that stalls on one rank must not cost the line:
+    every rank's watchdog leaves, rank 0 prints the line with the plain e2e first"""
+    env = dict(os.environ, KC_EMU_SMS="4", OMP_NUM_THREADS="1", KC_BENCH_E2E_PACKED_N="1", KC_BENCH_E2E_WATCHDOG_S="6",
+               KC_BENCH_TEST_STALL="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29677", DRYRUN, "--gpus", "2", "--workload", "tiny_k12", "--steps", "1", "--no-probe"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = _one_line(r.stdout)
+    assert d["n_gpus"] == 2 and d["e2e"]["value"] > 0 and d["e2e"]["packed"]["ok"] is False
+    assert d["e2e"]["api"].startswith("H2D")
