@@ -252,3 +252,15 @@ def test_pack_2bit_host_matches_store_layout(kmerlib):
             assert (p == wp).all() and (m == wm).all(), (n, nthreads, body)
     p, m = kmerlib.pack_2bit_host(np.zeros(0, dtype=np.uint8))
     assert p.size == 0 and m.size == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/kmer_b200.h must compile as C99 (and as C++11) without any CUDA or torch header"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "kmer_b200.h"\nint main(void) { return kc_version() > 0 ? 0 : 1; }\n')
+    inc = os.path.join(root, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc, "-fsyntax-only", str(src)],
+                ["g++", "-std=c++11", "-Wall", "-Werror", "-I" + inc, "-fsyntax-only", "-x", "c++", str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
