@@ -10,7 +10,7 @@ R="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 
 echo "== 1. NCCL parity tests (verified hash-sharded path, then the first-run-pending range-sharded radix path)"
 timeout 600 python -m pytest tests -m gpu -q -rxX -k "nccl" > $O/r02_pytest_nccl.log 2>&1; echo "pytest rc=$?"; tail -6 $O/r02_pytest_nccl.log
 echo "== 2. dense bench at N=$N: must print its line AND exit"
-timeout 300 $R --master-port 29741 bench.py --gpus $N --steps 20 --warmup 3 > $O/r02_dense_n$N.log 2> $O/r02_dense_n$N.err; echo "dense N=$N rc=$? (124 = hung)"; cut -c1-300 $O/r02_dense_n$N.log
+timeout 600 $R --master-port 29741 bench.py --gpus $N --steps 20 --warmup 3 > $O/r02_dense_n$N.log 2> $O/r02_dense_n$N.err; echo "dense N=$N rc=$? (124 = hung)"; cut -c1-300 $O/r02_dense_n$N.log
 echo "== 3. config 4 at 1/5 scale, N=$N: hash-sharded vs range-sharded radix"
 for A in hash radix; do
   timeout 600 $R --master-port 29742 bench.py --gpus $N --workload config4 --reads 20000000 --sparse-algo $A --steps 1 --warmup 1 > $O/r02_c4_n${N}_$A.log 2> $O/r02_c4_n${N}_$A.err

@@ -8,8 +8,8 @@ set -u
 mkdir -p gpurun_out
 O=gpurun_out
 R="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-echo "== config 3 (3.1 Gbp, k=12, dense, ncclReduce)"
-timeout 240 $R --master-port 29751 bench.py --gpus 8 --steps 20 --warmup 3 ${DENSE_ALGO:+--algo $DENSE_ALGO} > $O/r02_n8_dense.log 2> $O/r02_n8_dense.err; echo "rc=$?"; cut -c1-400 $O/r02_n8_dense.log
+echo "== config 3 (3.1 Gbp, k=12, dense, ncclReduce; rank 0 first probes the variants at N = 1 size: ~2 min on a fresh box)"
+timeout 600 $R --master-port 29751 bench.py --gpus 8 --steps 20 --warmup 3 ${DENSE_ALGO:+--algo $DENSE_ALGO} > $O/r02_n8_dense.log 2> $O/r02_n8_dense.err; echo "rc=$?"; cut -c1-400 $O/r02_n8_dense.log
 for W in config4 config5; do for A in hash radix; do
   echo "== $W (full scale) $A"
   timeout 300 $R --master-port 29752 bench.py --gpus 8 --workload $W --sparse-algo $A --steps 1 --warmup 1 > $O/r02_n8_${W}_$A.log 2> $O/r02_n8_${W}_$A.err
