@@ -564,6 +564,21 @@ def shard_windows(nbytes, k, rank, world):
     return b, e, b, min(e + k - 1, nbytes) if e > b else b
 
 
+def shard_seqs(offsets, rank, world):
+    """Sequence range [s0, s1) of `rank` for the per-sequence table (independent sequences): cut at
+    sequence starts, as close as they come to equal BYTES per rank (offsets = the loader's num_seqs + 1 starts)."""
+    off = np.asarray(offsets, dtype=np.int64)
+    n = off.size - 1
+    if n <= 0:
+        return 0, 0
+    total = int(off[-1] - off[0])
+    cut = [int(np.searchsorted(off[:-1], off[0] + total * r // world, side="left")) for r in range(world + 1)]
+    cut[0], cut[world] = 0, n
+    for r in range(1, world + 1):   # monotone
+        cut[r] = max(cut[r], cut[r - 1])
+    return cut[rank], cut[rank + 1]
+
+
 def shard_reads(nreads, rank, world):
     """Read range of `rank` for the sparse path (reads never straddle shards)."""
     return nreads * rank // world, nreads * (rank + 1) // world

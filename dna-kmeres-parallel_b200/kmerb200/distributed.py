@@ -5,6 +5,10 @@ dense   : the sequence is cut into window ranges; each rank reads its bytes plus
           a (k-1)-byte halo and counts only windows STARTING in its range, so no
           carry is exchanged; the uint32[4^k] tables are summed with one reduce
           (int32 views: two's-complement add == uint32 add mod 2^32).
+per-seq : the reference-shaped table int32[4^k][num_seqs] (kernels.h:142): sequences are
+          independent, so each rank counts a range of them (cut at sequence starts, equal
+          bytes per rank) and the columns are all-gathered; every rank ends with the whole
+          table, which is what the distance step (kernels.h:85-109) reads.
 sparse  : reads are cut by read index; each rank counts locally, buckets its
           (code, count) pairs by owner = mix64(code) % world, exchanges buckets
           with one all-to-all, and the owner merges what it received: every rank
@@ -15,7 +19,7 @@ GPU (kmerb200.Context) and in the gloo tests (the oracle stands in on the CPU).
 """
 import numpy as np
 
-from . import shard_reads, shard_windows  # noqa: F401  (re-exported)
+from . import shard_reads, shard_seqs, shard_windows  # noqa: F401  (re-exported)
 
 
 def _dist():
@@ -67,6 +71,31 @@ def count_dense_sharded(count_range, make_shard, nbytes, k, table, rank, world, 
         shard = make_shard(bb, be)
         count_range(shard, be - bb, 0, e - b, table)
     return reduce_table(table, dst)
+
+
+def count_per_seq_sharded(count_seqs, offsets, rank, world):
+    """SURVEY §8e, per-sequence mode.  count_seqs(s0, s1) returns this rank's columns, an int32 tensor
+    [4^k, s1 - s0] (k-mer-major like the reference's `sums`, kernels.h:142) for the sequences [s0, s1) — the
+    caller uploads only those sequences' bytes (offsets[s0] .. offsets[s1]).  Returns the whole table
+    [4^k, num_seqs] on every rank: the columns are all-gathered (padded to the widest shard, one collective)."""
+    import torch
+    dist = _dist()
+    n = len(offsets) - 1
+    cuts = [shard_seqs(offsets, r, world) for r in range(world)]
+    s0, s1 = cuts[rank]
+    local = count_seqs(s0, s1)
+    if world == 1 or not dist.is_initialized():
+        return local
+    nk = local.shape[0]
+    widest = max(max(c[1] - c[0] for c in cuts), 1)
+    padded = torch.zeros((nk, widest), dtype=local.dtype, device=local.device)
+    if s1 > s0:
+        padded[:, : s1 - s0] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    out = torch.cat([parts[r][:, : cuts[r][1] - cuts[r][0]] for r in range(world)], dim=1).contiguous()
+    assert out.shape == (nk, n)
+    return out
 
 
 def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):

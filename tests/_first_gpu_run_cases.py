@@ -298,3 +298,17 @@ def test_nccl_range_sharded_radix():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "NCCL_RADIX_WORKER_OK world=%d" % world in r.stdout
+
+
+def test_nccl_per_seq_sharded():
+    """multi-GPU (>= 2 GPUs visible), per-sequence mode of SURVEY §8e: sequences sharded, columns all-gathered, distances"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (tests/test_sharding_gloo.py runs the same worker with gloo + emulator kernels)")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+           "--master-addr", "127.0.0.1", "--master-port", "29662", os.path.join(ROOT, "tests", "_nccl_perseq_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "NCCL_PERSEQ_WORKER_OK world=%d" % world in r.stdout

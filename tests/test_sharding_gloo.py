@@ -42,6 +42,38 @@ def test_nccl_radix_worker_dry_run():
     assert "NCCL_RADIX_WORKER_OK world=2" in r.stdout
 
 
+def test_nccl_perseq_worker_dry_run():
+    """SURVEY §8e, per-sequence mode: the GPU worker (tests/_nccl_perseq_worker.py: sequences sharded at sequence
+    starts, kc_count_per_seq per rank, all-gather of the columns, the distance step on the gathered table), unmodified,
+    on the CPU with two ranks: emulator library + torch CUDA stand-ins + gloo"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29659", os.path.join(ROOT, "tests", "emu", "run_under_shim.py"),
+           os.path.join(ROOT, "tests", "_nccl_perseq_worker.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="1", KC_EMU_SMS="4", KC_NCCL_PERSEQ_CASES="23:3000:3,7:2000:5,2:500:4,1:300:2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "NCCL_PERSEQ_WORKER_OK world=2" in r.stdout
+
+
+def test_shard_seqs_cover(kmerlib):
+    """sequence shards: contiguous, disjoint, cover all sequences, cut at sequence starts, near-equal bytes"""
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 2, 7, 100, 1000):
+        lens = rng.integers(1, 5000, n)
+        offs = np.cumsum(np.concatenate([[0], lens + 1])).astype(np.int64)
+        for world in (1, 2, 3, 8):
+            prev = 0
+            sizes = []
+            for r in range(world):
+                s0, s1 = kmerlib.shard_seqs(offs, r, world)
+                assert s0 == prev and s1 >= s0
+                prev = s1
+                sizes.append(int(offs[s1] - offs[s0]) if n else 0)
+            assert prev == n
+            if n >= 100:   # no shard more than one sequence away from its fair share
+                assert max(sizes) <= offs[-1] / world + 5001 * 2, (n, world, sizes)
+
+
 def test_mix64_np_matches_engine(kmerlib, oracle):
     from kmerb200 import distributed as D
     xs = np.array([0, 1, 0xDEADBEEF, (1 << 62) - 1, 12345678901234567], dtype=np.uint64)

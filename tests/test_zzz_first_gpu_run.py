@@ -37,6 +37,7 @@ CASES = [
     "test_host_packed_count",
     "test_gpu_fasta_parser",
     "test_nccl_range_sharded_radix",
+    "test_nccl_per_seq_sharded",
 ]
 
 
