@@ -611,8 +611,8 @@ int kc_import_seqs(const char* path, int mode, long max_seqs, kc_seqset** out) {
 
 void kc_seqset_free(kc_seqset* s) {
     if (!s) return;
-    if (s->owner) {
-        DeviceGuard dg(s->owner->device);
+    if (s->device >= 0) {  // the ctx that made the device copies may already be destroyed: only its device index is used
+        DeviceGuard dg(s->device);
         if (s->d_data) cudaFree(s->d_data);
         if (s->d_offsets) cudaFree(s->d_offsets);
     }
@@ -624,13 +624,12 @@ uint64_t kc_seqset_nbytes(const kc_seqset* s) { return s ? s->data_len : 0; }
 const char* kc_seqset_data(const kc_seqset* s) {
     if (!s) return nullptr;
     // a set parsed on the GPU (kc_import_seqs_device) fetches its host image on first use
-    if (!s->data && s->d_data && s->owner && s->data_len) {
+    if (!s->data && s->d_data && s->device >= 0 && s->data_len) {
         kc_seqset* m = const_cast<kc_seqset*>(s);
-        DeviceGuard dg(m->owner->device);
+        DeviceGuard dg(m->device);
         char* h = (char*)malloc(m->data_len + 16);
         if (!h) return nullptr;
-        if (cudaMemcpyAsync(h, m->d_data, m->data_len, cudaMemcpyDeviceToHost, m->owner->stream) != cudaSuccess ||
-            cudaStreamSynchronize(m->owner->stream) != cudaSuccess) {
+        if (cudaMemcpy(h, m->d_data, m->data_len, cudaMemcpyDeviceToHost) != cudaSuccess) {  // synchronous: no ctx stream needed
             cudaGetLastError();
             free(h);
             return nullptr;
@@ -650,6 +649,7 @@ int kc_seqset_to_device(kc_ctx* ctx, kc_seqset* s, const char** d_data, const in
     DeviceGuard dg(ctx->device);
     if (!s->d_data) {
         s->owner = ctx;
+        s->device = ctx->device;
         KC_CUDA(ctx, cudaMalloc(&s->d_data, s->data_len ? s->data_len : 1));
         KC_CUDA(ctx, cudaMalloc(&s->d_offsets, s->offsets.size() * sizeof(int64_t)));
         KC_CUDA(ctx, cudaMemcpyAsync(s->d_data, s->data, s->data_len, cudaMemcpyHostToDevice, ctx->stream));

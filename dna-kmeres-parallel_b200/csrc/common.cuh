@@ -64,8 +64,10 @@ struct kc_seqset {
     std::vector<int64_t> offsets;   // num_seqs + 1
     ~kc_seqset() { free(data); }
     uint32_t num_seqs = 0;
-    // device copies
+    // device copies.  `device` is recorded when they are made: kc_seqset_free / kc_seqset_data must not
+    // dereference `owner`, which the caller may have destroyed first (kc_ctx_destroy before kc_seqset_free)
     kc_ctx* owner = nullptr;
+    int device = -1;
     char* d_data = nullptr;
     int64_t* d_offsets = nullptr;
 };
@@ -73,6 +75,7 @@ struct kc_seqset {
 // result of a sparse count: distinct codes ascending + their counts, both in device memory
 struct kc_sparse {
     kc_ctx* ctx = nullptr;
+    int device = -1;   // recorded at creation: kc_sparse_free does not dereference ctx (it may be gone)
     uint64_t size = 0;
     uint64_t* d_keys = nullptr;
     uint32_t* d_counts = nullptr;

@@ -1274,11 +1274,13 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         return kc_dense_partition_wide(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream);
     }
     const bool defer = (algo == KC_DENSE_PARTITION_DEFER || algo == KC_DENSE_PARTITION_DEFER_PAIR || algo == KC_DENSE_PARTITION_DEFER_TRIO);
-    const int pair = (algo == KC_DENSE_PARTITION_PAIR || algo == KC_DENSE_PARTITION_DEFER_PAIR)   ? 1
-                     : (algo == KC_DENSE_PARTITION_TRIO || algo == KC_DENSE_PARTITION_DEFER_TRIO) ? 2
-                                                                                                  : 0;
+    // KC_DENSE_AUTO at k = 12 takes the two-increment count (measured on B200, 3.1 Gbp: count pass 1.33 -> 0.83 ms,
+    // BENCH_r01 config.probe); KC_DENSE_PARTITION stays the five-sub-table count so that the two can be compared.
+    const int pair = (algo == KC_DENSE_PARTITION_PAIR || algo == KC_DENSE_PARTITION_DEFER_PAIR) ? 1
+                     : (algo == KC_DENSE_PARTITION_TRIO || algo == KC_DENSE_PARTITION_DEFER_TRIO || (algo == KC_DENSE_AUTO && k == 12)) ? 2
+                                                                                                                                        : 0;
     if (pair && k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_PAIR/TRIO are built for k = 12 (k=%d)", k);
-    if (defer || pair) algo = KC_DENSE_PARTITION;
+    if (defer || (pair && algo != KC_DENSE_AUTO)) algo = KC_DENSE_PARTITION;
     DeviceGuard dg(ctx->device);
     if (nbytes < (uint64_t)k) return KC_OK;
     const uint64_t nwin = nbytes - k + 1;
@@ -1292,8 +1294,9 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     const bool use_part =
         can_part && (algo == KC_DENSE_PARTITION ||
                      (algo == KC_DENSE_AUTO && (win_end - win_begin) >= g_partition_min_windows));
+    // k = 8: the checksum variant is the default (B200, config 2: 0.103 -> 0.074 ms, profiles/r02_*)
     if (k == 8 && algo == KC_DENSE_AUTO && (win_end - win_begin) >= (1ull << 22))
-        return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, st, false);
+        return dense_smem16(ctx, d_data, nbytes, win_begin, win_end, d_table, st, true);
     if (use_part) {
         // PartCfg<K, A, KB, CAP>: A windows per 32-bit record (K + A - 1 <= 16 bases), KB key bits
         // inside the bases all A windows share, CAP records per chunk.  k = 12 shape measured on

@@ -309,6 +309,7 @@ extern "C" int kc_import_seqs_device(kc_ctx* ctx, const char* d_raw, const char*
     try {
         s = new kc_seqset();
         s->owner = ctx;
+        s->device = ctx->device;
         static const uint32_t tile_env = getenv("KC_INGEST_TILE") ? (uint32_t)atoi(getenv("KC_INGEST_TILE")) : 0;  // test aid
         const uint32_t tile = tile_env ? tile_env : 8192u;
         const uint64_t ntiles = (nbytes + tile - 1) / tile;

@@ -222,6 +222,7 @@ int sort_reduce_pairs(kc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_cou
     cudaStream_t st = ctx->stream;
     kc_sparse* res = new kc_sparse();
     res->ctx = ctx;
+    res->device = ctx->device;
     *out = res;
     if (n == 0) return KC_OK;
     DevBuf ks, cs, uk, uc, nr, tmp;
@@ -317,6 +318,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
     if (nwin == 0) {
         kc_sparse* r = new kc_sparse();
         r->ctx = ctx;
+        r->device = ctx->device;
         *out = r;
         return KC_OK;
     }
@@ -353,6 +355,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
                 if (unsorted) {  // hand the compacted table over as it is
                     kc_sparse* res = new kc_sparse();
                     res->ctx = ctx;
+                    res->device = ctx->device;
                     res->size = nd;
                     res->d_keys = (uint64_t*)ok.release();
                     res->d_counts = (uint32_t*)oc.release();
@@ -460,8 +463,8 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
 
 void kc_sparse_free(kc_sparse* s) {
     if (!s) return;
-    if (s->ctx) {
-        DeviceGuard dg(s->ctx->device);
+    if (s->device >= 0) {  // not s->ctx->device: the ctx may have been destroyed before its results
+        DeviceGuard dg(s->device);
         if (s->d_keys) cudaFree(s->d_keys);
         if (s->d_counts) cudaFree(s->d_counts);
     }

@@ -623,6 +623,7 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
     }
     kc_sparse* res = new kc_sparse();
     res->ctx = ctx;
+    res->device = ctx->device;
     res->size = h.total;
     *out = res;
     if (h.total == 0) return KC_OK;

@@ -1,10 +1,9 @@
-"""GPU parity cases of paths whose kernels have so far only met the oracle on the CPU
-emulator (tests/test_emu_kernels.py) — written while the round's GPU budget was spent.
-NOT collected directly (file name): tests/test_zzz_first_gpu_run.py runs every case in its
-own process with a time limit, so that a hang or a fault of a never-run kernel cannot
-take the verified tests (or the pytest process) with it."""
+"""GPU parity cases of this round's NEW kernels.  NOT collected directly (file name):
+tests/test_zzz_first_gpu_run.py runs every case in its own process with a time limit, so that a
+hang or a fault of a young kernel cannot take the other tests (or the pytest process) with it.
+KC_FIRST_RUN_SCALE < 1 shrinks every input so that the same Python runs on the CPU emulator
+(tests/emu/run_under_shim.py)."""
 import os
-import subprocess
 import sys
 
 import numpy as np
@@ -14,8 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = [pytest.mark.gpu]
 
-# KC_FIRST_RUN_SCALE < 1 shrinks every input: the Python of these cases can then be run on the CPU emulator
-# (tests/emu/run_under_shim.py) before it meets a B200; assertions that only hold at full size check FULL.
 SCALE = float(os.environ.get("KC_FIRST_RUN_SCALE", "1"))
 FULL = SCALE == 1.0
 
@@ -33,41 +30,6 @@ def to_dev(arr):
     return buf
 
 
-@pytest.mark.parametrize("k", [13, 17, 18, 21, 25, 28, 31])
-def test_sparse_radix_vs_oracle(ctx, kmerlib, oracle, k):
-    """KC_SPARSE_RADIX (1024 x 1024 partitions, the shipped shape) on shallow-coverage reads;
-    NO_FALLBACK: the radix kernels themselves must produce the result."""
-    nreads = sz(30_000) if FULL else 600
-    reads = oracle.gen_reads(0xB2000004 + k, 4_000_000, 150, 200, 0, nreads)
-    wk, wc, _ = oracle.count_sparse(reads, k)
-    sp = ctx.count_sparse(to_dev(reads), reads.size, k, kmerlib.SPARSE_RADIX | kmerlib.SPARSE_NO_FALLBACK)
-    keys, counts = sp.to_host()
-    assert len(sp) == len(wk) and (keys == wk).all() and (counts == wc).all()
-
-
-def test_sparse_radix_deep_coverage_and_fallback(ctx, kmerlib, oracle):
-    """deep coverage (counts >> 1) and an input that must overflow a leaf (one k-mer only):
-    with fallback allowed both give the oracle's result."""
-    reads = oracle.gen_reads(0xB2000004, 200_000, 150, 200, 0, 40_000 if FULL else 800)
-    poly = np.full(sz(8_000_000), ord("A"), dtype=np.uint8)  # >= 4 M windows: the radix kernels run, overflow, and the hash path recounts
-    for data, k in ((reads, 21), (reads, 31), (poly, 21)):
-        wk, wc, _ = oracle.count_sparse(data, k)
-        keys, counts = ctx.count_sparse(to_dev(data), data.size, k, kmerlib.SPARSE_RADIX).to_host()
-        assert (keys == wk).all() and (counts == wc).all()
-
-
-def test_sparse_radix_equals_hash_at_scale(ctx, kmerlib):
-    """no oracle at this size (20 M windows): the two GPU algorithms must agree exactly"""
-    nreads, k = (150_000 if FULL else 700), 21
-    reads = ctx.gen_reads(0xB2000004, 50_000_000, 150, 200, 0, nreads)
-    a = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_HASH)
-    b = ctx.count_sparse(reads, nreads * 151, k, kmerlib.SPARSE_RADIX | kmerlib.SPARSE_NO_FALLBACK)
-    ka, ca = a.to_host()
-    kb, cb = b.to_host()
-    assert len(a) == len(b) and (ka == kb).all() and (ca == cb).all()
-    assert int(ca.astype(np.int64).sum()) == nreads * (150 - k + 1)
-
-
 def _dense(ctx, kmerlib, data, k, algo):
     import torch
     table = torch.zeros(kmerlib.num_kmers(k), dtype=torch.int32, device="cuda:0")
@@ -75,240 +37,3 @@ def _dense(ctx, kmerlib, data, k, algo):
     ctx.count_dense_range(d, data.size, 0, data.size, k, table, algo=algo)
     torch.cuda.synchronize()
     return table.cpu().numpy().view(np.uint32)
-
-
-def test_k8_checksum_variant(ctx, kmerlib, oracle):
-    """KC_DENSE_SMEM16C: uniform input (no CTA repaired), one-bin input (every CTA repaired), dirty bytes"""
-    n = sz(30_000_000)
-    genome = oracle.gen_genome(0xB2000002, n, 30, 300, 8, 0, n)
-    poly = np.full(sz(8_000_000), ord("A"), dtype=np.uint8)
-    for data in (genome, poly):
-        want, _ = oracle.count_dense(data, 8)
-        got = _dense(ctx, kmerlib, data, 8, kmerlib.DENSE_SMEM16C)
-        assert (got == want).all()
-
-
-def test_partition_deferred_retry(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_DEFER at k = 9..12 against the oracle, and against the shipped path at 1 Gbp"""
-    import torch
-    n = sz(40_000_000)
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    for k in (9, 10, 11, 12):
-        want, _ = oracle.count_dense(genome, k)
-        assert (_dense(ctx, kmerlib, genome, k, kmerlib.DENSE_PARTITION_DEFER) == want).all()
-    L = sz(1 << 30)
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_DEFER)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-
-
-def test_partition_two_increment_count(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_TRIO (k = 12) against the oracle, against the shipped path at 1 Gbp, and on
-    2^26 'A's (8-bit fields wrap in partition 0: checksum + 32-bit recount)"""
-    import torch
-    n = sz(40_000_000)
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_TRIO) == want).all()
-    L = sz(1 << 30)
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_TRIO)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-    del data, a, b
-    P = sz(1 << 26)
-    poly = torch.full((P,), ord("A"), dtype=torch.uint8, device="cuda:0")
-    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(poly, P, 0, P, 12, t, algo=kmerlib.DENSE_PARTITION_TRIO)
-    torch.cuda.synchronize()
-    assert int(t[0].item()) == P - 11 and int(t.to(torch.int64).sum().item()) == P - 11
-
-
-def test_partition_combined_variants(ctx, kmerlib, oracle):
-    """algo 8 / 9 (k = 12): the deferred-retry scatter with the paired / two-increment count, against the oracle
-    and against the shipped path at 1 Gbp"""
-    import torch
-    n = sz(40_000_000)
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    L = sz(1 << 30)
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    for algo in (kmerlib.DENSE_PARTITION_DEFER_PAIR, kmerlib.DENSE_PARTITION_DEFER_TRIO):
-        assert (_dense(ctx, kmerlib, genome, 12, algo) == want).all(), algo
-        b = torch.zeros_like(a)
-        ctx.count_dense_range(data, L, 0, L, 12, b, algo=algo)
-        torch.cuda.synchronize()
-        assert bool((a == b).all()), algo
-
-
-def test_partition_wide_records(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_WIDE (k = 12, seven windows per record) against the oracle, against the shipped
-    path at 1 Gbp, and on 2^26 'A's (4-bit fields wrap: checksum + 32-bit recount)"""
-    import torch
-    n = sz(40_000_000)
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_WIDE) == want).all()
-    L = sz(1 << 30)
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_WIDE)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-    del data, a, b
-    P = sz(1 << 26)
-    poly = torch.full((P,), ord("A"), dtype=torch.uint8, device="cuda:0")
-    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(poly, P, 0, P, 12, t, algo=kmerlib.DENSE_PARTITION_WIDE)
-    torch.cuda.synchronize()
-    assert int(t[0].item()) == P - 11 and int(t.to(torch.int64).sum().item()) == P - 11
-
-
-def test_partition_paired_count(ctx, kmerlib, oracle):
-    """KC_DENSE_PARTITION_PAIR (k = 12) against the oracle, and against the shipped path at 1 Gbp;
-    2^30 'A's: partition 0's regions hold ~127 K identical records (148 regions of ~860), one 16-bit
-    field wraps, the checksum fails and the 32-bit recount runs"""
-    import torch
-    n = sz(40_000_000)
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
-    want, _ = oracle.count_dense(genome, 12)
-    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_PAIR) == want).all()
-    L = sz(1 << 30)
-    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
-    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
-    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_PAIR)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-    del data, a, b
-    P = sz(1 << 30)
-    poly = torch.full((P,), ord("A"), dtype=torch.uint8, device="cuda:0")
-    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(poly, P, 0, P, 12, t, algo=kmerlib.DENSE_PARTITION_PAIR)
-    torch.cuda.synchronize()
-    assert int(t[0].item()) == P - 11 and int(t.to(torch.int64).sum().item()) == P - 11
-
-
-def test_packed_store(ctx, kmerlib, oracle):
-    """f4: pack -> layout of main.cu:78-86 + validity bitmap; unpack inverse (invalid -> 'N'); counting
-    from the store equals counting the bytes (k = 5, 8, 12; the last case is 1.2 Gbp: it crosses the 2^30 chunk edge)"""
-    import torch
-    n = sz(5_000_003)
-    data = oracle.gen_genome(0xB2000003, n, 5, 500, 12, 0, n).copy()
-    data[1000:1100] = np.frombuffer(b"acgtN\n\0|>x", dtype=np.uint8)[np.arange(100) % 10]
-    d = to_dev(data)
-    packed, mask = ctx.pack_2bit(d, n)
-    code = np.full(256, -1, dtype=np.int64)
-    for i, ch in enumerate(b"ACGT"):
-        code[ch] = i
-    c = code[data]
-    bad = c < 0
-    q = np.concatenate([np.where(bad, 0, c).astype(np.uint8), np.zeros((-n) % 4, np.uint8)]).reshape(-1, 4)
-    want = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
-    assert (packed[: want.size].cpu().numpy() == want).all()
-    back = ctx.unpack_2bit(packed, mask, n).cpu().numpy()
-    assert (back == np.where(bad, ord("N"), data)).all()
-    for k in (5, 8, 12):
-        t = ctx.count_dense_packed(packed, mask, n, k).cpu().numpy().view(np.uint32)
-        w, _ = oracle.count_dense(data, k)
-        assert (t == w).all(), k
-    L = sz(1_200_000_000)
-    big = ctx.gen_genome(0xB2000003, L, 60, 600, 12, 0, L)
-    p2, m2 = ctx.pack_2bit(big, L)
-    a = ctx.count_dense_packed(p2, m2, L, 12)
-    b = torch.zeros_like(a)
-    ctx.count_dense_range(big, L, 0, L, 12, b)
-    torch.cuda.synchronize()
-    assert bool((a == b).all())
-
-
-def test_host_packed_count(ctx, kmerlib, oracle):
-    """kc_count_dense_host_packed (host threads pack, 0.375 B/base or less over PCIe, GPU unpacks and counts behind
-    the copies) == the oracle at 40 Mbp (k = 12, 8, 3; pinned and pageable input), == kc_count_dense_host and the
-    resident-input table at 1.2 Gbp; dirty bytes; the bytes sent are the packed bytes + the bitmap blocks that
-    hold an invalid byte (sparse slots) or the whole bitmap (slots with > 1/4 dirty blocks)"""
-    import torch
-    n = sz(40_000_000)
-    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n).copy()
-    genome[12345:12400] = np.frombuffer(b"acgtN\n\0|>x\xff", dtype=np.uint8)[np.arange(55) % 11]
-    pinned = torch.from_numpy(genome).pin_memory()
-    for k in (12, 8, 3):
-        want, _ = oracle.count_dense(genome, k)
-        for src in (pinned, genome):
-            got = ctx.count_dense_host_packed(src, k)
-            assert (got == want).all(), k
-        # <= 3 slots with one 256-byte header each; a sparse slot sends whole 4 KiB bitmap blocks, the last one may be partial
-        assert (n + 3) // 4 <= ctx.last_h2d_bytes <= (n + 3) // 4 + (n + 31) // 32 * 4 + 256 * 3 + 4096
-    assert (ctx.count_dense_host_packed(genome[:7], 12) == 0).all()
-    L = sz(1_200_000_000)
-    big = ctx.gen_genome(0xB2000003, L, 60, 600, 12, 0, L)
-    host = torch.empty(L, dtype=torch.uint8, pin_memory=True)
-    host.copy_(big)
-    a = ctx.count_dense_host_packed(host, 12, nthreads=0)
-    # ~660 N runs in 36 K bitmap blocks: the bitmap crosses the bus sparse, 0.25 + < 0.01 bytes per base in all
-    assert L // 4 <= ctx.last_h2d_bytes and (ctx.last_h2d_bytes < 0.26 * L or not FULL)
-    b = ctx.count_dense_host(host, 12)
-    c = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
-    ctx.count_dense_range(big, L, 0, L, 12, c)
-    torch.cuda.synchronize()
-    assert (a == b).all() and (a == c.cpu().numpy().view(np.uint32)).all()
-
-
-def test_gpu_fasta_parser(ctx, kmerlib, oracle, golden):
-    """f2, device side: raw FASTA bytes in HBM -> kc_import_seqs_device == the host loader; then the
-    per-sequence counts of the device-resident set == the oracle's"""
-    rng = np.random.default_rng(5)
-    recs = []
-    for i in range(30):
-        seq = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, int(rng.integers(1, sz(200_000))))].tobytes()
-        recs.append(b">chr%d test\n" % i + b"\n".join(seq[j:j + 70] for j in range(0, len(seq), 70)) + b"\n\n")
-    texts = [b"".join(recs)] + [c["fasta"].encode("latin-1") for c in golden["loader"]]
-    for text in texts:
-        for mode in (0, 1):
-            want = kmerlib.SeqSet.from_memory(text, mode, 0)
-            d_raw = to_dev(np.frombuffer(text, dtype=np.uint8)) if text else None
-            got = kmerlib.SeqSet.from_device(ctx, d_raw, text, len(text), mode)
-            assert got.num_seqs == want.num_seqs and got.ids == want.ids
-            assert got.offsets.tolist() == want.offsets.tolist() and got.data == want.data
-            got.close()
-            want.close()
-
-
-def test_nccl_range_sharded_radix():
-    """multi-GPU (>= 2 GPUs visible): scatter, all-to-all of the slabs, count per rank, vs the oracle"""
-    import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs (tests/test_sharding_gloo.py covers the host logic with gloo + emulator kernels)")
-    world = 2 if n < 4 else 4
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
-           "--master-addr", "127.0.0.1", "--master-port", "29661", os.path.join(ROOT, "tests", "_nccl_radix_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "NCCL_RADIX_WORKER_OK world=%d" % world in r.stdout
-
-
-def test_nccl_per_seq_sharded():
-    """multi-GPU (>= 2 GPUs visible), per-sequence mode of SURVEY §8e: sequences sharded, columns all-gathered, distances"""
-    import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs (tests/test_sharding_gloo.py runs the same worker with gloo + emulator kernels)")
-    world = 2 if n < 4 else 4
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
-           "--master-addr", "127.0.0.1", "--master-port", "29662", os.path.join(ROOT, "tests", "_nccl_perseq_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "NCCL_PERSEQ_WORKER_OK world=%d" % world in r.stdout

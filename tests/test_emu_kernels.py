@@ -259,13 +259,13 @@ def test_gpu_fasta_parser_on_emulator():
     run_case("ingest", 3, 20)
 
 
-@pytest.mark.skipif(not os.environ.get("KC_RUN_SLOW"), reason="45 s; set KC_RUN_SLOW=1 (run by hand after editing tests/_first_gpu_run_cases.py)")
-def test_first_gpu_run_cases_on_emulator():
-    """the GPU-only cases of tests/_first_gpu_run_cases.py themselves, inputs shrunk 500x, on the emulator library with
+@pytest.mark.skipif(not os.environ.get("KC_RUN_SLOW"), reason="45 s; set KC_RUN_SLOW=1 (run by hand after editing tests/test_gpu_parity_variants.py)")
+def test_variant_gpu_cases_on_emulator():
+    """the GPU-only cases of tests/test_gpu_parity_variants.py themselves, inputs shrunk 500x, on the emulator library with
     torch's CUDA surface replaced by CPU stand-ins: their Python has then run before it meets a B200"""
     env = dict(os.environ, KC_FIRST_RUN_SCALE="0.002", KC_SPARSE_RADIX_SHAPE="small", KC_EMU_SMS="4")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_under_shim.py"), "-m", "pytest",
-                        os.path.join(ROOT, "tests", "_first_gpu_run_cases.py"), "-m", "gpu", "-q", "-p", "no:cacheprovider"],
+                        os.path.join(ROOT, "tests", "test_gpu_parity_variants.py"), "-m", "gpu", "-q", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "18 passed, 2 skipped" in r.stdout

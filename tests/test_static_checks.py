@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILES = ["bench.py", "__graft_entry__.py", "dna-kmeres-parallel_b200/kmerb200/__init__.py",
          "dna-kmeres-parallel_b200/kmerb200/distributed.py", "tests/_nccl_worker.py", "tests/_nccl_radix_worker.py", "tests/_nccl_perseq_worker.py",
-         "tests/_gloo_worker.py", "tests/_gloo_radix_worker.py", "tests/test_gpu_parity.py", "tests/test_zzz_first_gpu_run.py", "tests/_first_gpu_run_cases.py",
+         "tests/_gloo_worker.py", "tests/_gloo_radix_worker.py", "tests/test_gpu_parity.py", "tests/test_zzz_first_gpu_run.py", "tests/_first_gpu_run_cases.py", "tests/test_gpu_parity_variants.py",
          "tests/test_multi_gpu.py", "tests/test_zz_driver_cli.py", "tools/nccl_reduce_bench.py", "tools/sanitize_smoke.py", "tests/emu/bench_dryrun.py", "tests/emu/run_under_shim.py"]
 
 

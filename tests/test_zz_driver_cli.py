@@ -44,7 +44,6 @@ def test_driver_matches_reference_distances(golden, oracle, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first B200 run pending (GPU-side FASTA parser, emulator-verified)")
 def test_driver_gpu_parse_matches_host_parse(golden, tmp_path):
     """--gpu-parse: the same distances and sums as the host-parsed run"""
     _build()
