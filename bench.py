@@ -640,6 +640,8 @@ def main():
         sname = "part_scatter_kernel"
         if args.algo == 7:
             sname, cname = "part_scatter7_kernel", "part_count7_kernel"
+        if args.algo == 10:
+            sname, cname = "part_scatter7v2_kernel", "part_count7_kernel"
         kernels = {sname: (p1, bases_launch), cname: (p2, 4 * nk)}
     else:
         kernels = {"dense_direct_kernel": (p1, bases_launch + 4 * nk)}
@@ -798,7 +800,8 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "bases": L, "kmers_per_sec": (L - k + 1) / (ms_step * 1e-3),
                        "algo": {0: "auto", 1: "direct", 2: "partition", 3: "smem16-checksum", 4: "partition-deferred-retry", 5: "partition-paired-count", 6: "partition-two-increment-count", 7: "partition-wide-records",
-                                8: "partition-deferred-retry+paired-count", 9: "partition-deferred-retry+two-increment-count"}[args.algo],
+                                8: "partition-deferred-retry+paired-count", 9: "partition-deferred-retry+two-increment-count",
+                                10: "partition-wide-records-v2"}[args.algo],
                        "launch": "CUDA graph replay" if graph is not None else "plain launches",
                        "l2": ("input %.2f GB per GPU (+ as much scratch written per step) exceeds the 126 MB L2: "
                               "no flush needed" % (nb / 1e9)) if nb > 252e6 else

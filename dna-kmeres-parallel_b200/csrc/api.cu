@@ -12,9 +12,23 @@
 #include <thread>
 #include <vector>
 
+#include <time.h>
+
 #include "common.cuh"
 
 static thread_local std::string g_last_error;
+
+void kc_trace(kc_ctx* ctx, const char* what, bool sync) {
+    static const bool on = getenv("KC_TRACE") != nullptr;
+    if (!on) return;
+    static double last = 0;
+    if (sync && ctx) cudaStreamSynchronize(ctx->stream);
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    fprintf(stderr, "kc_trace %-28s +%9.3f ms\n", what, last ? now - last : 0.0);
+    last = now;
+}
 
 int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];

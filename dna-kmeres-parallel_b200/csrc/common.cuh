@@ -90,8 +90,13 @@ int kc_dense_direct_range(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint
                           uint32_t* d_table, cudaStream_t st);
 int kc_dense_partition_wide(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
                             uint32_t* d_table, cudaStream_t st);
+int kc_dense_partition_wide2(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
+                             uint32_t* d_table, cudaStream_t st);
 
 int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...);
+// KC_TRACE=1: host wall-clock between named points of a call, on stderr (measurement aid; a point with
+// sync = true first waits for the ctx stream, so the interval before it includes the device work)
+void kc_trace(kc_ctx* ctx, const char* what, bool sync = false);
 int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes);   // ctx->scratch  >= nbytes
 int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes);  // ctx->scratch2 >= nbytes
 
@@ -248,6 +253,15 @@ __device__ __forceinline__ uint32_t smem_ld(uint32_t saddr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint64_t smem_ld64(uint32_t saddr) {
+    uint64_t r;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(saddr) : "memory");
+    return r;
+}
+// 64-bit global store of two words, 8-byte aligned
+__device__ __forceinline__ void kc_stg64(uint32_t* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
@@ -307,6 +321,16 @@ static inline void smem_st64(uint32_t saddr, uint64_t v) {
 static inline uint32_t smem_ld(uint32_t saddr) {
     emu::maybe_preempt();
     return *(uint32_t*)emu::smem_ptr(saddr, 4);
+}
+static inline uint64_t smem_ld64(uint32_t saddr) {
+    emu::maybe_preempt();
+    return *(uint64_t*)emu::smem_ptr(saddr, 8);
+}
+static inline void kc_stg64(uint32_t* p, uint32_t a, uint32_t b) {
+    emu::maybe_preempt();
+    if ((uintptr_t)p & 7) emu::fail("kc_stg64: pointer not 8-byte aligned");
+    p[0] = a;
+    p[1] = b;
 }
 static inline uint4 smem_ld128(uint32_t saddr) {
     emu::maybe_preempt();

@@ -1255,7 +1255,8 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
     if (!d_table || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     if (algo != KC_DENSE_AUTO && algo != KC_DENSE_DIRECT && algo != KC_DENSE_PARTITION && algo != KC_DENSE_SMEM16C &&
         algo != KC_DENSE_PARTITION_DEFER && algo != KC_DENSE_PARTITION_PAIR && algo != KC_DENSE_PARTITION_TRIO &&
-        algo != KC_DENSE_PARTITION_WIDE && algo != KC_DENSE_PARTITION_DEFER_PAIR && algo != KC_DENSE_PARTITION_DEFER_TRIO)
+        algo != KC_DENSE_PARTITION_WIDE && algo != KC_DENSE_PARTITION_DEFER_PAIR && algo != KC_DENSE_PARTITION_DEFER_TRIO &&
+        algo != KC_DENSE_PARTITION_WIDE2)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown dense algo %d", algo);
     if (algo == KC_DENSE_SMEM16C) {
         if (k != 8) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_SMEM16C is the k = 8 path (k=%d)", k);
@@ -1272,6 +1273,14 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         if (win_end > nbytes - 11) win_end = nbytes - 11;
         if (win_begin >= win_end) return KC_OK;
         return kc_dense_partition_wide(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream);
+    }
+    if (algo == KC_DENSE_PARTITION_WIDE2) {
+        if (k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_WIDE2 is built for k = 12 (k=%d)", k);
+        DeviceGuard dgw(ctx->device);
+        if (nbytes < 12) return KC_OK;
+        if (win_end > nbytes - 11) win_end = nbytes - 11;
+        if (win_begin >= win_end) return KC_OK;
+        return kc_dense_partition_wide2(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream);
     }
     const bool defer = (algo == KC_DENSE_PARTITION_DEFER || algo == KC_DENSE_PARTITION_DEFER_PAIR || algo == KC_DENSE_PARTITION_DEFER_TRIO);
     // KC_DENSE_AUTO at k = 12 takes the two-increment count (measured on B200, 3.1 Gbp: count pass 1.33 -> 0.83 ms,

@@ -204,6 +204,258 @@ part_scatter7_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t*
     }
 }
 
+// ---------------------------------------------------------------------------
+// Pass 1, second generation (KC_DENSE_PARTITION_WIDE2): the same 18-base records and slab layout as
+// part_scatter7_kernel, rebuilt around what the ncu captures showed.  Round 1's kernel
+// (profiles/r01_ncu_instruction_mix.txt): 339 warp instructions per 512-byte step, a quarter of them
+// control flow; 2.2 % of the records in a divergent RED fallback that costs 22 % of the instructions;
+// 2.56 x the necessary DRAM traffic.  Two earlier shapes of THIS kernel (profiles/r02_scatter7v2_history.txt):
+// fully unrolled record slots = 13.6 K instructions, 36 % of the stalls on the instruction cache, 5.05 ms;
+// rolled, warp-cooperative bin flush = issue-bound at 3227 instructions per super-step, 3.01 ms.
+//
+//   * SUPER-STEP = 7 x 512 bytes per warp = 3584 bases = exactly 512 records.  Every lane decodes its
+//     seven coalesced 16-byte blocks, the 2-bit words go through a warp-private shared-memory tile
+//     (one conflict-free store per block), and every lane reads its own 112 CONTIGUOUS bases back:
+//     exactly 16 records per lane at bit offsets 14 r.  No per-lane alignment state and no idle record
+//     slots (the kernels above run 4 or 3 slots per lane and step for 3.2 or 2.3 records).
+//   * Three warp-uniform cases per super-step: no invalid base in it (every record is whole: no validity
+//     arithmetic), every base invalid (inside an N run: nothing to do), mixed (the lane decodes the
+//     bad-base masks of its own 128 bases again; rare).
+//   * ONE shared atomic per record.  The state word of a bin is (generation << 16 | slots reserved); a
+//     record carries the parity of its generation in bit 31, so "all 16 slots written" is visible in the
+//     records themselves and the second atomic of the old protocol is gone; generation * 16 is also the
+//     bin's write position in the CTA's private region, so the cursor array and its atomic are gone too.
+//     The lane that takes slot 15 flushes the bin at once (four 128-bit shared loads, one AND/OR tree
+//     over the 16 flags — read again while a writer of this generation sits between its atomic and its
+//     store —, one store that opens the next generation, four 128-bit global stores; the flag bit travels
+//     with the record, pass 2 ignores it).
+//   * A record that meets a full bin WAITS IN A REGISTER: the lane stages it in its next record slot and
+//     lets the new record wait instead (the lane stays one record behind; no extra pass).  The waiting
+//     records get one slot of their own at the end of every super-step.  Only a failure while another
+//     record already waits is counted with global REDs (measured: < 0.5 % of the records).
+//
+// No waiting on other lanes except the flusher's re-read, and the writers it waits for never wait.
+// ---------------------------------------------------------------------------
+constexpr int W2_BLOCKS = 7;            // 16-byte blocks per lane and super-step
+constexpr int W2_TILE = 8 * 32;         // words of a warp's tile: 7 blocks + the next super-step's first one (halo)
+
+#ifdef KC_EMU
+#define KC_W2_PAUSE() emu::maybe_preempt_always()
+#else
+#define KC_W2_PAUSE() __nanosleep(20)
+#endif
+
+struct W2Stage {
+    uint32_t s_state, s_bins;   // shared-window addresses
+    uint32_t* my_slabs;         // this CTA's regions
+    uint32_t region_cap;
+    uint32_t* table;
+};
+
+// region overflow (skewed input): the 16 records of a bin are counted directly.  Rare, slow, exact.
+__device__ __noinline__ void w2_overflow(uint4 a, uint4 b, uint4 c, uint4 d, uint32_t pid, uint32_t* table) {
+    KC_STAT(9);
+    const uint32_t v[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll 1
+    for (int q = 0; q < 16; q++) wide_fallback(wide_rec(v[q] & 0x7FFFFFFFu, pid), 0x7Fu, table);
+}
+
+// the lane that completed bin `pid` (generation `gen`, records flagged `flag`) writes it out
+__device__ __forceinline__ void w2_flush(const W2Stage& c, uint32_t pid, uint32_t gen, uint32_t flag, uint32_t binaddr) {
+    uint4 v0, v1, v2, v3;
+    for (;;) {
+        v0 = smem_ld128(binaddr);
+        v1 = smem_ld128(binaddr + 16);
+        v2 = smem_ld128(binaddr + 32);
+        v3 = smem_ld128(binaddr + 48);
+        // every record's bit 31 must equal the generation's flag
+        const uint32_t all_and = v0.x & v0.y & v0.z & v0.w & v1.x & v1.y & v1.z & v1.w & v2.x & v2.y & v2.z & v2.w & v3.x & v3.y & v3.z & v3.w;
+        const uint32_t all_or = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w | v2.x | v2.y | v2.z | v2.w | v3.x | v3.y | v3.z | v3.w;
+        if ((int32_t)(flag ? all_and : ~all_or) < 0) break;
+        KC_STAT(8);  // a writer of this generation is between its atomic and its store
+        // The pause is load-bearing: with an empty retry path nvcc 12.9 compiled this loop to ONE pass without the
+        // test (the four shared loads, then the reset store: cuobjdump of the first build), and ~1e-4 of the records
+        // were flushed as zeros on a B200 while the sequentially consistent emulator saw nothing.
+        KC_W2_PAUSE();
+    }
+    smem_st(c.s_state + pid * 4, (gen + 1u) << 16);  // the next generation is open
+    const uint32_t pos = gen * WCAP;
+    if (pos + WCAP <= c.region_cap) {
+        uint4* dst = reinterpret_cast<uint4*>(c.my_slabs + (uint64_t)pid * c.region_cap + pos);  // 64-byte aligned
+        dst[0] = v0;
+        dst[1] = v1;
+        dst[2] = v2;
+        dst[3] = v3;
+    } else {
+        w2_overflow(v0, v1, v2, v3, pid, c.table);
+    }
+}
+
+// one attempt: true = the record is in its bin
+__device__ __forceinline__ bool w2_stage(const W2Stage& c, uint32_t pid, uint32_t Y) {
+    const uint32_t old = smem_atom_add(c.s_state + pid * 4, 1u);
+    const uint32_t slot = old & 0xFFFFu;
+    if (slot >= (uint32_t)WCAP) return false;
+    const uint32_t flag = (~old & 0x10000u) << 15;  // bit 31 = parity of the generation, inverted (slots start as 0)
+    const uint32_t binaddr = c.s_bins + pid * (WCAP * 4);
+    smem_st(binaddr + slot * 4, Y | flag);
+    if (slot == (uint32_t)WCAP - 1) w2_flush(c, pid, old >> 16, flag, binaddr);
+    return true;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t* __restrict__ table,
+                       uint32_t* __restrict__ slabs, uint32_t* __restrict__ counts, uint32_t region_cap) {
+    constexpr int NW = THREADS / 32;
+    KC_DYN_SMEM(uint32_t, smem);
+    // words: state[WP] | bins[WP][16] | tile[NW warps][256]
+    W2Stage c;
+    c.s_state = (uint32_t)__cvta_generic_to_shared(smem);
+    c.s_bins = c.s_state + WP * 4;
+    c.region_cap = region_cap;
+    c.table = table;
+    c.my_slabs = slabs + (uint64_t)blockIdx.x * WP * region_cap;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_tile = c.s_bins + WP * WCAP * 4 + (uint32_t)warp * (W2_TILE * 4);
+    const uint32_t s_mine = s_tile + 7u * (uint32_t)lane * 4u;  // this lane's 8 words
+    for (int b = tid; b < WP * (1 + WCAP); b += THREADS) smem[b] = 0;  // generation 0, empty; slots carry parity 0 = "not written"
+    __syncthreads();
+
+    const uint64_t nwarps = (uint64_t)gridDim.x * NW;
+    const uint64_t w = (uint64_t)blockIdx.x * NW + warp;
+    const uint64_t sb = w * nsuper / nwarps, se = (w + 1) * nsuper / nwarps;
+
+    uint32_t pend_pid = 0, pend_Y = 0;
+    bool have_pend = false;
+    // hand one record slot to the lane: the waiting record (if any) goes first and the new one waits
+    auto submit = [&](bool valid, uint32_t pid, uint32_t Y) {
+        if (have_pend) {
+            const uint32_t tp = pend_pid, ty = pend_Y;
+            pend_pid = pid;
+            pend_Y = Y;
+            pid = tp;
+            Y = ty;
+            have_pend = valid;
+            valid = true;
+        }
+        if (valid && !w2_stage(c, pid, Y)) {
+            if (have_pend) {
+                KC_STAT(2);
+                wide_fallback(wide_rec(Y, pid), 0x7Fu, table);
+            } else {
+                KC_STAT(0);
+                pend_pid = pid;
+                pend_Y = Y;
+                have_pend = true;
+            }
+        }
+    };
+
+    if (sb < se) {
+        const uint4* ptr = base + sb * (W2_BLOCKS * 32) + lane;
+        Decoded16 carry = kc_decode16(kc_ldg_stream(ptr));  // block 0 of the first super-step
+        uint4 raw[W2_BLOCKS];
+#pragma unroll
+        for (int j = 0; j < W2_BLOCKS; j++) raw[j] = kc_ldg_stream(ptr + 32 * (j + 1));
+        for (uint64_t s = sb; s < se; s++) {
+            // decode blocks 1..7 of this super-step (block 7 = block 0 of the next one: halo now, carry later) and
+            // refill every register with the block the NEXT iteration decodes: seven loads per lane stay in flight
+            // for a whole super-step
+            uint32_t anybad = carry.bad, allbad = carry.bad;
+            smem_st(s_tile + lane * 4, carry.packed);
+#pragma unroll
+            for (int j = 0; j < W2_BLOCKS; j++) {
+                const Decoded16 d = kc_decode16(raw[j]);
+                raw[j] = kc_ldg_stream(ptr + 32 * (j + 1 + W2_BLOCKS));
+                smem_st(s_tile + ((j + 1) * 32 + lane) * 4, d.packed);
+                anybad |= d.bad;
+                if (j < W2_BLOCKS - 1) allbad &= d.bad;
+                if (j == W2_BLOCKS - 1) carry = d;
+            }
+            const uint4* const blk = ptr + 6 * lane;  // = base + s * 224 + 7 * lane: this lane's eight CONSECUTIVE blocks
+            ptr += W2_BLOCKS * 32;
+            const bool clean = !__any_sync(0xffffffffu, anybad != 0);
+            // inside an N run: no window that starts in this super-step is valid
+            if (!clean && __all_sync(0xffffffffu, allbad == 0xFFFFu)) continue;
+            __syncwarp();
+            uint64_t B01 = 0, B23 = 0;
+            if (!clean) {
+                KC_STAT(10);
+                // validity of the 112 + 16 bases behind this lane's first base: the decoder runs again on the lane's
+                // own region, this time for the masks (a mixed super-step is rare: ~1.5 % of the bench genome)
+                uint32_t h[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) h[q] = kc_decode16(kc_ldg_stream(blk + q)).bad;
+                B01 = (uint64_t)(h[0] | (h[1] << 16)) | ((uint64_t)(h[2] | (h[3] << 16)) << 32);
+                B23 = (uint64_t)(h[4] | (h[5] << 16)) | ((uint64_t)(h[6] | (h[7] << 16)) << 32);
+            }
+            // The lane's 16 records start at bit 14 r of the 256-bit string tile[7 lane .. 7 lane + 7].  ONE rolled
+            // loop body (two records) keeps the kernel small: three conflict-free shared loads per two records
+            // instead of eight registers and 16 copies of the staging code.
+#pragma unroll 1
+            for (int i = 0; i < 8; i++) {
+                const uint32_t bit = 28u * (uint32_t)i;  // warp-uniform
+                const uint32_t wa = s_mine + (bit >> 5) * 4u;
+                uint32_t sh = bit & 31u;
+                uint32_t w0 = smem_ld(wa), w1 = smem_ld(wa + 4), w2 = smem_ld(wa + 8);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (sh >= 32u) {  // warp-uniform
+                        sh -= 32u;
+                        w0 = w1;
+                        w1 = w2;
+                        w2 = 0;  // (the second record never reaches past w2: 31 + 14 + 36 <= 96)
+                    }
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh);
+                    const uint32_t hi = __funnelshift_r(w1, w2, sh) & 0xFu;  // bases 16, 17
+                    bool valid = true;
+                    if (!clean) {
+                        // 18 bad bits at bit 7r of B, then "any bad base among 12" per window start
+                        const uint32_t o = 7u * (uint32_t)(2 * i + h);  // <= 105
+                        const uint64_t cur = (o & 64u) ? B23 : B01, nxt = (o & 64u) ? 0ull : B23;
+                        const uint32_t os = o & 63u;
+                        uint32_t bb = (uint32_t)(cur >> os);
+                        if (os > 46u) bb |= (uint32_t)(nxt << (64u - os));
+                        bb &= 0x3FFFFu;
+                        const uint32_t y2 = bb | (bb >> 1), y4 = y2 | (y2 >> 2), y8 = y4 | (y4 >> 4);
+                        const uint32_t okr = ~(y8 | (y4 >> 8)) & 0x7Fu;
+                        valid = okr == 0x7Fu;
+                        if (!valid && okr) wide_fallback((uint64_t)lo | ((uint64_t)hi << 32), okr, table);  // next to an invalid base
+                    }
+                    submit(valid, (lo >> 13) & (WP - 1), (lo & 0x1FFFu) | ((lo >> 24) << 13) | (hi << 21));
+                    sh += 14u;
+                }
+            }
+            if (__any_sync(0xffffffffu, have_pend)) submit(false, 0, 0);  // a slot for the records that wait
+            __syncwarp();  // every lane has read its words: the tile may be overwritten
+        }
+    }
+    if (have_pend) {  // (only after an all-N tail)
+        if (!w2_stage(c, pend_pid, pend_Y)) wide_fallback(wide_rec(pend_Y, pend_pid), 0x7Fu, table);
+    }
+    // final flush of the partially filled bins, then publish the region lengths
+    __syncthreads();
+    for (int b = warp; b < WP; b += NW) {
+        const uint32_t st = smem[b];
+        uint32_t n = st & 0xFFFFu;  // < WCAP: a full bin was flushed by the lane that filled it
+        if (n > (uint32_t)WCAP) n = WCAP;
+        const uint32_t pos = (st >> 16) * WCAP;
+        const uint32_t base_off = b * region_cap;
+        uint32_t stored = pos < region_cap ? pos : region_cap;
+        if ((uint32_t)lane < n) {
+            const uint32_t r = smem[WP + b * WCAP + lane] & 0x7FFFFFFFu;
+            if (pos + WCAP <= region_cap)
+                c.my_slabs[base_off + pos + lane] = r;
+            else
+                wide_fallback(wide_rec(r, b), 0x7Fu, table);
+        }
+        if (pos + WCAP <= region_cap) stored = pos + n;
+        if (lane == 0) counts[(uint64_t)b * gridDim.x + blockIdx.x] = stored;
+    }
+}
+
 __device__ __forceinline__ uint32_t nibsum(uint32_t v) {  // sum of the eight 4-bit fields
     const uint32_t a = (v & 0x0F0F0F0Fu) + ((v >> 4) & 0x0F0F0F0Fu);  // bytes <= 30
     return (a * 0x01010101u) >> 24;                                    // <= 120
@@ -430,6 +682,68 @@ int kc_dense_partition_wide(kc_ctx* ctx, const char* d_data, uint64_t nbytes, ui
     KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter7_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     KC_LAUNCH(part_scatter7_kernel<DEPTH>, grid1, 1024, smem1, st, base, ngroups, d_table, slabs, counts, (uint32_t)cap);
     KC_LAUNCH_CHECK(ctx, "part_scatter7_kernel");
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
+    const int grid2 = ctx->sm_count < WP ? ctx->sm_count : WP;
+    KC_CUDA(ctx, cudaFuncSetAttribute(part_count7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    KC_LAUNCH(part_count7_kernel, grid2, 1024, smem2, st, d_table, slabs, counts, (uint32_t)cap, (uint32_t)grid1, work);
+    KC_LAUNCH_CHECK(ctx, "part_count7_kernel");
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[2], st));
+    const bool timing = ctx->timing;
+    ctx->timing = false;
+    rc = KC_OK;
+    if (head_end > win_begin) rc = kc_dense_direct_range(ctx, d_data, nbytes, win_begin, head_end, WK, d_table, st);
+    if (!rc && tail_begin < win_end) rc = kc_dense_direct_range(ctx, d_data, nbytes, tail_begin, win_end, WK, d_table, st);
+    ctx->timing = timing;
+    if (timing) ctx->timed_kernels = 2;
+    return rc;
+}
+
+// Host side of KC_DENSE_PARTITION_WIDE2: part_scatter7v2_kernel + part_count7_kernel.  The interior is a whole
+// number of super-steps (7 groups of 512 bytes = 512 records), so the records tile it exactly.
+int kc_dense_partition_wide2(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
+                             uint32_t* d_table, cudaStream_t st) {
+    const ScanGeom g = kc_make_geom(d_data, nbytes, win_begin, win_end, WK);
+    const uint64_t G0 = (max(g.lo, g.wlo) + 511) >> 9;
+    const uint64_t lim = min(g.hi, g.whi);
+    const uint64_t Gl = lim >> 9;
+    // the last warp prefetches one super-step + one block past its last super-step: 2 * 7 + 2 groups stay readable
+    const uint64_t G1 = Gl > (uint64_t)(2 * W2_BLOCKS + 2) ? Gl - (2 * W2_BLOCKS + 2) : 0;
+    if (G1 <= G0 + 64) return kc_dense_direct_range(ctx, d_data, nbytes, win_begin, win_end, WK, d_table, st);
+    const uint64_t nsuper = (G1 - G0) / W2_BLOCKS;
+    const uint64_t ngroups = nsuper * W2_BLOCKS;
+    const uint64_t nrec = nsuper * 512;  // records start at (G0<<9) + 7 m and tile the interior groups exactly
+    const uint64_t shift = g.lo;
+    const uint64_t head_end = (G0 << 9) - shift;
+    const uint64_t tail_begin = ((G0 + ngroups) << 9) - shift;
+    const uint64_t want = (nsuper + 31) / 32;
+    const int grid1 = (int)(want > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want);
+    uint64_t cap = nrec / ((uint64_t)WP * grid1);
+    cap = cap + cap / 8 + 4 * WCAP;
+    cap = (cap + 31) / 32 * 32;
+    if ((uint64_t)WP * cap >= (1ull << 32) || cap / WCAP >= 65535)  // the bin generation (= chunks written) is a 16-bit field
+        return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "partition region too large");
+    const size_t nregions = (size_t)WP * grid1;
+    const size_t ctl_pad = ((nregions + 64) * sizeof(uint32_t) + 255) & ~(size_t)255;
+    int rc = kc_scratch_reserve(ctx, ctl_pad + nregions * cap * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t* counts = (uint32_t*)ctx->scratch;
+    uint32_t* work = counts + nregions;
+    uint32_t* slabs = (uint32_t*)((char*)ctx->scratch + ctl_pad);
+    KC_CUDA(ctx, cudaMemsetAsync(work, 0, 64 * sizeof(uint32_t), st));
+    static const int threads_env = getenv("KC_W2_THREADS") ? atoi(getenv("KC_W2_THREADS")) : 0;  // measurement aid
+    const int threads = threads_env == 512 ? 512 : 1024;
+    const size_t smem1 = (size_t)(WP + WP * WCAP + (threads / 32) * W2_TILE) * sizeof(uint32_t);
+    const size_t smem2 = 57344 * sizeof(uint32_t);
+    const uint4* base = g.abase + (G0 << 5);
+    if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
+    if (threads == 512) {
+        KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter7v2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        KC_LAUNCH(part_scatter7v2_kernel<512>, grid1, 512, smem1, st, base, nsuper, d_table, slabs, counts, (uint32_t)cap);
+    } else {
+        KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter7v2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        KC_LAUNCH(part_scatter7v2_kernel<1024>, grid1, 1024, smem1, st, base, nsuper, d_table, slabs, counts, (uint32_t)cap);
+    }
+    KC_LAUNCH_CHECK(ctx, "part_scatter7v2_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
     const int grid2 = ctx->sm_count < WP ? ctx->sm_count : WP;
     KC_CUDA(ctx, cudaFuncSetAttribute(part_count7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

@@ -401,9 +401,41 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
                 }
             }
             __syncthreads();
-            // thread t owns sub-bucket t = s_sorted[begin, begin+cnt): insertion sort, count runs
-            uint32_t runs = 0;
-            if (cnt) {
+            // thread t owns sub-bucket t = s_sorted[begin, begin+cnt).
+            // A leaf of deep-coverage reads holds ~coverage copies of every genomic k-mer, and all copies of a k-mer
+            // sit in ONE sub-bucket: plain insertion sort is quadratic in exactly the sub-buckets that are large
+            // (config 4, 30x: the slowest thread of a leaf ran ~1000-3000 shift steps while the average one ran 30;
+            // sp_leaf_kernel took 871 of the path's 973 ms).  So the sub-bucket is not sorted but COLLAPSED: the
+            // spare high bits of a record (r2bits < 8 sizeof(R2T)) hold "copies - 1", and each element is either
+            // merged into its key's entry or inserted into the sorted list of DISTINCT keys, whose length is what
+            // the shift cost now depends on (1-3 per sub-bucket at any coverage).  The list is built in place at the
+            // front of the sub-bucket (entry count <= elements consumed).  A saturated entry simply gets a sibling
+            // entry of the same key behind it; the run-length pass below merges equal neighbours.  Records that fill
+            // all bits of R2T (spare < 4) keep the plain insertion sort.
+            constexpr int RBITS = 8 * (int)sizeof(R2T);
+            const int spare = RBITS - r2bits;
+            const bool collapse = spare >= 4;
+            const R2T keymask = (R2T)r2mask;
+            const R2T one = collapse ? ((R2T)1 << r2bits) : (R2T)0;
+            const R2T cmax = collapse ? (R2T)(~keymask) : (R2T)0;  // count field all ones
+            uint32_t nent = cnt;  // entries of this sub-bucket after the pass
+            if (cnt && collapse) {
+                uint32_t nd = 0;
+                for (uint32_t a = 0; a < cnt; a++) {
+                    const R2T v = s_sorted[begin + a] & keymask;
+                    uint32_t b = nd;
+                    R2T e = 0;
+                    while (b > 0 && ((e = s_sorted[begin + b - 1]) & keymask) > v) b--;
+                    if (b > 0 && (e & keymask) == v && (e & cmax) != cmax) {
+                        s_sorted[begin + b - 1] = e + one;
+                    } else {
+                        for (uint32_t c = nd; c > b; c--) s_sorted[begin + c] = s_sorted[begin + c - 1];
+                        s_sorted[begin + b] = v;
+                        nd++;
+                    }
+                }
+                nent = nd;
+            } else if (cnt) {
                 for (uint32_t a = begin + 1; a < begin + cnt; a++) {
                     const R2T v = s_sorted[a];
                     uint32_t b = a;
@@ -413,8 +445,12 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
                     }
                     s_sorted[b] = v;
                 }
+            }
+            uint32_t runs = 0;
+            if (cnt) {
                 runs = 1;
-                for (uint32_t a = begin + 1; a < begin + cnt; a++) runs += (s_sorted[a] != s_sorted[a - 1]) ? 1u : 0u;
+                for (uint32_t a = begin + 1; a < begin + nent; a++)
+                    runs += ((s_sorted[a] & keymask) != (s_sorted[a - 1] & keymask)) ? 1u : 0u;
             }
             uint32_t leaf_runs;
             const uint32_t off = block_excl_scan(runs, s_warp, &leaf_runs);
@@ -433,18 +469,21 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
             if (cnt && base + leaf_runs <= out_cap) {
                 const uint64_t hi = ((uint64_t)p1 << r1bits) | ((uint64_t)p2 << r2bits);
                 uint64_t o = base + off;
-                R2T cur = s_sorted[begin];
-                uint32_t c = 1;
-                for (uint32_t a = begin + 1; a < begin + cnt; a++) {
-                    const R2T v = s_sorted[a];
+                R2T e0 = s_sorted[begin];
+                R2T cur = e0 & keymask;
+                uint32_t c = 1u + (uint32_t)((uint64_t)(e0 & cmax) >> (collapse ? r2bits : 0));
+                for (uint32_t a = begin + 1; a < begin + nent; a++) {
+                    const R2T ev = s_sorted[a];
+                    const R2T v = ev & keymask;
+                    const uint32_t cv = 1u + (uint32_t)((uint64_t)(ev & cmax) >> (collapse ? r2bits : 0));
                     if (v != cur) {
                         tmp_keys[o] = hi | (uint64_t)cur;
                         tmp_counts[o] = c;
                         o++;
                         cur = v;
-                        c = 1;
+                        c = cv;
                     } else {
-                        c++;
+                        c += cv;
                     }
                 }
                 tmp_keys[o] = hi | (uint64_t)cur;
@@ -595,11 +634,13 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
     const uint64_t most = (uint64_t)nsrc * plan->max_windows + 1024;
     if (out_cap > most) out_cap = most;
     if (out_cap < 1024) return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: no device memory left for the run list");
+    kc_trace(ctx, "count: enter", true);
     DevMem tkeys, tcounts;
     if (tkeys.alloc(out_cap * 8) || tcounts.alloc(out_cap * 4)) {
         cudaGetLastError();
         return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: out of device memory for the run list");
     }
+    kc_trace(ctx, "count: run-list alloc");
     KC_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(SpCtl), st));
     KC_CUDA(ctx, cudaMemsetAsync(leaf_n, 0, nleaves * 4, st));
     constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
@@ -617,6 +658,7 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
     SpCtl h;
     KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
     KC_CUDA(ctx, cudaStreamSynchronize(st));
+    kc_trace(ctx, "count: leaf + scan kernels");
     if (h.failed) {
         *failed = (int)h.failed;
         return KC_OK;
@@ -634,10 +676,12 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
         *out = nullptr;
         return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: out of device memory for %llu k-mers", h.total);
     }
+    kc_trace(ctx, "count: result alloc");
     KC_LAUNCH(sp_gather_kernel, ctx->sm_count * 8, 256, 0, st, leaf_n, leaf_base, leaf_off, nleaves, (const uint64_t*)tkeys.p,
               (const uint32_t*)tcounts.p, (uint64_t*)fk.p, (uint32_t*)fc.p);
     KC_LAUNCH_CHECK(ctx, "sp_gather_kernel");
     KC_CUDA(ctx, cudaStreamSynchronize(st));
+    kc_trace(ctx, "count: gather kernel");
     res->d_keys = (uint64_t*)fk.release();
     res->d_counts = (uint32_t*)fc.release();
     return KC_OK;
@@ -779,8 +823,11 @@ int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_
     if (rc) return rc;
     void* slabs = ctx->scratch;
     uint32_t* counts = (uint32_t*)((char*)ctx->scratch + pad((size_t)plan.slab_bytes));
+    kc_trace(ctx, "radix: plan + scratch", true);
     rc = kc_sparse_radix_scatter(ctx, d_data, nbytes, &plan, slabs, counts);
+    kc_trace(ctx, "radix: scatter");
     if (rc == KC_OK) rc = kc_sparse_radix_count(ctx, &plan, slabs, counts, 1, 0, plan.partitions, out);
+    kc_trace(ctx, "radix: count (incl. frees)", true);
     if (rc == KC_ERR_TABLE_FULL) {  // an overflow: the error text says which; the caller falls back
         *failed = 1;
         return KC_OK;

@@ -21,6 +21,7 @@ DENSE_AUTO, DENSE_DIRECT, DENSE_PARTITION = 0, 1, 2
 DENSE_SMEM16C, DENSE_PARTITION_DEFER, DENSE_PARTITION_PAIR, DENSE_PARTITION_TRIO = 3, 4, 5, 6
 DENSE_PARTITION_WIDE = 7  # first B200 run pending; never chosen by DENSE_AUTO
 DENSE_PARTITION_DEFER_PAIR, DENSE_PARTITION_DEFER_TRIO = 8, 9  # the scatter of 4 with the count of 5 / 6
+DENSE_PARTITION_WIDE2 = 10  # seven windows per record, second-generation scatter (cooperative flush)
 SPARSE_HASH, SPARSE_SORT, SPARSE_RADIX = 0, 1, 2
 SPARSE_UNSORTED = 0x100
 SPARSE_NO_FALLBACK = 0x200

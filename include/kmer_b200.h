@@ -199,6 +199,9 @@ KC_API int kc_count_dense_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes
                                       2 shared increments instead of 5                           */
 #define KC_DENSE_PARTITION_DEFER_PAIR 8  /* k = 12: the scatter of 4 with the count of 5 */
 #define KC_DENSE_PARTITION_DEFER_TRIO 9  /* k = 12: the scatter of 4 with the count of 6 */
+#define KC_DENSE_PARTITION_WIDE2 10  /* k = 12: seven windows per record, second-generation scatter: 16 records per
+                                        lane at static offsets, one shared atomic per record, warp-cooperative
+                                        64-byte bin flush                                         */
 KC_API int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
                                       uint64_t win_begin, uint64_t win_end, int k,
                                       uint32_t* d_table, int algo, void* stream);

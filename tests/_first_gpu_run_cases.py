@@ -37,3 +37,39 @@ def _dense(ctx, kmerlib, data, k, algo):
     ctx.count_dense_range(d, data.size, 0, data.size, k, table, algo=algo)
     torch.cuda.synchronize()
     return table.cpu().numpy().view(np.uint32)
+
+
+def test_partition_wide2(ctx, kmerlib, oracle):
+    """KC_DENSE_PARTITION_WIDE2 (k = 12; 16 records per lane and super-step, one shared atomic per record,
+    warp-cooperative bin flush) against the oracle (genome with N runs, dirty bytes, unaligned pointer),
+    against the five-sub-table partition path at 1 Gbp, and on 2^26 'A's (every record into one bin:
+    retries, region overflow, nibble wraps -> 32-bit recount)"""
+    import torch
+    n = sz(40_000_000)
+    genome = oracle.gen_genome(0xB2000003, n, 40, 400, 12, 0, n)
+    want, _ = oracle.count_dense(genome, 12)
+    assert (_dense(ctx, kmerlib, genome, 12, kmerlib.DENSE_PARTITION_WIDE2) == want).all()
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTACGTNacgt\n\0|>", dtype=np.uint8)
+    dirty = alpha[rng.integers(0, alpha.size, sz(30_000_000))]
+    want, _ = oracle.count_dense(dirty, 12)
+    table = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    d = to_dev(np.concatenate([np.zeros(5, np.uint8), dirty]))
+    ctx.count_dense_range(d[5:], dirty.size, 0, dirty.size, 12, table, algo=kmerlib.DENSE_PARTITION_WIDE2)
+    torch.cuda.synchronize()
+    assert (table.cpu().numpy().view(np.uint32) == want).all()
+    L = sz(1 << 30)
+    data = ctx.gen_genome(0xB2000003, L, 300, 3000, 12, 0, L)
+    a = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    b = torch.zeros_like(a)
+    ctx.count_dense_range(data, L, 0, L, 12, a, algo=kmerlib.DENSE_PARTITION)
+    ctx.count_dense_range(data, L, 0, L, 12, b, algo=kmerlib.DENSE_PARTITION_WIDE2)
+    torch.cuda.synchronize()
+    assert bool((a == b).all())
+    del data, a, b
+    P = sz(1 << 26)
+    poly = torch.full((P,), ord("A"), dtype=torch.uint8, device="cuda:0")
+    t = torch.zeros(kmerlib.num_kmers(12), dtype=torch.int32, device="cuda:0")
+    ctx.count_dense_range(poly, P, 0, P, 12, t, algo=kmerlib.DENSE_PARTITION_WIDE2)
+    torch.cuda.synchronize()
+    assert int(t[0].item()) == P - 11 and int(t.to(torch.int64).sum().item()) == P - 11

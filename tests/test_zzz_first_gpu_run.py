@@ -22,6 +22,7 @@ FILE_BUDGET_S = 900      # all cases together: a systematic hang must not eat th
 _state = {"t0": None, "gpu_lost": False}
 
 CASES = [
+    "test_partition_wide2",
 ]
 
 
