@@ -221,20 +221,17 @@ part_scatter7_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t*
 //   * Three warp-uniform cases per super-step: no invalid base in it (every record is whole: no validity
 //     arithmetic), every base invalid (inside an N run: nothing to do), mixed (the lane decodes the
 //     bad-base masks of its own 128 bases again; rare).
-//   * ONE shared atomic per record.  The state word of a bin is (generation << 16 | slots reserved); a
-//     record carries the parity of its generation in bit 31, so "all 16 slots written" is visible in the
-//     records themselves and the second atomic of the old protocol is gone; generation * 16 is also the
-//     bin's write position in the CTA's private region, so the cursor array and its atomic are gone too.
-//     The lane that takes slot 15 flushes the bin at once (four 128-bit shared loads, one AND/OR tree
-//     over the 16 flags — read again while a writer of this generation sits between its atomic and its
-//     store —, one store that opens the next generation, four 128-bit global stores; the flag bit travels
-//     with the record, pass 2 ignores it).
-//   * A record that meets a full bin WAITS IN A REGISTER: the lane stages it in its next record slot and
-//     lets the new record wait instead (the lane stays one record behind; no extra pass).  The waiting
-//     records get one slot of their own at the end of every super-step.  Only a failure while another
-//     record already waits is counted with global REDs (measured: < 0.5 % of the records).
+//   * The state word of a bin is (generation << 16 | slots reserved): generation * 16 is also the bin's write
+//     position in the CTA's private region, so the cursor array of the old kernel and its atomic are gone.  A
+//     writer reserves a slot (returning atomic), stores, and bumps done[bin] (non-returning).  The lane that
+//     takes slot 15 flushes the bin at once: it waits until done[bin] says that all 16 records of its generation
+//     are stored, reads them with four 128-bit shared loads, opens the next generation with one store and
+//     writes the 64-byte chunk with four 128-bit global stores.
+//   * A record that meets a full bin WAITS IN A REGISTER for an extra record slot at the end of the
+//     super-step.  Only a failure while another record already waits is counted with global REDs
+//     (measured: < 0.5 % of the records; the old kernel sent 2.2 % there).
 //
-// No waiting on other lanes except the flusher's re-read, and the writers it waits for never wait.
+// No waiting on other lanes except the flusher's wait for done[], and the writers it waits for never wait.
 // ---------------------------------------------------------------------------
 constexpr int W2_BLOCKS = 7;            // 16-byte blocks per lane and super-step
 constexpr int W2_TILE = 8 * 32;         // words of a warp's tile: 7 blocks + the next super-step's first one (halo)
@@ -246,8 +243,8 @@ constexpr int W2_TILE = 8 * 32;         // words of a warp's tile: 7 blocks + th
 #endif
 
 struct W2Stage {
-    uint32_t s_state, s_bins;   // shared-window addresses
-    uint32_t* my_slabs;         // this CTA's regions
+    uint32_t s_state, s_done, s_bins;   // shared-window addresses
+    uint32_t* my_slabs;                 // this CTA's regions
     uint32_t region_cap;
     uint32_t* table;
 };
@@ -257,31 +254,25 @@ __device__ __noinline__ void w2_overflow(uint4 a, uint4 b, uint4 c, uint4 d, uin
     KC_STAT(9);
     const uint32_t v[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
 #pragma unroll 1
-    for (int q = 0; q < 16; q++) wide_fallback(wide_rec(v[q] & 0x7FFFFFFFu, pid), 0x7Fu, table);
+    for (int q = 0; q < 16; q++) wide_fallback(wide_rec(v[q], pid), 0x7Fu, table);
 }
 
-// the lane that completed bin `pid` (generation `gen`, records flagged `flag`) writes it out
-__device__ __forceinline__ void w2_flush(const W2Stage& c, uint32_t pid, uint32_t gen, uint32_t flag, uint32_t binaddr) {
-    uint4 v0, v1, v2, v3;
-    for (;;) {
-        v0 = smem_ld128(binaddr);
-        v1 = smem_ld128(binaddr + 16);
-        v2 = smem_ld128(binaddr + 32);
-        v3 = smem_ld128(binaddr + 48);
-        // every record's bit 31 must equal the generation's flag
-        const uint32_t all_and = v0.x & v0.y & v0.z & v0.w & v1.x & v1.y & v1.z & v1.w & v2.x & v2.y & v2.z & v2.w & v3.x & v3.y & v3.z & v3.w;
-        const uint32_t all_or = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w | v2.x | v2.y | v2.z | v2.w | v3.x | v3.y | v3.z | v3.w;
-        if ((int32_t)(flag ? all_and : ~all_or) < 0) break;
+// the lane that completed generation `gen` of bin `pid` writes it out
+__device__ __forceinline__ void w2_flush(const W2Stage& c, uint32_t pid, uint32_t gen, uint32_t binaddr) {
+    // done[pid] counts the records STORED into the bin since the launch: generation gen is complete at 16 (gen + 1)
+    const uint32_t want = (gen + 1u) * WCAP;
+    while (smem_ld(c.s_done + pid * 4) != want) {
         KC_STAT(8);  // a writer of this generation is between its atomic and its store
-        // The pause is load-bearing: with an empty retry path nvcc 12.9 compiled this loop to ONE pass without the
-        // test (the four shared loads, then the reset store: cuobjdump of the first build), and ~1e-4 of the records
-        // were flushed as zeros on a B200 while the sequentially consistent emulator saw nothing.
+        // The pause is load-bearing: with an EMPTY retry path nvcc 12.9 compiled an earlier form of this wait to one
+        // pass without the test (cuobjdump showed the loads, then the reset store), and ~1e-4 of the records were
+        // flushed as zeros on a B200 while the sequentially consistent emulator saw nothing.
         KC_W2_PAUSE();
     }
+    const uint4 v0 = smem_ld128(binaddr), v1 = smem_ld128(binaddr + 16), v2 = smem_ld128(binaddr + 32), v3 = smem_ld128(binaddr + 48);
     smem_st(c.s_state + pid * 4, (gen + 1u) << 16);  // the next generation is open
     const uint32_t pos = gen * WCAP;
     if (pos + WCAP <= c.region_cap) {
-        uint4* dst = reinterpret_cast<uint4*>(c.my_slabs + (uint64_t)pid * c.region_cap + pos);  // 64-byte aligned
+        uint4* dst = reinterpret_cast<uint4*>(c.my_slabs + (pid * c.region_cap + pos));  // 64-byte aligned; < 2^32 words per CTA (host)
         dst[0] = v0;
         dst[1] = v1;
         dst[2] = v2;
@@ -291,15 +282,19 @@ __device__ __forceinline__ void w2_flush(const W2Stage& c, uint32_t pid, uint32_
     }
 }
 
-// one attempt: true = the record is in its bin
+// one attempt: true = the record is in its bin.  Two shared atomics per record as in part_scatter_kernel, but the
+// second one does not return (RED), nothing is ever reset but the state word, and the flusher is known from the FIRST
+// atomic — it waits for done[] instead of being chosen by it.  (A first form of this kernel carried the generation's
+// parity in bit 31 of every record and checked the 16 flags of a bin: one atomic per record, but the 16-way test was a
+// quarter of the kernel's ALU-pipe instructions, and the ALU pipe is what bounds it: profiles/r02_scatter7v2_history.txt.)
 __device__ __forceinline__ bool w2_stage(const W2Stage& c, uint32_t pid, uint32_t Y) {
     const uint32_t old = smem_atom_add(c.s_state + pid * 4, 1u);
     const uint32_t slot = old & 0xFFFFu;
     if (slot >= (uint32_t)WCAP) return false;
-    const uint32_t flag = (~old & 0x10000u) << 15;  // bit 31 = parity of the generation, inverted (slots start as 0)
     const uint32_t binaddr = c.s_bins + pid * (WCAP * 4);
-    smem_st(binaddr + slot * 4, Y | flag);
-    if (slot == (uint32_t)WCAP - 1) w2_flush(c, pid, old >> 16, flag, binaddr);
+    smem_st(binaddr + slot * 4, Y);
+    smem_red_add(c.s_done + pid * 4, 1u);  // after the store, in program order
+    if (slot == (uint32_t)WCAP - 1) w2_flush(c, pid, old >> 16, binaddr);
     return true;
 }
 
@@ -309,10 +304,11 @@ part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t
                        uint32_t* __restrict__ slabs, uint32_t* __restrict__ counts, uint32_t region_cap) {
     constexpr int NW = THREADS / 32;
     KC_DYN_SMEM(uint32_t, smem);
-    // words: state[WP] | bins[WP][16] | tile[NW warps][256]
+    // words: state[WP] | done[WP] | bins[WP][16] | tile[NW warps][256]
     W2Stage c;
     c.s_state = (uint32_t)__cvta_generic_to_shared(smem);
-    c.s_bins = c.s_state + WP * 4;
+    c.s_done = c.s_state + WP * 4;
+    c.s_bins = c.s_done + WP * 4;
     c.region_cap = region_cap;
     c.table = table;
     c.my_slabs = slabs + (uint64_t)blockIdx.x * WP * region_cap;
@@ -320,7 +316,7 @@ part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t s_tile = c.s_bins + WP * WCAP * 4 + (uint32_t)warp * (W2_TILE * 4);
     const uint32_t s_mine = s_tile + 7u * (uint32_t)lane * 4u;  // this lane's 8 words
-    for (int b = tid; b < WP * (1 + WCAP); b += THREADS) smem[b] = 0;  // generation 0, empty; slots carry parity 0 = "not written"
+    for (int b = tid; b < 2 * WP; b += THREADS) smem[b] = 0;  // generation 0, empty; nothing stored
     __syncthreads();
 
     const uint64_t nwarps = (uint64_t)gridDim.x * NW;
@@ -329,18 +325,10 @@ part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t
 
     uint32_t pend_pid = 0, pend_Y = 0;
     bool have_pend = false;
-    // hand one record slot to the lane: the waiting record (if any) goes first and the new one waits
-    auto submit = [&](bool valid, uint32_t pid, uint32_t Y) {
-        if (have_pend) {
-            const uint32_t tp = pend_pid, ty = pend_Y;
-            pend_pid = pid;
-            pend_Y = Y;
-            pid = tp;
-            Y = ty;
-            have_pend = valid;
-            valid = true;
-        }
-        if (valid && !w2_stage(c, pid, Y)) {
+    // a record that meets a full bin waits in a register for the extra slot at the end of the super-step; a second
+    // one while the first still waits is counted with global REDs
+    auto submit = [&](uint32_t pid, uint32_t Y) {
+        if (!w2_stage(c, pid, Y)) {
             if (have_pend) {
                 KC_STAT(2);
                 wide_fallback(wide_rec(Y, pid), 0x7Fu, table);
@@ -408,8 +396,9 @@ part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t
                         w1 = w2;
                         w2 = 0;  // (the second record never reaches past w2: 31 + 14 + 36 <= 96)
                     }
-                    const uint32_t lo = __funnelshift_r(w0, w1, sh);
-                    const uint32_t hi = __funnelshift_r(w1, w2, sh) & 0xFu;  // bases 16, 17
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh);   // bases 0 .. 15
+                    const uint32_t hiw = __funnelshift_r(w1, w2, sh);  // bases 16, 17 in bits [0, 4)
+                    const uint32_t hi = hiw & 0xFu;
                     bool valid = true;
                     if (!clean) {
                         // 18 bad bits at bit 7r of B, then "any bad base among 12" per window start
@@ -424,11 +413,19 @@ part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t
                         valid = okr == 0x7Fu;
                         if (!valid && okr) wide_fallback((uint64_t)lo | ((uint64_t)hi << 32), okr, table);  // next to an invalid base
                     }
-                    submit(valid, (lo >> 13) & (WP - 1), (lo & 0x1FFFu) | ((lo >> 24) << 13) | (hi << 21));
+                    // Y = record bits [0,13) | bits [24,36) << 13, built with two funnel shifts; its bits >= 25 are
+                    // whatever follows the record (pass 2 masks every index it takes from Y)
+                    const uint32_t t12 = __funnelshift_r(lo, hiw, 24);
+                    if (valid) submit((lo << 8) >> 21, __funnelshift_r(lo << 19, t12, 19));
                     sh += 14u;
                 }
             }
-            if (__any_sync(0xffffffffu, have_pend)) submit(false, 0, 0);  // a slot for the records that wait
+            if (__any_sync(0xffffffffu, have_pend)) {  // a slot for the records that wait
+                if (have_pend) {
+                    have_pend = false;
+                    submit(pend_pid, pend_Y);  // (a failure puts it back)
+                }
+            }
             __syncwarp();  // every lane has read its words: the tile may be overwritten
         }
     }
@@ -445,7 +442,7 @@ part_scatter7v2_kernel(const uint4* __restrict__ base, uint64_t nsuper, uint32_t
         const uint32_t base_off = b * region_cap;
         uint32_t stored = pos < region_cap ? pos : region_cap;
         if ((uint32_t)lane < n) {
-            const uint32_t r = smem[WP + b * WCAP + lane] & 0x7FFFFFFFu;
+            const uint32_t r = smem[2 * WP + b * WCAP + lane];
             if (pos + WCAP <= region_cap)
                 c.my_slabs[base_off + pos + lane] = r;
             else
@@ -730,19 +727,13 @@ int kc_dense_partition_wide2(kc_ctx* ctx, const char* d_data, uint64_t nbytes, u
     uint32_t* work = counts + nregions;
     uint32_t* slabs = (uint32_t*)((char*)ctx->scratch + ctl_pad);
     KC_CUDA(ctx, cudaMemsetAsync(work, 0, 64 * sizeof(uint32_t), st));
-    static const int threads_env = getenv("KC_W2_THREADS") ? atoi(getenv("KC_W2_THREADS")) : 0;  // measurement aid
-    const int threads = threads_env == 512 ? 512 : 1024;
-    const size_t smem1 = (size_t)(WP + WP * WCAP + (threads / 32) * W2_TILE) * sizeof(uint32_t);
+    // 1024 threads: the 512-thread build (126 registers, no spills) measured 8 % slower on B200
+    const size_t smem1 = (size_t)(2 * WP + WP * WCAP + 32 * W2_TILE) * sizeof(uint32_t);
     const size_t smem2 = 57344 * sizeof(uint32_t);
     const uint4* base = g.abase + (G0 << 5);
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
-    if (threads == 512) {
-        KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter7v2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        KC_LAUNCH(part_scatter7v2_kernel<512>, grid1, 512, smem1, st, base, nsuper, d_table, slabs, counts, (uint32_t)cap);
-    } else {
-        KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter7v2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        KC_LAUNCH(part_scatter7v2_kernel<1024>, grid1, 1024, smem1, st, base, nsuper, d_table, slabs, counts, (uint32_t)cap);
-    }
+    KC_CUDA(ctx, cudaFuncSetAttribute(part_scatter7v2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    KC_LAUNCH(part_scatter7v2_kernel<1024>, grid1, 1024, smem1, st, base, nsuper, d_table, slabs, counts, (uint32_t)cap);
     KC_LAUNCH_CHECK(ctx, "part_scatter7v2_kernel");
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
     const int grid2 = ctx->sm_count < WP ? ctx->sm_count : WP;
