@@ -169,8 +169,12 @@ def run_reference(args):
 
 
 def run_sparse(args):
-    """configs 4/5 (not the default bench line): sparse counting of reads, hash or sort,
-    hash-sharded all-to-all when world > 1.  --reads scales the number of reads."""
+    """configs 4/5 (not the default bench line): sparse counting of reads.  N = 1: kc_count_sparse; N > 1: reads are
+    cut by read index, KC_SPARSE_RADIX shards the result by code RANGE (one all-to-all of the level-1 slabs, every rank
+    counts the partitions it owns), KC_SPARSE_HASH by owner = mix64(code) % N (all-to-all of (code,count) pairs +
+    merge).  --reads scales the number of reads.  The line carries a full-scale self-check that does not depend on
+    the counting kernels: the multiset fingerprint of the input windows (one streaming scan per rank, summed over the
+    ranks) must equal the fingerprint of the result, and the sum of the counts the number of valid windows."""
     import torch
     import torch.distributed as dist
     import kmerb200
@@ -191,59 +195,87 @@ def run_sparse(args):
     data = ctx.gen_reads(w["seed"], w["genome"], rl, w["err_den"], r0, r1 - r0)
     nb = (r1 - r0) * (rl + 1)
     torch.cuda.synchronize()
-    algo = {"hash": kmerb200.SPARSE_HASH, "sort": kmerb200.SPARSE_SORT,
+    algo = {"auto": kmerb200.SPARSE_AUTO, "hash": kmerb200.SPARSE_HASH, "sort": kmerb200.SPARSE_SORT,
             "radix": kmerb200.SPARSE_RADIX | kmerb200.SPARSE_NO_FALLBACK}[args.sparse_algo]
     hint = args.capacity_hint
 
+    def allsum(vals):  # uint64 values as wrapping int64
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in vals], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(x) & ((1 << 64) - 1) for x in t.tolist()]
+
+    fp_in, win_in = allsum(ctx.window_fingerprint(data, nb, k))
+
     def step():
         if world == 1:
-            sp = ctx.count_sparse(data, nb, k, algo, hint)
-        else:
-            sp = D.count_sparse_sharded_gpu(ctx, data, nb, k, algo)
-        return len(sp), sp
+            return ctx.count_sparse(data, nb, k, algo, hint)
+        return D.count_sparse_sharded_gpu(ctx, data, nb, k, algo)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(1, args.warmup)):
-        n, sp = step()
+    err = None
+    try:
+        for _ in range(max(1, args.warmup)):
+            step().close()
+        barrier()
+        launches0 = ctx.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        sp = None
+        for _ in range(args.steps):
+            if sp is not None:
+                sp.close()
+            sp = step()
+        ev1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / args.steps
+        dt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3 / args.steps, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        sec, wall = float(dt[0].item()), float(dt[1].item())
+        launches = int(ctx.launch_count - launches0)
+        fp_out, sum_out, descents, ndist = allsum(list(ctx.sparse_fingerprint(sp)) + [len(sp)])
         sp.close()
-    barrier()
-    launches0 = ctx.launch_count
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        n, sp = step()
-        if _ + 1 < args.steps:
-            sp.close()
-    barrier()
-    dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-    nd = torch.tensor([n], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nd, op=dist.ReduceOp.SUM)
-    sec = float(dt.item())
+    except Exception as ex:  # out of memory at a scale that does not fit this many GPUs, ...
+        err = "%s: %s" % (type(ex).__name__, str(ex)[:300])
+    if err is not None:
+        if rank == 0:
+            emit({"metric": METRIC, "value": None, "unit": "bases/s", "n_gpus": world, "error": err,
+                  "config": {"workload": w["desc"], "k": k, "reads": nreads, "algo": args.sparse_algo}})
+        leave(world)
+        return 0
     bases = nreads * rl
     peak, peak_src = hbm_peak()
-    alg_bytes = nreads * (rl + 1) + 12 * int(nd.item())
+    alg_bytes = nreads * (rl + 1) + 12 * ndist
     if rank == 0:
         line = {
             "metric": METRIC, "value": bases / sec, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "reads": nreads, "bases": bases, "algo": args.sparse_algo,
-                       "distinct_kmers": int(nd.item()), "kmers_per_sec": nreads * (rl - k + 1) / sec,
-                       "timing": "wall clock around the synchronous C-ABI call (sorted result included)",
-                       "sharding": "reads by index, owner = mix64(code) % G, all-to-all" if world > 1 else "single GPU"},
+                       "distinct_kmers": ndist, "kmers_per_sec": nreads * (rl - k + 1) / sec,
+                       "timing": "CUDA events around the synchronous calls (sorted result included), max over ranks; wall %.1f ms" % (wall * 1e3),
+                       "sharding": ("reads by index; " + ("code ranges: all-to-all of level-1 slabs, each rank counts its partitions"
+                                                          if args.sparse_algo in ("radix", "auto") else
+                                                          "owner = mix64(code) % N: all-to-all of (code,count) pairs + merge"))
+                       if world > 1 else "single GPU",
+                       "self_check": {"valid_windows": win_in, "sum_of_counts": sum_out,
+                                      "fingerprint_in": "%016x" % fp_in, "fingerprint_out": "%016x" % fp_out,
+                                      "keys_not_strictly_ascending": descents,
+                                      "ok": bool(win_in == sum_out and fp_in == fp_out and descents == 0),
+                                      "what": "sum over valid input windows of mix64(code) == sum over result of count*mix64(code) (mod 2^64); csrc/check.cu"}},
             "roofline": {"bound": "hbm", "kernel": "whole call", "achieved": alg_bytes / sec / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": int(ctx.launch_count - launches0),
+            "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
         }
         emit(line)
     leave(world)
-    sp.close()
     ctx.close()
     return 0
 
@@ -288,7 +320,7 @@ def leave(world):
 # variant is used for the timed run only if its table is bit-identical to the shipped path's (a
 # position-weighted fingerprint of all 4^k bins) and it is at least 3 % faster.  Every probe's time and
 # verdict goes into the result line (config.probe).
-PROBE_CANDIDATES = {12: [4, 5, 6, 7, 8, 9], 8: [3]}
+PROBE_CANDIDATES = {12: [2, 6, 7], 8: [3]}
 PROBE_SCRIPT = os.path.abspath(__file__)  # tests put a stand-in here
 E2E_PACKED_OK = "/tmp/kc_bench_e2e_packed_ok"  # written by an N = 1 run whose packed host path reproduced the table
 
@@ -429,7 +461,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(SPARSE_WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="sparse workloads: number of reads (0 = full scale)")
-    ap.add_argument("--sparse-algo", default="hash", choices=["hash", "sort", "radix"])
+    ap.add_argument("--sparse-algo", default="auto", choices=["auto", "hash", "sort", "radix"])
     ap.add_argument("--capacity-hint", type=int, default=0, help="sparse hash: expected distinct k-mers")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct, 2 partition, 3 k=8 checksum variant, 4 partition with deferred retry, 5 partition with paired count (k=12), 6 partition with 14-mer + 13-mer count (k=12), 7 partition with seven windows per record (k=12), 8 = 4 + 5, 9 = 4 + 6")
     ap.add_argument("--length", type=int, default=0, help="override the sequence length (debug)")
@@ -443,7 +475,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of a replayed CUDA graph")
     ap.add_argument("--probe", action="store_true", help="internal: this run is a variant probe of a parent bench.py")
     ap.add_argument("--probe-e2e", action="store_true", help="internal: measure kc_count_dense_host_packed for a parent bench.py")
-    ap.add_argument("--no-probe", action="store_true", help="do not try the not-yet-default kernel variants (see probe_variants)")
+    ap.add_argument("--probe-variants", action="store_true", help="also time the non-default kernel variants, each in its own process (cross-check of KC_DENSE_AUTO)")
+    ap.add_argument("--no-probe", action="store_true", help="skip every child-process probe (kernel variants and the packed host path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -466,12 +499,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     probe_report, base_fp = None, None
-    if rank == 0 and args.algo == 0 and not args.probe and not args.no_probe and not os.environ.get("KC_BENCH_NO_PROBE"):
+    # The timed run is the library's own default (algo 0 = KC_DENSE_AUTO): what a caller of kc_count_dense gets.
+    # --probe-variants additionally times the other kernels, each in its own process, as a cross-check of that
+    # default (round 1 used the probes to pick the timed kernel; the measured winners are the default since round 2).
+    if rank == 0 and args.algo == 0 and args.probe_variants and not args.probe and not args.no_probe and not os.environ.get("KC_BENCH_NO_PROBE"):
         try:
             chosen, probe_report = probe_variants(args, WORKLOADS[args.workload]["k"], local)
             if probe_report and probe_report.get("0", {}).get("ok"):
                 base_fp = probe_report["0"]["fp"]
-            args.algo = chosen
+            if probe_report is not None:
+                probe_report["fastest"] = chosen  # reported only: the timed run stays the library default
         except Exception as ex:  # the probes are an extra: never let them cost the measurement
             sys.stderr.write("bench: variant probes failed (%s); timing the shipped path\n" % ex)
             args.algo = 0
@@ -630,7 +667,7 @@ def main():
     p2 = float(np.mean([p[1] for p in passes]))
     bases_launch = e - b + k - 1
     if p2 > 0 and k == 8:  # shared-memory 16-bit bins + reduce of the per-CTA partials
-        if args.algo == 3:  # checksum variant; the second interval covers its reduce + repair kernels
+        if args.algo in (0, 3):  # checksum variant (the default); the second interval covers its reduce + repair kernels
             kernels = {"dense_smem16c_kernel": (p1, bases_launch), "smem16c_reduce_kernel+smem16_repair_kernel": (p2, 4 * nk)}
         else:
             kernels = {"dense_smem16_kernel": (p1, bases_launch), "smem16_reduce_kernel": (p2, 4 * nk)}
@@ -640,8 +677,10 @@ def main():
         sname = "part_scatter_kernel"
         if args.algo == 7:
             sname, cname = "part_scatter7_kernel", "part_count7_kernel"
-        if args.algo == 10:
+        if args.algo == 10 or (args.algo == 0 and k == 12 and not os.environ.get("KC_DENSE_AUTO_R01")):
             sname, cname = "part_scatter7v2_kernel", "part_count7_kernel"
+        elif args.algo == 0 and k == 12:
+            cname = "part_count_trio12_kernel"
         kernels = {sname: (p1, bases_launch), cname: (p2, 4 * nk)}
     else:
         kernels = {"dense_direct_kernel": (p1, bases_launch + 4 * nk)}

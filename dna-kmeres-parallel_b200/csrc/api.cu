@@ -41,6 +41,27 @@ int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
+cudaError_t kc_pool_alloc(void** p, size_t nbytes) {
+    return cudaMallocAsync(p, nbytes ? nbytes : 1, (cudaStream_t)0);
+}
+void kc_pool_free(void* p) {
+    if (p && cudaFreeAsync(p, (cudaStream_t)0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+    }
+}
+size_t kc_pool_idle_bytes(int device) {
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess ||
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess ||
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return reserved > used ? (size_t)(reserved - used) : 0;
+}
+
 static int reserve(kc_ctx* ctx, void** p, size_t* have, size_t nbytes) {
     if (*have >= nbytes) return KC_OK;
     DeviceGuard dg(ctx->device);
@@ -105,6 +126,13 @@ int kc_ctx_create(int device, kc_ctx** out) {
         delete ctx;
         return kc_set_error(nullptr, KC_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    {  // freed pool memory stays with the pool (see kc_pool_alloc)
+        cudaMemPool_t pool;
+        uint64_t keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess ||
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+            cudaGetLastError();
+    }
     *out = ctx;
     return KC_OK;
 }
@@ -117,6 +145,12 @@ void kc_ctx_destroy(kc_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess ||
+            cudaMemPoolTrimTo(pool, 0) != cudaSuccess)
+            cudaGetLastError();
+    }
     for (auto& ev : ctx->tev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);

@@ -97,6 +97,15 @@ int kc_set_error(kc_ctx* ctx, int code, const char* fmt, ...);
 // KC_TRACE=1: host wall-clock between named points of a call, on stderr (measurement aid; a point with
 // sync = true first waits for the ctx stream, so the interval before it includes the device work)
 void kc_trace(kc_ctx* ctx, const char* what, bool sync = false);
+// Temporary and result buffers of the sparse paths come from the device's stream-ordered memory pool
+// (cudaMallocAsync on the legacy default stream, which is ordered against the ctx's blocking streams like cudaMalloc /
+// cudaFree are, but costs microseconds once the pool is warm: config 4 spent ~200 of 676 ms per call in cudaMalloc /
+// cudaFree of multi-GB arrays, gpurun_out r02 call 4).  kc_ctx_create raises the pool's release threshold so that freed
+// memory stays with the pool; the driver hands it back when another allocation would otherwise fail, and
+// kc_ctx_destroy trims it.  kc_pool_free accepts cudaMalloc'ed pointers too.
+cudaError_t kc_pool_alloc(void** p, size_t nbytes);
+void kc_pool_free(void* p);
+size_t kc_pool_idle_bytes(int device);  // reserved by the pool but not in use: available to kc_pool_alloc
 int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes);   // ctx->scratch  >= nbytes
 int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes);  // ctx->scratch2 >= nbytes
 

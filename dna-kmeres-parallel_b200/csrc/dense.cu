@@ -1245,6 +1245,7 @@ int kc_dense_direct_range(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint
     return dense_direct(ctx, kc_make_geom(d_data, nbytes, win_begin, win_end, k), d_table, st);
 }
 
+
 static uint64_t g_partition_min_windows = 1ull << 26;  // below this the direct path wins
 
 extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
@@ -1273,6 +1274,13 @@ extern "C" int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint6
         if (win_end > nbytes - 11) win_end = nbytes - 11;
         if (win_begin >= win_end) return KC_OK;
         return kc_dense_partition_wide(ctx, d_data, nbytes, win_begin, win_end, d_table, (cudaStream_t)stream);
+    }
+    // KC_DENSE_AUTO at k = 12: the second-generation scatter with seven windows per record, by measurement on B200
+    // (3.1 Gbp: 2.75 ms against 3.48 ms for the five-window scatter + two-increment count; profiles/r02_*)
+    static const bool auto_old12 = getenv("KC_DENSE_AUTO_R01") != nullptr;  // measurement aid: round 1's choice
+    if (algo == KC_DENSE_AUTO && k == 12 && !auto_old12 && nbytes >= 12) {
+        const uint64_t we = win_end > nbytes - 11 ? nbytes - 11 : win_end;
+        if (we > win_begin && we - win_begin >= g_partition_min_windows) algo = KC_DENSE_PARTITION_WIDE2;
     }
     if (algo == KC_DENSE_PARTITION_WIDE2) {
         if (k != 12) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "KC_DENSE_PARTITION_WIDE2 is built for k = 12 (k=%d)", k);

@@ -183,14 +183,12 @@ __global__ void owner_scatter_kernel(const uint64_t* __restrict__ keys, const ui
 // ---------------------------------------------------------------------------
 namespace {
 
-struct DevBuf {
+struct DevBuf {  // pool memory (kc_pool_alloc), returned when the buffer goes out of scope
     void* p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    ~DevBuf() { kc_pool_free(p); }
+    cudaError_t alloc(size_t n) { return kc_pool_alloc(&p, n); }
     void reset() {
-        if (p) cudaFree(p);
+        kc_pool_free(p);
         p = nullptr;
     }
     template <typename T>
@@ -309,8 +307,13 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
     const bool unsorted = (algo & KC_SPARSE_UNSORTED) != 0;
     const bool no_fallback = (algo & KC_SPARSE_NO_FALLBACK) != 0;
     algo &= ~(KC_SPARSE_UNSORTED | KC_SPARSE_NO_FALLBACK);
-    if (algo != KC_SPARSE_HASH && algo != KC_SPARSE_SORT && algo != KC_SPARSE_RADIX)
+    if (algo != KC_SPARSE_HASH && algo != KC_SPARSE_SORT && algo != KC_SPARSE_RADIX && algo != KC_SPARSE_AUTO)
         return kc_set_error(ctx, KC_ERR_INVALID, "unknown sparse algo %d", algo);
+    // KC_SPARSE_AUTO, by measurement on B200 (profiles/r02_sparse_*.json): the radix path beat the hash
+    // table at every size and coverage tried (config 4: 135 vs 373 ms at 1/5 scale, 0.68 vs 1.79 s at full scale;
+    // config 5: 221 vs 546 ms at 1/10, 319 vs 1471 ms at 1/4), so it is the default wherever it exists (2k > 20);
+    // skewed inputs overflow a region and are recounted by the hash table, tiny ones go there directly (below).
+    if (algo == KC_SPARSE_AUTO) algo = (2 * k > 20) ? KC_SPARSE_RADIX : KC_SPARSE_HASH;
     if (!d_data && nbytes) return kc_set_error(ctx, KC_ERR_INVALID, "null data");
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->stream;
@@ -343,6 +346,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         if (want > bound) want = bound;
         size_t free_b = 0, total_b = 0;
         KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        free_b += kc_pool_idle_bytes(ctx->device);
         uint64_t cap = next_pow2(want + want / 2 + 1024);
         while (cap * 16 > free_b * 6 / 10 && cap > 1024) cap >>= 1;  // keep room for the compacted copy
         for (;;) {
@@ -447,8 +451,8 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
                 kc_sparse_free(part);
                 return rc;
             }
-            cudaFree(acc_k.p);
-            cudaFree(acc_c.p);
+            kc_pool_free(acc_k.p);
+            kc_pool_free(acc_c.p);
             acc_k.p = part->d_keys;
             acc_c.p = part->d_counts;
             acc_n = merged_n = part->size;
@@ -465,8 +469,8 @@ void kc_sparse_free(kc_sparse* s) {
     if (!s) return;
     if (s->device >= 0) {  // not s->ctx->device: the ctx may have been destroyed before its results
         DeviceGuard dg(s->device);
-        if (s->d_keys) cudaFree(s->d_keys);
-        if (s->d_counts) cudaFree(s->d_counts);
+        kc_pool_free(s->d_keys);
+        kc_pool_free(s->d_counts);
     }
     delete s;
 }

@@ -547,12 +547,10 @@ sp_gather_kernel(const uint32_t* __restrict__ leaf_n, const unsigned long long* 
     }
 }
 
-struct DevMem {
+struct DevMem {  // pool memory (kc_pool_alloc)
     void* p = nullptr;
-    ~DevMem() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    ~DevMem() { kc_pool_free(p); }
+    cudaError_t alloc(size_t n) { return kc_pool_alloc(&p, n); }
     void* release() {
         void* q = p;
         p = nullptr;
@@ -630,6 +628,7 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
     // need the same again), never more than one per window
     size_t free_b = 0, total_b = 0;
     KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    free_b += kc_pool_idle_bytes(ctx->device);  // what earlier calls returned to the pool is ours to take again
     uint64_t out_cap = (uint64_t)(free_b / 100 * 45) / 12;
     const uint64_t most = (uint64_t)nsrc * plan->max_windows + 1024;
     if (out_cap > most) out_cap = most;

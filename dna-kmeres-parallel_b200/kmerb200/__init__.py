@@ -23,6 +23,7 @@ DENSE_PARTITION_WIDE = 7  # first B200 run pending; never chosen by DENSE_AUTO
 DENSE_PARTITION_DEFER_PAIR, DENSE_PARTITION_DEFER_TRIO = 8, 9  # the scatter of 4 with the count of 5 / 6
 DENSE_PARTITION_WIDE2 = 10  # seven windows per record, second-generation scatter (cooperative flush)
 SPARSE_HASH, SPARSE_SORT, SPARSE_RADIX = 0, 1, 2
+SPARSE_AUTO = 3  # the engine picks (radix wherever it exists, by measurement on B200)
 SPARSE_UNSORTED = 0x100
 SPARSE_NO_FALLBACK = 0x200
 IMPORT_BLANKLINE, IMPORT_NONL = 0, 1
@@ -118,6 +119,9 @@ def lib():
         "kc_sparse_bucket_by_owner": (i32, [vp, vp, vp, u64, u32, vp, vp, vp]),
         "kc_sparse_merge": (i32, [vp, vp, vp, u64, C.POINTER(vp)]),
         "kc_mix64": (u64, [u64]),
+        "kc_window_fingerprint": (i32, [vp, vp, u64, i32, C.POINTER(u64), C.POINTER(u64)]),
+        "kc_sparse_fingerprint": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "kc_dense_fingerprint": (i32, [vp, vp, i32, C.POINTER(u64), C.POINTER(u64)]),
         "kc_dump_counts": (i32, [C.c_char_p, vp, i32, u32]),
         "kc_kmer_distance": (i32, [vp, vp, vp, u32, i32, vp]),
         "kc_triangular_index": (i64, [i64, i64, i64]),
@@ -505,6 +509,26 @@ class Context:
         self._check(lib().kc_sparse_radix_count(self._h, C.addressof(plan), _ptr(slabs), _ptr(counts), nsrc, part_first, nparts,
                                                 C.byref(h)))
         return Sparse(self, h)
+
+    # ---- full-scale self-checks (csrc/check.cu): (fingerprint, total) pairs; a correct count has equal pairs ----
+    def window_fingerprint(self, d_data, nbytes, k):
+        """(sum of mix64(code) over the valid windows of the input mod 2^64, number of valid windows)"""
+        fp, n = C.c_uint64(), C.c_uint64()
+        self._check(lib().kc_window_fingerprint(self._h, _ptr(d_data), nbytes, k, C.byref(fp), C.byref(n)))
+        return int(fp.value), int(n.value)
+
+    def sparse_fingerprint(self, sp):
+        """(sum of count * mix64(code) over a sparse result mod 2^64, sum of counts, positions where the keys are
+        not strictly ascending — 0 for a valid result)"""
+        fp, n, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(lib().kc_sparse_fingerprint(self._h, sp._h, C.byref(fp), C.byref(n), C.byref(d)))
+        return int(fp.value), int(n.value), int(d.value)
+
+    def dense_fingerprint(self, table, k):
+        """(sum of count * mix64(code) over a dense table mod 2^64, sum of counts)"""
+        fp, n = C.c_uint64(), C.c_uint64()
+        self._check(lib().kc_dense_fingerprint(self._h, _ptr(table), k, C.byref(fp), C.byref(n)))
+        return int(fp.value), int(n.value)
 
     def sparse_merge(self, d_keys, d_counts, n):
         self._torch().cuda.current_stream().synchronize()

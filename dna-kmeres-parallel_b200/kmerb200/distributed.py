@@ -107,39 +107,52 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
     `engine` provides radix_plan / radix_scatter / radix_count (kmerb200.Context on the GPU; the
     CPU tests pass an adapter over the emulator build).  Returns None when any rank overflowed
     (skewed input): the caller then takes the hash-sharded path.  `table_full` = exception
-    types that mean "overflow" for this engine."""
+    types that mean "overflow" for this engine.  ANY exception on one rank (out of memory, a bad
+    argument) is voted on like an overflow before it is raised again, so that no rank is left
+    waiting in a collective its peer never enters."""
     import torch
     dist = _dist()
     world, rank = dist.get_world_size(), dist.get_rank()
 
-    def all_ok(ok, dev):
-        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    def vote(state, dev):
+        """state: 2 = ok, 1 = overflow, 0 = error; returns the minimum over the ranks"""
+        t = torch.tensor([state], dtype=torch.int32, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return bool(t.item())
+        return int(t.item())
+
+    def stage(f, dev):
+        """run f() on this rank, agree on the outcome with every rank"""
+        res, err, state = None, None, 2
+        try:
+            res = f()
+        except table_full:
+            state = 1
+        except Exception as ex:  # noqa: BLE001 — voted on, then raised again below
+            err, state = ex, 0
+        worst = vote(state, dev)
+        if err is not None:
+            raise err
+        if worst == 0:
+            raise RuntimeError("sharded sparse radix: another rank failed (see its error)")
+        return res if worst == 2 else None
 
     dev = reads.device if hasattr(reads, "device") else "cpu"
     t = torch.tensor([max(nbytes - k + 1, 0)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    plan = engine.radix_plan(int(t.item()), k, world)
-    slabs = counts = None
-    try:
-        slabs, counts = engine.radix_scatter(reads, nbytes, plan)
-    except table_full:
-        pass
-    if not all_ok(slabs is not None, dev):
+    plan = stage(lambda: engine.radix_plan(int(t.item()), k, world), dev)
+    if plan is None:
         return None
-    recv_s, recv_c = torch.empty_like(slabs), torch.empty_like(counts)
+    sc = stage(lambda: engine.radix_scatter(reads, nbytes, plan), dev)
+    if sc is None:
+        return None
+    slabs, counts = sc
+    del sc
+    bufs = stage(lambda: (torch.empty_like(slabs), torch.empty_like(counts)), dev)
+    recv_s, recv_c = bufs
     dist.all_to_all_single(recv_s, slabs)  # equal splits: block o = partitions [o, o+1) * parts_per_rank
     dist.all_to_all_single(recv_c, counts)
-    del slabs, counts
-    res = None
-    try:
-        res = engine.radix_count(plan, recv_s, recv_c, world, rank * plan.parts_per_rank, plan.parts_per_rank)
-    except table_full:
-        pass
-    if not all_ok(res is not None, dev):
-        return None
-    return res
+    del slabs, counts, bufs
+    return stage(lambda: engine.radix_count(plan, recv_s, recv_c, world, rank * plan.parts_per_rank, plan.parts_per_rank), dev)
 
 
 def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):
@@ -151,7 +164,13 @@ def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return ctx.count_sparse(d_reads, nbytes, k, algo)
-    from . import KC_ERR_TABLE_FULL, SPARSE_HASH, SPARSE_NO_FALLBACK, SPARSE_RADIX, SPARSE_UNSORTED, KmerError
+    from . import KC_ERR_TABLE_FULL, SPARSE_AUTO, SPARSE_HASH, SPARSE_NO_FALLBACK, SPARSE_RADIX, SPARSE_UNSORTED, KmerError
+    if (algo & 0xFF) == SPARSE_AUTO:  # as kc_count_sparse: radix wherever it exists
+        algo = (algo & ~0xFF) | (SPARSE_RADIX if 2 * k > 20 else SPARSE_HASH)
+    if (algo & 0xFF) == SPARSE_RADIX and 1024 % world != 0:
+        if algo & SPARSE_NO_FALLBACK:
+            raise KmerError(-1, "range-sharded radix needs a world size that divides 1024 (got %d)" % world)
+        algo = SPARSE_HASH  # the documented fallback: owner-hash sharding works for any world size
     if (algo & 0xFF) == SPARSE_RADIX:
         class _Full(KmerError):
             pass

@@ -217,6 +217,8 @@ KC_API int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes,
 #define KC_SPARSE_RADIX 2  /* MSD radix partition, leaves sorted in shared memory (k >= 11);
                               falls back to KC_SPARSE_HASH when skewed data overflows a region, and
                               takes that path directly for inputs below 4 M windows            */
+#define KC_SPARSE_AUTO 3   /* the engine picks: KC_SPARSE_RADIX wherever it exists (k >= 11), chosen by
+                              measurement on B200, else KC_SPARSE_HASH          */
 /* OR-ed into `algo`: leave the distinct (code,count) pairs in table order instead of
  * sorting them — for callers that re-bucket and merge anyway (the multi-GPU path).   */
 #define KC_SPARSE_UNSORTED 0x100
@@ -273,6 +275,22 @@ KC_API int kc_sparse_merge(kc_ctx* ctx, const uint64_t* d_keys, const uint32_t* 
                            uint64_t n, kc_sparse** out);
 /* owner hash, exported so host-side sharding logic and tests agree with the GPU */
 KC_API uint64_t kc_mix64(uint64_t code);
+
+/* Full-scale self-checks of a count (csrc/check.cu).  The reference verifies itself by running its CPU
+ * path beside its GPU path on the same input (main.cu:169,172) and diffing the outputs by hand; at the
+ * sizes of BASELINE configs 3-5 the equivalent is a multiset fingerprint with h = kc_mix64:
+ *   kc_window_fingerprint: F = sum over the VALID windows of the input of h(code), and their number,
+ *                          from one streaming scan (additive over shards and ranks);
+ *   kc_sparse_fingerprint / kc_dense_fingerprint: F = sum over the k-mers of count * h(code), and the
+ *                          sum of the counts, from a result.
+ * A correct count has equal F (mod 2^64) and equal totals.  Results are written to HOST pointers. */
+KC_API int kc_window_fingerprint(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k,
+                                 uint64_t* h_fp, uint64_t* h_windows);
+/* *h_descents (may be NULL): positions where the keys are not strictly ascending — 0 for a valid result */
+KC_API int kc_sparse_fingerprint(kc_ctx* ctx, const kc_sparse* s, uint64_t* h_fp, uint64_t* h_total,
+                                 uint64_t* h_descents);
+KC_API int kc_dense_fingerprint(kc_ctx* ctx, const uint32_t* d_table, int k, uint64_t* h_fp,
+                                uint64_t* h_total);
 
 /* ------------------------------------------------------------------ */
 /* "Next" row f4: the 2-bit packed sequence store sketched in the      */

@@ -73,3 +73,34 @@ def test_partition_wide2(ctx, kmerlib, oracle):
     ctx.count_dense_range(poly, P, 0, P, 12, t, algo=kmerlib.DENSE_PARTITION_WIDE2)
     torch.cuda.synchronize()
     assert int(t[0].item()) == P - 11 and int(t.to(torch.int64).sum().item()) == P - 11
+
+
+def test_fingerprint_self_checks(ctx, kmerlib, oracle):
+    """csrc/check.cu: the window fingerprint of an input (one streaming scan) equals the numpy value from the oracle's
+    count, and the fingerprint of every GPU count of it (sparse auto / hash / radix, dense); at 20 M windows, where the
+    oracle does not go, input and result fingerprints agree and the keys are strictly ascending"""
+    import torch
+    from kmerb200.distributed import mix64_np
+    reads = oracle.gen_reads(0xB2000004, 3_000_000, 150, 200, 0, sz(30_000) if FULL else 600)
+    d = to_dev(reads)
+    for k in (12, 21, 31):
+        wk, wc, _ = oracle.count_sparse(reads, k)
+        with np.errstate(over="ignore"):
+            want = (int((mix64_np(wk) * wc.astype(np.uint64)).sum(dtype=np.uint64)), int(wc.astype(np.uint64).sum()))
+        assert ctx.window_fingerprint(d, reads.size, k) == want, k
+        for algo in (kmerlib.SPARSE_AUTO, kmerlib.SPARSE_HASH, kmerlib.SPARSE_RADIX):
+            sp = ctx.count_sparse(d, reads.size, k, algo)
+            assert ctx.sparse_fingerprint(sp) == want + (0,), (k, algo)
+            sp.close()
+        if k == 12:
+            t = torch.zeros(kmerlib.num_kmers(k), dtype=torch.int32, device="cuda:0")
+            ctx.count_dense_range(d, reads.size, 0, reads.size, k, t)
+            torch.cuda.synchronize()
+            assert ctx.dense_fingerprint(t, k) == want
+    nreads = 150_000 if FULL else 700
+    big = ctx.gen_reads(0xB2000004, 50_000_000, 150, 200, 0, nreads)
+    fin = ctx.window_fingerprint(big, nreads * 151, 21)
+    assert fin[1] == nreads * 130
+    sp = ctx.count_sparse(big, nreads * 151, 21, kmerlib.SPARSE_AUTO)
+    assert ctx.sparse_fingerprint(sp) == fin + (0,)
+    sp.close()

@@ -519,7 +519,47 @@ def case_ingest(args):
     print("ok ingest", *args, "files", len(texts))
 
 
-CASES = {"dense_host_packed": case_dense_host_packed, "ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+def case_fingerprint(args):
+    """csrc/check.cu: the window fingerprint of an input == the fingerprint of its sparse and dense counts
+    == the numpy value from the oracle's count (sum of count * mix64(code) mod 2^64), totals included"""
+    k, n, kind, seed, offset = int(args[0]), int(args[1]), args[2], int(args[3]), int(args[4])
+    O = _oracle()
+    sys.path.insert(0, os.path.join(ROOT, "dna-kmeres-parallel_b200"))
+    from kmerb200.distributed import mix64_np
+    data = make_input(kind, n, seed, k)
+    wk, wc, _ = O.count_sparse(data, k)
+    with np.errstate(over="ignore"):
+        want_fp = int((mix64_np(wk) * wc.astype(np.uint64)).sum(dtype=np.uint64))
+    want_n = int(wc.astype(np.uint64).sum())
+    ctx = EmuContext()
+    L = ctx.L
+    L.kc_window_fingerprint.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.kc_sparse_fingerprint.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.kc_dense_fingerprint.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    base, p = ctx.upload(np.ascontiguousarray(data, dtype=np.uint8), offset)
+    fp, tot = C.c_uint64(), C.c_uint64()
+    ctx.check(L.kc_window_fingerprint(ctx.h, p, data.size, k, C.byref(fp), C.byref(tot)))
+    assert (fp.value, tot.value) == (want_fp, want_n), ("window", fp.value, tot.value, want_fp, want_n)
+    sp = C.c_void_p()
+    ctx.check(L.kc_count_sparse(ctx.h, p, data.size, k, 3, 0, C.byref(sp)))  # KC_SPARSE_AUTO
+    desc = C.c_uint64(7)
+    ctx.check(L.kc_sparse_fingerprint(ctx.h, sp, C.byref(fp), C.byref(tot), C.byref(desc)))
+    assert (fp.value, tot.value, desc.value) == (want_fp, want_n, 0), ("sparse", fp.value, tot.value, desc.value, want_fp, want_n)
+    L.kc_sparse_free(sp)
+    if k <= 12:
+        nb = 4 << (2 * k)
+        t = ctx.alloc(nb)
+        ctx.check(L.kc_memset_d(ctx.h, t, 0, nb))
+        ctx.check(L.kc_count_dense_range_async(ctx.h, p, data.size, 0, max(0, data.size - k + 1), k, t, 0, None))
+        ctx.check(L.kc_dense_fingerprint(ctx.h, t, k, C.byref(fp), C.byref(tot)))
+        assert (fp.value, tot.value) == (want_fp, want_n), ("dense", fp.value, tot.value, want_fp, want_n)
+        ctx.free(t)
+    ctx.free(base)
+    ctx.close()
+    print("ok fingerprint", *args)
+
+
+CASES = {"fingerprint": case_fingerprint, "dense_host_packed": case_dense_host_packed, "ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

@@ -253,6 +253,21 @@ static inline cudaError_t cudaMalloc(T** p, size_t n) {
     return emu_cuda_malloc((void**)p, n);
 }
 cudaError_t cudaFree(void* p);
+// stream-ordered pool allocation (kc_pool_alloc): plain guarded allocations here
+typedef struct emu_pool* cudaMemPool_t;
+enum { cudaMemPoolAttrReleaseThreshold = 4, cudaMemPoolAttrReservedMemCurrent = 5, cudaMemPoolAttrUsedMemCurrent = 7 };
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return emu_cuda_malloc(p, n); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) {
+    *pool = nullptr;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
+static inline cudaError_t cudaMemPoolGetAttribute(cudaMemPool_t, int, void* v) {
+    *(uint64_t*)v = 0;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
     *p = malloc(n ? n : 1);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;

@@ -251,6 +251,13 @@ def test_host_packed_count_on_emulator():
         run_case("dense_host_packed", 3, n, 5, "dirty", 2, KC_HOSTPACK_ITEM=32)
 
 
+@pytest.mark.parametrize("case", [(12, 300_000, "genome", 3, 0), (21, 200_000, "dirty", 4, 5), (31, 150_000, "sparseN40", 5, 9),
+                                  (5, 100_000, "dirty", 6, 1)], ids=lambda c: "k%d-%s" % (c[0], c[2]))
+def test_fingerprint_self_checks_on_emulator(case):
+    """csrc/check.cu: window fingerprint of the input == fingerprint of its counts == the oracle's value"""
+    run_case("fingerprint", *case)
+
+
 def test_gpu_fasta_parser_on_emulator():
     """f2, device side: kc_import_seqs_device == the host loader on the reference-generated fixtures and
     random files, with 16- and 5-byte tiles (lines, ids and records span tiles; > 1024 tiles in one file)"""
