@@ -590,9 +590,10 @@ def main():
         # One step = zero-fill + ~8 launches (+ the NCCL reduce): captured once in a CUDA
         # graph and replayed, so the timed region is not paced by Python/ctypes launches.
         graph = None
-        # N > 1 keeps plain launches: a captured NCCL reduce replays fine (N=8: 1.02 ms/step) but the
-        # process then hung in teardown (graph + process group), which no timing gain is worth.
-        if not args.no_graph and world == 1:
+        # N > 1 as well: the captured step holds the NCCL reduce (round 1 kept plain launches there because the
+        # process hung in teardown of graph + process group; it now leaves through os._exit right behind the
+        # result line, see leave()).  KC_BENCH_GRAPH_N=0 goes back to plain launches.
+        if not args.no_graph and (world == 1 or os.environ.get("KC_BENCH_GRAPH_N", "1") != "0"):
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())

@@ -192,7 +192,7 @@ struct SpCtl {  // one 64-byte control block in device memory
 template <typename Shape, typename R1T, int HALO>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ counts1, uint32_t cap1, SpCtl* ctl,
-                  int flush256) {
+                  int flush256, int rbits, uint32_t round) {
     KC_DYN_SMEM(uint32_t, smem);
     using St = Stager<R1T, Shape::P1>;
     St st;
@@ -202,7 +202,10 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
     st.init(smem, slabs1 + (uint64_t)blockIdx.x * cap1, (uint64_t)gridDim.x * cap1, cap1, &ctl->failed);
     __syncthreads();
     const int k = g.k;
-    const int r1bits = 2 * k - Shape::KB1;
+    // ROUNDS: the top `rbits` bits of the code select the round a window belongs to; this launch keeps the windows of
+    // `round` only, and everything below works on the remaining cb = 2k - rbits bits (see kc_sparse_radix_plan)
+    const int cb = 2 * k - rbits;
+    const int r1bits = cb - Shape::KB1;
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;
     const uint64_t r1mask = (1ull << r1bits) - 1ull;
     const uint32_t pref = threadIdx.x >> 5;
@@ -225,7 +228,8 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
             const int j = __ffs((int)m) - 1;
             m &= m - 1u;
             const uint64_t code = lw.code64(j, kmask);
-            st.stage((uint32_t)(code >> r1bits), (R1T)(code & r1mask), pref + (uint32_t)j);
+            if (rbits && (uint32_t)(code >> cb) != round) continue;
+            st.stage((uint32_t)(code >> r1bits) & (Shape::P1 - 1), (R1T)(code & r1mask), pref + (uint32_t)j);
         }
     });
     __syncthreads();
@@ -265,7 +269,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 // ---------------------------------------------------------------------------
 template <typename Shape, typename R1T, typename R2T>
 __global__ void __launch_bounds__(SP_THREADS, 1)
-sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict__ counts1, uint32_t cap1,
+sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefix /* round << cb */, const R1T* __restrict__ slabs1, const uint32_t* __restrict__ counts1, uint32_t cap1,
                uint32_t grid1, uint32_t nsrc, uint32_t nparts, uint32_t part_first, R2T* __restrict__ scratch2,
                uint32_t cap2, uint64_t* __restrict__ tmp_keys,
                uint32_t* __restrict__ tmp_counts, uint64_t out_cap, unsigned long long* __restrict__ leaf_base,
@@ -279,7 +283,7 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
     constexpr int PER_THREAD = LEAF_CAP / SP_THREADS;
     static_assert(LEAF_CAP % SP_THREADS == 0, "leaf records are held in registers, PER_THREAD per thread");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r1bits = 2 * k - Shape::KB1;
+    const int r1bits = cb - Shape::KB1;
     const int r2bits = r1bits - Shape::KB2;  // >= 1 (host checks)
     const int dbits = r2bits < 10 ? r2bits : 10;
     const int lowbits = r2bits - dbits;
@@ -467,7 +471,7 @@ sp_leaf_kernel(int k, const R1T* __restrict__ slabs1, const uint32_t* __restrict
             __syncthreads();
             const unsigned long long base = s_base;
             if (cnt && base + leaf_runs <= out_cap) {
-                const uint64_t hi = ((uint64_t)p1 << r1bits) | ((uint64_t)p2 << r2bits);
+                const uint64_t hi = prefix | ((uint64_t)p1 << r1bits) | ((uint64_t)p2 << r2bits);
                 uint64_t o = base + off;
                 R2T e0 = s_sorted[begin];
                 R2T cur = e0 & keymask;
@@ -580,8 +584,8 @@ uint64_t region_records(uint64_t mean, int chunk, int slack_div, int sigmas) {
 // partition range with ONE all-to-all (kmerb200/distributed.py), and runs `count` on what it
 // received — every rank then owns a disjoint, sorted range of codes and nothing is merged.
 template <typename Shape, typename R1T, int HALO>
-int run_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs, uint32_t* d_counts,
-                SpCtl* ctl) {
+int run_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, uint32_t round, void* d_slabs,
+                uint32_t* d_counts, SpCtl* ctl) {
     using St1 = Stager<R1T, Shape::P1>;
     cudaStream_t st = ctx->stream;
     const int k = plan->k;
@@ -596,19 +600,19 @@ int run_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix
     auto kern = sp_scatter_kernel<Shape, R1T, HALO>;
     KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     KC_LAUNCH(kern, (int)plan->grid, SP_THREADS, smem1, st, g, (R1T*)d_slabs, d_counts, (uint32_t)plan->region_records, ctl,
-              flush256_env());
+              flush256_env(), (int)plan->round_bits, round);
     KC_LAUNCH_CHECK(ctx, "sp_scatter_kernel");
     return KC_OK;
 }
 
 template <typename Shape, typename R1T, typename R2T>
-int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
               uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, kc_sparse** out, int* failed) {
     using St2 = Stager<R2T, Shape::P2>;
     cudaStream_t st = ctx->stream;
-    const int k = plan->k;
+    const int cb = 2 * plan->k - (int)plan->round_bits;
     const int grid2 = ctx->sm_count < (int)nparts ? ctx->sm_count : (int)nparts;
-    const uint64_t part_mean = (uint64_t)nsrc * plan->max_windows / Shape::P1 + 1;
+    const uint64_t part_mean = (uint64_t)nsrc * (plan->max_windows >> plan->round_bits) / Shape::P1 + 1;
     const uint64_t cap2 = region_records((part_mean + part_mean / 8) / Shape::P2 + 1, St2::CAP, 4, 16);
     if ((uint64_t)Shape::P2 * cap2 >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: leaf region too large");
     const uint64_t nleaves = (uint64_t)nparts * Shape::P2;
@@ -630,7 +634,8 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
     KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     free_b += kc_pool_idle_bytes(ctx->device);  // what earlier calls returned to the pool is ours to take again
     uint64_t out_cap = (uint64_t)(free_b / 100 * 45) / 12;
-    const uint64_t most = (uint64_t)nsrc * plan->max_windows + 1024;
+    const uint64_t round_windows = plan->max_windows >> plan->round_bits;
+    const uint64_t most = (uint64_t)nsrc * (round_windows + round_windows / 8) / (plan->partitions / nparts) + (1u << 20);  // this rank's share of the round
     if (out_cap > most) out_cap = most;
     if (out_cap < 1024) return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: no device memory left for the run list");
     kc_trace(ctx, "count: enter", true);
@@ -647,7 +652,7 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
     {
         auto kern = sp_leaf_kernel<Shape, R1T, R2T>;
         KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, k, (const R1T*)d_slabs, d_counts, (uint32_t)plan->region_records,
+        KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, cb, (uint64_t)round << cb, (const R1T*)d_slabs, d_counts, (uint32_t)plan->region_records,
                   plan->grid, nsrc, nparts, part_first, scratch2, (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p,
                   out_cap, leaf_base, leaf_n, ctl, flush256_env());
         KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
@@ -689,9 +694,9 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const
 // bytes of the work area run_count needs (ctl + leaf directory + level-2 scratch)
 template <typename Shape>
 size_t count_work_bytes(const kc_ctx* ctx, const kc_radix_plan* plan, uint32_t nsrc, uint32_t nparts) {
-    const int rec2 = (2 * plan->k - Shape::KB1 - Shape::KB2) <= 32 ? 4 : 8;
+    const int rec2 = (2 * plan->k - (int)plan->round_bits - Shape::KB1 - Shape::KB2) <= 32 ? 4 : 8;
     const int grid2 = ctx->sm_count < (int)nparts ? ctx->sm_count : (int)nparts;
-    const uint64_t part_mean = (uint64_t)nsrc * plan->max_windows / Shape::P1 + 1;
+    const uint64_t part_mean = (uint64_t)nsrc * (plan->max_windows >> plan->round_bits) / Shape::P1 + 1;
     const uint64_t cap2 = region_records((part_mean + part_mean / 8) / Shape::P2 + 1, 64 / rec2, 4, 16);
     const uint64_t nleaves = (uint64_t)nparts * Shape::P2;
     auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
@@ -700,21 +705,51 @@ size_t count_work_bytes(const kc_ctx* ctx, const kc_radix_plan* plan, uint32_t n
 
 template <typename Shape>
 int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t shape_id, kc_radix_plan* plan) {
-    const int r1 = 2 * k - Shape::KB1, r2 = r1 - Shape::KB2;
-    if (r2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix needs 2k > %d (k=%d)", Shape::KB1 + Shape::KB2, k);
+    if (2 * k - Shape::KB1 - Shape::KB2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix needs 2k > %d (k=%d)", Shape::KB1 + Shape::KB2, k);
     if (world < 1 || Shape::P1 % world) return kc_set_error(ctx, KC_ERR_INVALID, "sparse radix: world %u must divide %d partitions", world, Shape::P1);
+    // ROUNDS.  A leaf (one of P1 x P2 code ranges) is sorted in shared memory and must fit it; the slabs of all
+    // windows must fit the device.  Large inputs are therefore counted in 2^round_bits rounds: round r keeps the
+    // windows whose top round_bits code bits are r, and the partition tree works on the remaining bits.  Config 5
+    // (24 G windows, 64-bit leaf records): 22.9 K records per leaf against a capacity of 10 240 -> 4 rounds.
+    static const int rb_env = getenv("KC_SPARSE_RADIX_RBITS") ? atoi(getenv("KC_SPARSE_RADIX_RBITS")) : -1;  // tests
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        free_b = total_b = 0;
+    }
+    free_b += kc_pool_idle_bytes(ctx->device);
+    int rbits = 0;
+    for (;; rbits++) {
+        const int r1 = 2 * k - rbits - Shape::KB1, r2 = r1 - Shape::KB2;
+        if (r2 < 1) {
+            rbits = rbits ? rbits - 1 : 0;
+            break;
+        }
+        if (rb_env >= 0) {
+            if (rbits >= rb_env) break;
+            continue;
+        }
+        const uint64_t leaf_cap = (uint64_t)Shape::LEAF_CAP / (r2 <= 32 ? 1 : 2);  // records of 4 or 8 bytes
+        const uint64_t leaf_mean = ((uint64_t)world * max_windows >> rbits) / ((uint64_t)Shape::P1 * Shape::P2);
+        const uint64_t slab = (max_windows >> rbits) * (r1 <= 32 ? 4 : 8);
+        const bool leaf_ok = leaf_mean * 5 <= leaf_cap * 3;                       // mean <= 60 % of the capacity
+        const bool mem_ok = free_b == 0 || (slab + slab / 4) * (world > 1 ? 2 : 1) <= free_b / 2;  // + the received copy
+        if ((leaf_ok && mem_ok) || rbits >= 8) break;
+    }
+    const int r1 = 2 * k - rbits - Shape::KB1;
     memset(plan, 0, sizeof *plan);
     plan->k = k;
     plan->world = world;
     plan->partitions = Shape::P1;
     plan->parts_per_rank = Shape::P1 / world;
     plan->shape = shape_id;
+    plan->round_bits = (uint32_t)rbits;
     plan->rec_bytes = r1 <= 32 ? 4 : 8;
     plan->max_windows = max_windows;
     const uint64_t ngroups = (max_windows + k + 511 + 15) / 512 + 1;
     const uint64_t want1 = (ngroups + 31) / 32;
     plan->grid = (uint32_t)(want1 < 1 ? 1 : (want1 > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want1));
-    plan->region_records = region_records(max_windows / ((uint64_t)Shape::P1 * plan->grid) + 1, 64 / (int)plan->rec_bytes, 8, 8);
+    plan->region_records = region_records((max_windows >> rbits) / ((uint64_t)Shape::P1 * plan->grid) + 1, 64 / (int)plan->rec_bytes, 8, 8);
     if (plan->region_records >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: region too large");
     plan->slab_bytes = (uint64_t)Shape::P1 * plan->grid * plan->region_records * plan->rec_bytes;
     plan->counts_bytes = (uint64_t)Shape::P1 * plan->grid * 4;
@@ -722,23 +757,23 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
 }
 
 template <typename Shape>
-int scatter_dispatch(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs,
+int scatter_dispatch(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, uint32_t round, void* d_slabs,
                      uint32_t* d_counts, SpCtl* ctl) {
     if (plan->rec_bytes == 4)
-        return plan->k <= 17 ? run_scatter<Shape, uint32_t, 1>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl)
-                             : run_scatter<Shape, uint32_t, 2>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl);
-    return run_scatter<Shape, uint64_t, 2>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl);
+        return plan->k <= 17 ? run_scatter<Shape, uint32_t, 1>(ctx, d_data, nbytes, plan, round, d_slabs, d_counts, ctl)
+                             : run_scatter<Shape, uint32_t, 2>(ctx, d_data, nbytes, plan, round, d_slabs, d_counts, ctl);
+    return run_scatter<Shape, uint64_t, 2>(ctx, d_data, nbytes, plan, round, d_slabs, d_counts, ctl);
 }
 
 template <typename Shape>
-int count_dispatch(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+int count_dispatch(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
                    uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, kc_sparse** out, int* failed) {
-    const int r2 = 2 * plan->k - Shape::KB1 - Shape::KB2;
+    const int r2 = 2 * plan->k - (int)plan->round_bits - Shape::KB1 - Shape::KB2;
     if (plan->rec_bytes == 4)
-        return run_count<Shape, uint32_t, uint32_t>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+        return run_count<Shape, uint32_t, uint32_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
     if (r2 <= 32)
-        return run_count<Shape, uint64_t, uint32_t>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
-    return run_count<Shape, uint64_t, uint64_t>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+        return run_count<Shape, uint64_t, uint32_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+    return run_count<Shape, uint64_t, uint64_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
 }
 
 using ShapeShipped = SpShape<10, 10, 20480>;
@@ -751,6 +786,7 @@ uint32_t shape_from_env() {
 
 bool plan_ok(kc_ctx* ctx, const kc_radix_plan* plan) {
     return ctx && plan && plan->k >= 1 && plan->k <= KC_MAX_K && plan->shape <= 1 && plan->grid >= 1 && plan->region_records >= 1 &&
+           plan->round_bits <= 8 &&
            plan->partitions == (plan->shape ? (uint32_t)ShapeSmall::P1 : (uint32_t)ShapeShipped::P1);
 }
 
@@ -766,17 +802,18 @@ int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint
               : make_plan<ShapeShipped>(ctx, max_windows_per_rank, k, world, sh, plan);
 }
 
-int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs,
-                            uint32_t* d_counts) {
-    if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || (!d_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_scatter: bad argument");
+int kc_sparse_radix_scatter_round(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, uint32_t round,
+                                  void* d_slabs, uint32_t* d_counts) {
+    if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || (!d_data && nbytes) || round >= (1u << plan->round_bits))
+        return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_scatter: bad argument");
     const uint64_t nwin = nbytes >= (uint64_t)plan->k ? nbytes - plan->k + 1 : 0;
     if (nwin > plan->max_windows) return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_scatter: %llu windows, plan made for %llu", (unsigned long long)nwin, (unsigned long long)plan->max_windows);
     DeviceGuard dg(ctx->device);
     int rc = kc_scratch2_reserve(ctx, 256);
     if (rc) return rc;
     SpCtl* ctl = (SpCtl*)ctx->scratch2;
-    rc = plan->shape ? scatter_dispatch<ShapeSmall>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl)
-                     : scatter_dispatch<ShapeShipped>(ctx, d_data, nbytes, plan, d_slabs, d_counts, ctl);
+    rc = plan->shape ? scatter_dispatch<ShapeSmall>(ctx, d_data, nbytes, plan, round, d_slabs, d_counts, ctl)
+                     : scatter_dispatch<ShapeShipped>(ctx, d_data, nbytes, plan, round, d_slabs, d_counts, ctl);
     if (rc) return rc;
     SpCtl h;
     KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -787,23 +824,73 @@ int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, co
     return KC_OK;
 }
 
-int kc_sparse_radix_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
-                          uint32_t part_first, uint32_t nparts, kc_sparse** out) {
+int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts,
+                                uint32_t nsrc, uint32_t part_first, uint32_t nparts, kc_sparse** out) {
     if (!out) return KC_ERR_INVALID;
     *out = nullptr;
-    if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || nsrc < 1 || nparts < 1 || (uint64_t)part_first + nparts > plan->partitions)
+    if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || nsrc < 1 || nparts < 1 || (uint64_t)part_first + nparts > plan->partitions ||
+        round >= (1u << plan->round_bits))
         return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_count: bad argument");
     DeviceGuard dg(ctx->device);
     const size_t wb = plan->shape ? count_work_bytes<ShapeSmall>(ctx, plan, nsrc, nparts) : count_work_bytes<ShapeShipped>(ctx, plan, nsrc, nparts);
     int rc = kc_scratch2_reserve(ctx, wb);
     if (rc) return rc;
     int failed = 0;
-    rc = plan->shape ? count_dispatch<ShapeSmall>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed)
-                     : count_dispatch<ShapeShipped>(ctx, plan, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed);
+    rc = plan->shape ? count_dispatch<ShapeSmall>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed)
+                     : count_dispatch<ShapeShipped>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed);
     if (rc) return rc;
     if (failed)
         return kc_set_error(ctx, KC_ERR_TABLE_FULL, "sparse radix count overflowed (skewed input):%s%s%s%s", (failed & 1) ? " leaf region" : "",
                             (failed & 2) ? " staging bins" : "", (failed & 4) ? " leaf buffer" : "", (failed & 8) ? " run list" : "");
+    return KC_OK;
+}
+
+// single-round forms (plans with round_bits = 0)
+int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs,
+                            uint32_t* d_counts) {
+    if (plan && plan->round_bits) return kc_set_error(ctx, KC_ERR_INVALID, "this plan has %u rounds: use kc_sparse_radix_scatter_round", 1u << plan->round_bits);
+    return kc_sparse_radix_scatter_round(ctx, d_data, nbytes, plan, 0, d_slabs, d_counts);
+}
+int kc_sparse_radix_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+                          uint32_t part_first, uint32_t nparts, kc_sparse** out) {
+    if (plan && plan->round_bits) {
+        if (out) *out = nullptr;
+        return kc_set_error(ctx, KC_ERR_INVALID, "this plan has %u rounds: use kc_sparse_radix_count_round", 1u << plan->round_bits);
+    }
+    return kc_sparse_radix_count_round(ctx, plan, 0, d_slabs, d_counts, nsrc, part_first, nparts, out);
+}
+
+// results of consecutive rounds (or any ascending pieces) -> one result; the pieces stay valid
+int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_sparse** out) {
+    if (!ctx || !out || (!parts && nparts)) return KC_ERR_INVALID;
+    *out = nullptr;
+    DeviceGuard dg(ctx->device);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nparts; i++) total += parts[i] ? parts[i]->size : 0;
+    kc_sparse* res = new kc_sparse();
+    res->ctx = ctx;
+    res->device = ctx->device;
+    res->size = total;
+    if (total) {
+        void *dk = nullptr, *dc = nullptr;
+        if (kc_pool_alloc(&dk, total * 8) != cudaSuccess || kc_pool_alloc(&dc, total * 4) != cudaSuccess) {
+            cudaGetLastError();
+            kc_pool_free(dk);
+            delete res;
+            return kc_set_error(ctx, KC_ERR_NOMEM, "kc_sparse_concat: out of device memory for %llu k-mers", (unsigned long long)total);
+        }
+        res->d_keys = (uint64_t*)dk;
+        res->d_counts = (uint32_t*)dc;
+        uint64_t at = 0;
+        for (uint32_t i = 0; i < nparts; i++) {
+            if (!parts[i] || !parts[i]->size) continue;
+            KC_CUDA(ctx, cudaMemcpyAsync(res->d_keys + at, parts[i]->d_keys, parts[i]->size * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            KC_CUDA(ctx, cudaMemcpyAsync(res->d_counts + at, parts[i]->d_counts, parts[i]->size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            at += parts[i]->size;
+        }
+        KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = res;
     return KC_OK;
 }
 
@@ -823,10 +910,23 @@ int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_
     void* slabs = ctx->scratch;
     uint32_t* counts = (uint32_t*)((char*)ctx->scratch + pad((size_t)plan.slab_bytes));
     kc_trace(ctx, "radix: plan + scratch", true);
-    rc = kc_sparse_radix_scatter(ctx, d_data, nbytes, &plan, slabs, counts);
-    kc_trace(ctx, "radix: scatter");
-    if (rc == KC_OK) rc = kc_sparse_radix_count(ctx, &plan, slabs, counts, 1, 0, plan.partitions, out);
-    kc_trace(ctx, "radix: count (incl. frees)", true);
+    const uint32_t rounds = 1u << plan.round_bits;
+    std::vector<kc_sparse*> parts(rounds, nullptr);
+    for (uint32_t r = 0; r < rounds && rc == KC_OK; r++) {
+        rc = kc_sparse_radix_scatter_round(ctx, d_data, nbytes, &plan, r, slabs, counts);
+        kc_trace(ctx, "radix: scatter");
+        if (rc == KC_OK) rc = kc_sparse_radix_count_round(ctx, &plan, r, slabs, counts, 1, 0, plan.partitions, &parts[r]);
+        kc_trace(ctx, "radix: count (incl. frees)", true);
+    }
+    if (rc == KC_OK) {
+        if (rounds == 1) {
+            *out = parts[0];
+            parts[0] = nullptr;
+        } else {
+            rc = kc_sparse_concat(ctx, parts.data(), rounds, out);
+        }
+    }
+    for (kc_sparse* p : parts) kc_sparse_free(p);
     if (rc == KC_ERR_TABLE_FULL) {  // an overflow: the error text says which; the caller falls back
         *failed = 1;
         return KC_OK;

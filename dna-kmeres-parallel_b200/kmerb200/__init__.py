@@ -118,6 +118,9 @@ def lib():
         "kc_sparse_copy_to_host": (i32, [vp, vp, vp, vp]),
         "kc_sparse_bucket_by_owner": (i32, [vp, vp, vp, u64, u32, vp, vp, vp]),
         "kc_sparse_merge": (i32, [vp, vp, vp, u64, C.POINTER(vp)]),
+        "kc_sparse_radix_scatter_round": (i32, [vp, vp, u64, vp, u32, vp, vp]),
+        "kc_sparse_radix_count_round": (i32, [vp, vp, u32, vp, vp, u32, u32, u32, C.POINTER(vp)]),
+        "kc_sparse_concat": (i32, [vp, vp, u32, C.POINTER(vp)]),
         "kc_mix64": (u64, [u64]),
         "kc_window_fingerprint": (i32, [vp, vp, u64, i32, C.POINTER(u64), C.POINTER(u64)]),
         "kc_sparse_fingerprint": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
@@ -315,7 +318,7 @@ class SeqSet:
 class RadixPlan(C.Structure):
     """kc_radix_plan (include/kmer_b200.h)"""
     _fields_ = [("k", C.c_int32), ("world", C.c_uint32), ("partitions", C.c_uint32), ("parts_per_rank", C.c_uint32),
-                ("grid", C.c_uint32), ("rec_bytes", C.c_uint32), ("shape", C.c_uint32), ("reserved", C.c_uint32),
+                ("grid", C.c_uint32), ("rec_bytes", C.c_uint32), ("shape", C.c_uint32), ("round_bits", C.c_uint32),
                 ("max_windows", C.c_uint64), ("region_records", C.c_uint64), ("slab_bytes", C.c_uint64),
                 ("counts_bytes", C.c_uint64)]
 
@@ -491,23 +494,38 @@ class Context:
         self._check(lib().kc_sparse_radix_plan(self._h, max_windows, k, world, C.addressof(plan)))
         return plan
 
-    def radix_scatter(self, d_data, nbytes, plan):
-        """-> (slabs uint8[plan.slab_bytes], counts int32[plan.counts_bytes / 4]) on this GPU,
-        partition-major; raises KmerError(KC_ERR_TABLE_FULL) when a region overflowed"""
+    def radix_scatter(self, d_data, nbytes, plan, rnd=0, out=None):
+        """-> (slabs uint8[plan.slab_bytes], counts int32[plan.counts_bytes / 4]) on this GPU, partition-major, for
+        round `rnd` of the plan (`out` = buffers of an earlier round to reuse); raises KmerError(KC_ERR_TABLE_FULL)
+        when a region overflowed"""
         torch = self._torch()
         torch.cuda.current_stream().synchronize()
         dev = "cuda:%d" % self.device
-        slabs = torch.empty(plan.slab_bytes, dtype=torch.uint8, device=dev)
-        counts = torch.empty(plan.counts_bytes // 4, dtype=torch.int32, device=dev)
+        if out is None:
+            slabs = torch.empty(plan.slab_bytes, dtype=torch.uint8, device=dev)
+            counts = torch.empty(plan.counts_bytes // 4, dtype=torch.int32, device=dev)
+        else:
+            slabs, counts = out
         torch.cuda.current_stream().synchronize()
-        self._check(lib().kc_sparse_radix_scatter(self._h, _ptr(d_data), nbytes, C.addressof(plan), _ptr(slabs), _ptr(counts)))
+        self._check(lib().kc_sparse_radix_scatter_round(self._h, _ptr(d_data), nbytes, C.addressof(plan), rnd, _ptr(slabs), _ptr(counts)))
         return slabs, counts
 
-    def radix_count(self, plan, slabs, counts, nsrc, part_first, nparts):
+    def radix_count(self, plan, slabs, counts, nsrc, part_first, nparts, rnd=0):
         self._torch().cuda.current_stream().synchronize()
         h = C.c_void_p()
-        self._check(lib().kc_sparse_radix_count(self._h, C.addressof(plan), _ptr(slabs), _ptr(counts), nsrc, part_first, nparts,
-                                                C.byref(h)))
+        self._check(lib().kc_sparse_radix_count_round(self._h, C.addressof(plan), rnd, _ptr(slabs), _ptr(counts), nsrc, part_first,
+                                                      nparts, C.byref(h)))
+        return Sparse(self, h)
+
+    def sparse_concat(self, parts):
+        """one result from ascending pieces (the rounds of a radix plan); the pieces are closed"""
+        if len(parts) == 1:
+            return parts[0]
+        arr = (C.c_void_p * len(parts))(*[p._h for p in parts])
+        h = C.c_void_p()
+        self._check(lib().kc_sparse_concat(self._h, arr, len(parts), C.byref(h)))
+        for p in parts:
+            p.close()
         return Sparse(self, h)
 
     # ---- full-scale self-checks (csrc/check.cu): (fingerprint, total) pairs; a correct count has equal pairs ----

@@ -142,17 +142,30 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
     plan = stage(lambda: engine.radix_plan(int(t.item()), k, world), dev)
     if plan is None:
         return None
-    sc = stage(lambda: engine.radix_scatter(reads, nbytes, plan), dev)
-    if sc is None:
-        return None
-    slabs, counts = sc
-    del sc
-    bufs = stage(lambda: (torch.empty_like(slabs), torch.empty_like(counts)), dev)
-    recv_s, recv_c = bufs
-    dist.all_to_all_single(recv_s, slabs)  # equal splits: block o = partitions [o, o+1) * parts_per_rank
-    dist.all_to_all_single(recv_c, counts)
-    del slabs, counts, bufs
-    return stage(lambda: engine.radix_count(plan, recv_s, recv_c, world, rank * plan.parts_per_rank, plan.parts_per_rank), dev)
+    # Large inputs run in 2^round_bits rounds (round r = the windows whose top code bits are r; the plan sizes them so
+    # that a leaf fits shared memory and the slabs fit the device): every round has its own scatter, all-to-all and
+    # count and reuses the buffers; rank r's pieces are ascending code ranges, joined at the end.
+    rounds = 1 << getattr(plan, "round_bits", 0)
+    parts, bufs, recv = [], None, None
+    for rnd in range(rounds):
+        sc = stage(lambda: engine.radix_scatter(reads, nbytes, plan, rnd, bufs), dev)
+        if sc is None:
+            for p in parts:
+                p.close()
+            return None
+        bufs = sc
+        if recv is None:
+            recv = stage(lambda: (torch.empty_like(bufs[0]), torch.empty_like(bufs[1])), dev)
+        dist.all_to_all_single(recv[0], bufs[0])  # equal splits: block o = partitions [o, o+1) * parts_per_rank
+        dist.all_to_all_single(recv[1], bufs[1])
+        res = stage(lambda: engine.radix_count(plan, recv[0], recv[1], world, rank * plan.parts_per_rank, plan.parts_per_rank, rnd), dev)
+        if res is None:
+            for p in parts:
+                p.close()
+            return None
+        parts.append(res)
+    del bufs, recv
+    return parts[0] if rounds == 1 else stage(lambda: engine.sparse_concat(parts), dev)
 
 
 def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):

@@ -239,7 +239,9 @@ typedef struct kc_radix_plan {
     uint32_t grid;            /* pass-1 CTAs = regions per partition and rank                   */
     uint32_t rec_bytes;       /* size of a level-1 record: 4 (k <= 21) or 8                     */
     uint32_t shape;           /* 0 = shipped 1024 x 1024, 1 = 16 x 16 (KC_SPARSE_RADIX_SHAPE=small, tests) */
-    uint32_t reserved;
+    uint32_t round_bits;      /* the count runs in 2^round_bits ROUNDS: round r holds the windows whose top round_bits
+                                 code bits are r (chosen by kc_sparse_radix_plan so that a leaf fits shared memory and
+                                 the slabs fit the device; 0 = one round)                        */
     uint64_t max_windows;     /* the plan is good for inputs of up to this many windows per rank */
     uint64_t region_records;  /* capacity of one (partition, CTA) region                         */
     uint64_t slab_bytes;      /* partitions * grid * region_records * rec_bytes                  */
@@ -258,6 +260,16 @@ KC_API int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nby
 KC_API int kc_sparse_radix_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_slabs,
                                  const uint32_t* d_counts, uint32_t nsrc, uint32_t part_first,
                                  uint32_t nparts, kc_sparse** out);
+/* The same two stages for ONE round of a plan with round_bits > 0 (run the rounds 0 .. 2^round_bits - 1
+ * one after the other, each with its own all-to-all; the slab buffers can be reused).  Rank r's results of
+ * consecutive rounds are ascending code ranges: kc_sparse_concat joins them (the pieces stay valid).    */
+KC_API int kc_sparse_radix_scatter_round(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
+                                         const kc_radix_plan* plan, uint32_t round, void* d_slabs,
+                                         uint32_t* d_counts);
+KC_API int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round,
+                                       const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+                                       uint32_t part_first, uint32_t nparts, kc_sparse** out);
+KC_API int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_sparse** out);
 KC_API void kc_sparse_free(kc_sparse* s);
 KC_API uint64_t kc_sparse_size(const kc_sparse* s);
 KC_API const uint64_t* kc_sparse_d_keys(const kc_sparse* s);    /* device, sorted */

@@ -104,3 +104,29 @@ def test_fingerprint_self_checks(ctx, kmerlib, oracle):
     sp = ctx.count_sparse(big, nreads * 151, 21, kmerlib.SPARSE_AUTO)
     assert ctx.sparse_fingerprint(sp) == fin + (0,)
     sp.close()
+
+
+def test_sparse_radix_rounds(kmerlib):
+    """KC_SPARSE_RADIX in several ROUNDS (what inputs too large for one pass take: kc_sparse_radix_plan picks round_bits
+    from leaf capacity and device memory; KC_SPARSE_RADIX_RBITS forces it at test sizes, read once per process, hence
+    the child): the result must equal the hash path's and the input's window fingerprint, keys strictly ascending"""
+    code = r"""
+import os, sys
+sys.path.insert(0, os.path.join(%r, "dna-kmeres-parallel_b200"))
+import numpy as np, kmerb200 as K
+ctx = K.Context(0)
+for k, nreads in ((21, %d), (31, %d), (13, %d)):
+    reads = ctx.gen_reads(0xB2000004, 50_000_000, 150, 200, 0, nreads)
+    nb = nreads * 151
+    a = ctx.count_sparse(reads, nb, k, K.SPARSE_HASH)
+    b = ctx.count_sparse(reads, nb, k, K.SPARSE_RADIX | K.SPARSE_NO_FALLBACK)
+    ka, ca = a.to_host(); kb, cb = b.to_host()
+    assert len(a) == len(b) and (ka == kb).all() and (ca == cb).all(), k
+    assert ctx.sparse_fingerprint(b) == ctx.window_fingerprint(reads, nb, k) + (0,), k
+print("ROUNDS_OK")
+""" % (ROOT, sz(150_000) if FULL else 700, sz(100_000) if FULL else 500, sz(100_000) if FULL else 500)
+    import subprocess
+    for rbits in ("1", "3"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=200,
+                           env=dict(os.environ, KC_SPARSE_RADIX_RBITS=rbits))
+        assert r.returncode == 0 and "ROUNDS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]

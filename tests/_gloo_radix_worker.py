@@ -40,23 +40,23 @@ class EmuEngine:
         self._check(self.ctx.L.kc_sparse_radix_plan(self.ctx.h, max_windows, k, world, C.byref(plan)))
         return plan
 
-    def radix_scatter(self, reads, nbytes, plan):
+    def radix_scatter(self, reads, nbytes, plan, rnd=0, out=None):
         base, p = self.ctx.upload(reads.numpy(), 1)
         d_s, d_c = self.ctx.alloc(plan.slab_bytes), self.ctx.alloc(plan.counts_bytes)
         try:
-            self._check(self.ctx.L.kc_sparse_radix_scatter(self.ctx.h, p, nbytes, C.byref(plan), d_s, d_c))
+            self._check(self.ctx.L.kc_sparse_radix_scatter_round(self.ctx.h, p, nbytes, C.byref(plan), rnd, d_s, d_c))
             return (torch.from_numpy(self.ctx.download(d_s, plan.slab_bytes, np.uint8)),
                     torch.from_numpy(self.ctx.download(d_c, plan.counts_bytes, np.int32)))
         finally:
             for q in (base, d_s, d_c):
                 self.ctx.free(q)
 
-    def radix_count(self, plan, slabs, counts, nsrc, part_first, nparts):
+    def radix_count(self, plan, slabs, counts, nsrc, part_first, nparts, rnd=0):
         b1, d_s = self.ctx.upload(slabs.numpy())
         b2, d_c = self.ctx.upload(counts.numpy())
         sp = C.c_void_p()
         try:
-            self._check(self.ctx.L.kc_sparse_radix_count(self.ctx.h, C.byref(plan), d_s, d_c, nsrc, part_first, nparts, C.byref(sp)))
+            self._check(self.ctx.L.kc_sparse_radix_count_round(self.ctx.h, C.byref(plan), rnd, d_s, d_c, nsrc, part_first, nparts, C.byref(sp)))
         finally:
             self.ctx.free(b1)
             self.ctx.free(b2)
@@ -65,6 +65,9 @@ class EmuEngine:
         self.ctx.check(self.ctx.L.kc_sparse_copy_to_host(self.ctx.h, sp, keys.ctypes.data, cnts.ctypes.data))
         self.ctx.L.kc_sparse_free(sp)
         return keys, cnts
+
+    def sparse_concat(self, parts):  # the rounds' pieces of this rank, ascending
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
 
 
 def main():
@@ -80,8 +83,13 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, (keys, cnts))
         if rank == 0:
-            allk = np.concatenate([g[0] for g in gathered])  # rank order = code order: no sort here
+            allk = np.concatenate([g[0] for g in gathered])  # one round: rank order = code order, no sort here
             allc = np.concatenate([g[1] for g in gathered])
+            if int(os.environ.get("KC_SPARSE_RADIX_RBITS", "0")) > 0:  # several rounds: every rank holds one ascending range per round
+                for g in gathered:
+                    assert (np.diff(g[0].astype(np.int64)) > 0).all(), "a rank's keys must be ascending"
+                order = np.argsort(allk, kind="stable")
+                allk, allc = allk[order], allc[order]
             whole = O.gen_reads(0xB2000004, genome, 100, 50, 0, nreads)
             wk, wc, _ = O.count_sparse(whole, k)
             assert allk.size == wk.size and (allk == wk).all() and (allc == wc).all(), "sharded radix != whole (k=%d)" % k

@@ -33,8 +33,13 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, (keys, counts))
         if rank == 0:
-            allk = np.concatenate([g[0] for g in gathered])  # rank order = code order
+            allk = np.concatenate([g[0] for g in gathered])  # one round: rank order = code order
             allc = np.concatenate([g[1] for g in gathered])
+            if int(os.environ.get("KC_SPARSE_RADIX_RBITS", "0")) > 0:  # several rounds: one ascending range per round and rank
+                for g in gathered:
+                    assert (np.diff(g[0].astype(np.int64)) > 0).all(), "a rank's keys must be ascending"
+                order = np.argsort(allk, kind="stable")
+                allk, allc = allk[order], allc[order]
             whole = O.gen_reads(0xB2000004, 20_000_000, 150, 200, 0, nreads)
             wk, wc, _ = O.count_sparse(whole, k)
             assert allk.size == wk.size and (allk == wk).all() and (allc == wc).all(), "sharded radix != oracle (k=%d)" % k

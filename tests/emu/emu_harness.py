@@ -88,6 +88,9 @@ def lib():
         L.kc_count_dense_host_packed_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
         L.kc_sparse_radix_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p]
         L.kc_sparse_radix_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kc_sparse_radix_scatter_round.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.kc_sparse_radix_count_round.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.c_void_p]
         L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                             C.POINTER(C.c_void_p)]
         L.kc_gen_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
@@ -100,7 +103,7 @@ def lib():
 
 class RadixPlan(C.Structure):  # kc_radix_plan (include/kmer_b200.h)
     _fields_ = [("k", C.c_int32), ("world", C.c_uint32), ("partitions", C.c_uint32), ("parts_per_rank", C.c_uint32),
-                ("grid", C.c_uint32), ("rec_bytes", C.c_uint32), ("shape", C.c_uint32), ("reserved", C.c_uint32),
+                ("grid", C.c_uint32), ("rec_bytes", C.c_uint32), ("shape", C.c_uint32), ("round_bits", C.c_uint32),
                 ("max_windows", C.c_uint64), ("region_records", C.c_uint64), ("slab_bytes", C.c_uint64),
                 ("counts_bytes", C.c_uint64)]
 
@@ -312,34 +315,39 @@ def case_radix_sharded(args):
     plan = RadixPlan()
     ctx.check(L.kc_sparse_radix_plan(ctx.h, max(max(x.size - k + 1, 0) for x in reads), k, world, C.byref(plan)))
     assert plan.parts_per_rank * world == plan.partitions
-    slabs, counts = [], []
-    for x in reads:
-        base, p = ctx.upload(x, 3)
-        d_s, d_c = ctx.alloc(plan.slab_bytes), ctx.alloc(plan.counts_bytes)
-        ctx.check(L.kc_sparse_radix_scatter(ctx.h, p, x.size, C.byref(plan), d_s, d_c))
-        slabs.append(ctx.download(d_s, plan.slab_bytes, np.uint8))
-        counts.append(ctx.download(d_c, plan.counts_bytes, np.uint32))
-        for q in (base, d_s, d_c):
-            ctx.free(q)
+    rounds = 1 << plan.round_bits  # > 1 only when KC_SPARSE_RADIX_RBITS forces it at these sizes
     sb, cb = plan.slab_bytes // world, plan.counts_bytes // 4 // world   # one rank's block of a scatter output
-    keys, cnts = [], []
-    for o in range(world):
-        recv_s = np.concatenate([slabs[src][o * sb:(o + 1) * sb] for src in range(world)])
-        recv_c = np.concatenate([counts[src][o * cb:(o + 1) * cb] for src in range(world)])
-        b1, d_s = ctx.upload(recv_s)
-        b2, d_c = ctx.upload(recv_c)
-        sp = C.c_void_p()
-        ctx.check(L.kc_sparse_radix_count(ctx.h, C.byref(plan), d_s, d_c, world, o * plan.parts_per_rank, plan.parts_per_rank,
-                                          C.byref(sp)))
-        n = int(L.kc_sparse_size(sp))
-        kk, cc = np.empty(n, np.uint64), np.empty(n, np.uint32)
-        ctx.check(L.kc_sparse_copy_to_host(ctx.h, sp, kk.ctypes.data, cc.ctypes.data))
-        L.kc_sparse_free(sp)
-        ctx.free(b1)
-        ctx.free(b2)
-        keys.append(kk)
-        cnts.append(cc)
-    allk, allc = np.concatenate(keys), np.concatenate(cnts)
+    keys, cnts = [[] for _ in range(world)], [[] for _ in range(world)]
+    for rnd in range(rounds):
+        slabs, counts = [], []
+        for x in reads:
+            base, p = ctx.upload(x, 3)
+            d_s, d_c = ctx.alloc(plan.slab_bytes), ctx.alloc(plan.counts_bytes)
+            ctx.check(L.kc_sparse_radix_scatter_round(ctx.h, p, x.size, C.byref(plan), rnd, d_s, d_c))
+            slabs.append(ctx.download(d_s, plan.slab_bytes, np.uint8))
+            counts.append(ctx.download(d_c, plan.counts_bytes, np.uint32))
+            for q in (base, d_s, d_c):
+                ctx.free(q)
+        for o in range(world):
+            recv_s = np.concatenate([slabs[src][o * sb:(o + 1) * sb] for src in range(world)])
+            recv_c = np.concatenate([counts[src][o * cb:(o + 1) * cb] for src in range(world)])
+            b1, d_s = ctx.upload(recv_s)
+            b2, d_c = ctx.upload(recv_c)
+            sp = C.c_void_p()
+            ctx.check(L.kc_sparse_radix_count_round(ctx.h, C.byref(plan), rnd, d_s, d_c, world, o * plan.parts_per_rank, plan.parts_per_rank,
+                                                    C.byref(sp)))
+            n = int(L.kc_sparse_size(sp))
+            kk, cc = np.empty(n, np.uint64), np.empty(n, np.uint32)
+            ctx.check(L.kc_sparse_copy_to_host(ctx.h, sp, kk.ctypes.data, cc.ctypes.data))
+            L.kc_sparse_free(sp)
+            ctx.free(b1)
+            ctx.free(b2)
+            keys[o].append(kk)
+            cnts[o].append(cc)
+    # round-major, rank-minor is code order (one round: rank order)
+    allk = np.concatenate([keys[o][rnd] for rnd in range(rounds) for o in range(world)])
+    allc = np.concatenate([cnts[o][rnd] for rnd in range(rounds) for o in range(world)])
+    keys = [np.concatenate(kl) for kl in keys]
     wk, wc, _ = O.count_sparse(np.concatenate(reads), k)
     assert allk.size == wk.size and (allk == wk).all() and (allc == wc).all(), "sharded radix differs from the oracle"
     assert all(kk.size > 0 for kk in keys), "a rank owns nothing?"

@@ -296,9 +296,10 @@ def test_nccl_range_sharded_radix():
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
            "--master-addr", "127.0.0.1", "--master-port", "29661", os.path.join(ROOT, "tests", "_nccl_radix_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "NCCL_RADIX_WORKER_OK world=%d" % world in r.stdout
+    for rbits in ("0", "2"):  # one round, and four rounds forced (what large inputs take: kc_sparse_radix_plan)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, KC_SPARSE_RADIX_RBITS=rbits))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        assert "NCCL_RADIX_WORKER_OK world=%d" % world in r.stdout
 
 
 def test_nccl_per_seq_sharded():

@@ -24,6 +24,7 @@ _state = {"t0": None, "gpu_lost": False}
 CASES = [
     "test_partition_wide2",
     "test_fingerprint_self_checks",
+    "test_sparse_radix_rounds",
 ]
 
 
