@@ -48,6 +48,7 @@ struct kc_ctx {
     size_t scratch2_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    uint64_t caller_reusable_bytes = 0;  // device memory the caller holds in its own cache and will hand back (kc_ctx_set_reusable_bytes)
     uint64_t last_h2d_bytes = 0;        // bytes the last *_host* entry point sent over PCIe (kc_ctx_last_h2d_bytes)
     // optional per-kernel timing (kc_ctx_set_timing)
     bool timing = false;

@@ -717,7 +717,9 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
         cudaGetLastError();
         free_b = total_b = 0;
     }
-    free_b += kc_pool_idle_bytes(ctx->device);
+    // memory this count can take again: the pool's idle blocks, the ctx's own scratch (the slabs of the last call
+    // live there) and what the caller says its allocator has cached (the multi-GPU path keeps the slabs in torch tensors)
+    free_b += kc_pool_idle_bytes(ctx->device) + ctx->scratch_bytes + ctx->scratch2_bytes + (size_t)ctx->caller_reusable_bytes;
     int rbits = 0;
     for (;; rbits++) {
         const int r1 = 2 * k - rbits - Shape::KB1, r2 = r1 - Shape::KB2;
@@ -732,7 +734,9 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
         const uint64_t leaf_cap = (uint64_t)Shape::LEAF_CAP / (r2 <= 32 ? 1 : 2);  // records of 4 or 8 bytes
         const uint64_t leaf_mean = ((uint64_t)world * max_windows >> rbits) / ((uint64_t)Shape::P1 * Shape::P2);
         const uint64_t slab = (max_windows >> rbits) * (r1 <= 32 ? 4 : 8);
-        const bool leaf_ok = leaf_mean * 5 <= leaf_cap * 3;                       // mean <= 60 % of the capacity
+        // mean <= 65 % of the capacity: a leaf holds ~coverage copies of every k-mer in it (compound Poisson); config 4
+        // at 30 x has mean 12.4 K, sigma 0.6 K against 20 480, and ran in one round without an overflow
+        const bool leaf_ok = leaf_mean * 20 <= leaf_cap * 13;
         const bool mem_ok = free_b == 0 || (slab + slab / 4) * (world > 1 ? 2 : 1) <= free_b / 2;  // + the received copy
         if ((leaf_ok && mem_ok) || rbits >= 8) break;
     }
@@ -861,7 +865,8 @@ int kc_sparse_radix_count(kc_ctx* ctx, const kc_radix_plan* plan, const void* d_
 }
 
 // results of consecutive rounds (or any ascending pieces) -> one result; the pieces stay valid
-int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_sparse** out) {
+// (consume = true, internal: every piece is freed as soon as it has been copied, so that the peak is the result + one piece)
+static int sparse_concat(kc_ctx* ctx, kc_sparse** parts, uint32_t nparts, kc_sparse** out, bool consume) {
     if (!ctx || !out || (!parts && nparts)) return KC_ERR_INVALID;
     *out = nullptr;
     DeviceGuard dg(ctx->device);
@@ -887,11 +892,19 @@ int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_s
             KC_CUDA(ctx, cudaMemcpyAsync(res->d_keys + at, parts[i]->d_keys, parts[i]->size * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             KC_CUDA(ctx, cudaMemcpyAsync(res->d_counts + at, parts[i]->d_counts, parts[i]->size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             at += parts[i]->size;
+            if (consume) {
+                KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                kc_sparse_free(parts[i]);
+                parts[i] = nullptr;
+            }
         }
         KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     *out = res;
     return KC_OK;
+}
+int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_sparse** out) {
+    return sparse_concat(ctx, const_cast<kc_sparse**>(parts), nparts, out, false);
 }
 
 }  // extern "C"
@@ -923,7 +936,7 @@ int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_
             *out = parts[0];
             parts[0] = nullptr;
         } else {
-            rc = kc_sparse_concat(ctx, parts.data(), rounds, out);
+            rc = sparse_concat(ctx, parts.data(), rounds, out, true);
         }
     }
     for (kc_sparse* p : parts) kc_sparse_free(p);

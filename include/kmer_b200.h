@@ -247,6 +247,9 @@ typedef struct kc_radix_plan {
     uint64_t slab_bytes;      /* partitions * grid * region_records * rec_bytes                  */
     uint64_t counts_bytes;    /* partitions * grid * 4                                           */
 } kc_radix_plan;
+/* Device memory the caller's own allocator has cached and will reuse for the buffers it passes in (a torch caller:
+ * memory_reserved - memory_allocated): kc_sparse_radix_plan counts it as available when it sizes the rounds. */
+KC_API void kc_ctx_set_reusable_bytes(kc_ctx* ctx, uint64_t nbytes);
 /* same plan on every rank: pass the LARGEST per-rank window count */
 KC_API int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world,
                                 kc_radix_plan* plan);
