@@ -652,6 +652,38 @@ def main():
     ms_step, value, launches, clocks, checksum, graph, table_fp = (res["ms_step"], res["value"], res["launches"], res["clocks"],
                                                                    res["checksum"], res["graph"], res["fp"])
 
+    # ---- N > 1: where the step goes (each phase alone, CUDA events, max over ranks) ----
+    phases = None
+    if world > 1:
+        def phase(fn, pre=None):
+            for _ in range(3):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = 0.0
+            n_ph = min(args.steps, 10)
+            for _ in range(n_ph):
+                if pre:
+                    pre()
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            t_ph = torch.tensor([tot / n_ph], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_ph, op=dist.ReduceOp.MAX)
+            return float(t_ph.item())
+
+        def count_only():
+            table.zero_()
+            ctx.count_dense_range(data, nb, 0, e - b, k, table, algo=args.algo)
+
+        phases = {"zero_fill_and_count_ms": phase(count_only),
+                  "nccl_reduce_ms": phase(lambda: dist.reduce(table, dst=0, op=dist.ReduceOp.SUM), pre=barrier),
+                  "note": "each phase timed alone (the reduce behind a barrier, so without waiting for the slowest rank's count); "
+                          "the step above is count + reduce back to back, max over ranks"}
+        count_only()  # leave a valid local table behind (the reduce test summed stale tables)
+
     # ---- per-kernel times for the roofline (events on the launching stream) ----
     kmerb200.lib().kc_ctx_set_timing(ctx._h, 1)
     passes = []
@@ -849,6 +881,7 @@ def main():
                        "sharding": ("window ranges + %d-byte halo; ncclReduce of uint32[4^k] to rank 0%s"
                                     % (k - 1, "" if S == 1 else " in %d slices overlapped with counting" % S))
                        if world > 1 else "single GPU",
+                       "phases": phases,
                        "table_checksum": checksum, "table_fingerprint": table_fp,
                        "probe": probe_report},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

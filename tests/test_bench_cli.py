@@ -73,6 +73,7 @@ def test_probe_variants_decision(tmp_path, monkeypatch):
     fake.write_text(FAKE_PROBE)
     monkeypatch.setattr(bench, "PROBE_SCRIPT", str(fake))
     monkeypatch.setenv("KC_BENCH_PROBE_SLACK_S", "3")
+    monkeypatch.setenv("KC_BENCH_PROBE_CANDIDATES", "4,5,6,7")  # the stand-in child knows these
     args = argparse.Namespace(workload="config3", length=987654321)  # the length keys the cache file: unique to this test
     import glob
     for f in glob.glob("/tmp/kc_bench_probe_config3_987654321_*.json"):
@@ -87,6 +88,7 @@ def test_probe_variants_decision(tmp_path, monkeypatch):
     assert best2 == 6 and "cached" in rep2
     for f in glob.glob("/tmp/kc_bench_probe_config3_987654321_*.json"):
         os.remove(f)
+    monkeypatch.delenv("KC_BENCH_PROBE_CANDIDATES")
     assert bench.probe_variants(args, 5, 0) == (0, None)   # no candidates for this k
 
 
@@ -110,7 +112,7 @@ def test_gpu_arm_dry_run_single(tmp_path):
     for f in glob.glob("/tmp/kc_bench_probe_tiny_k12_*.json"):
         os.remove(f)
     env = dict(os.environ, KC_EMU_SMS="4", KC_BENCH_PROBE_CANDIDATES="4")
-    r = subprocess.run([sys.executable, DRYRUN, "--workload", "tiny_k12", "--steps", "1", "--cpu-sample", "300000"], env=env,
+    r = subprocess.run([sys.executable, DRYRUN, "--workload", "tiny_k12", "--steps", "1", "--cpu-sample", "300000", "--probe-variants"], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     d = _one_line(r.stdout)
