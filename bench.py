@@ -722,19 +722,22 @@ def main():
     achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
     step_bytes = (L + 4 * nk)
     step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this
-    # workload, scaled by the bases this launch processed (bench.py cannot run ncu itself)
-    traffic = None
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of THIS kernel on THIS workload
+    # with the library default (profiles/r02_traffic.json records workload and algo per capture), scaled by the bases
+    # this launch processed.  bench.py cannot run ncu itself; a run with another algo or workload reports null.
+    traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f)
-        if args.workload == "config3" and dom in tj["kernels"]:
-            kj = tj["kernels"][dom]
-            traffic = (kj["dram_bytes_read"] + kj["dram_bytes_write"]) * bases_launch / tj["bases_per_launch"]
+        kj = tj["kernels"].get(dom)
+        if kj and args.algo == 0 and tj["algo"].get(kj["capture"]) == "auto" and tj["workload"].get(kj["capture"]) == args.workload \
+                and not os.environ.get("KC_DENSE_AUTO_R01"):
+            traffic = (kj["dram_bytes_read"] + kj["dram_bytes_write"]) * bases_launch / tj["bases_per_launch"][kj["capture"]]
+            traffic_src = "profiles/r02_traffic.json (ncu capture of %s, %s, algo auto)" % (dom, args.workload)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu)" if traffic else None,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "kernel_ms": {n: v[0] for n, v in kernels.items()},
                 "algorithmic_bytes_per_launch": dbytes,

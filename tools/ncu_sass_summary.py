@@ -11,6 +11,7 @@ def main():
     rows = list(csv.reader(open(sys.argv[1])))
     topn = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     i = 0
+    seen = set()
     while i < len(rows):
         if rows[i] and rows[i][0] == "Kernel Name":
             name = rows[i][1]
@@ -35,8 +36,12 @@ def main():
                 op = op.split(".")[0]
                 ops[op] += n
                 opsamp[op] += int(r[ix["# Samples"]] or 0)
-                opwf[op] += int(r[ix["L1 Wavefronts Shared"]] or 0)
+                if "L1 Wavefronts Shared" in ix:
+                    opwf[op] += int(r[ix["L1 Wavefronts Shared"]] or 0)
                 lines.append((int(r[ix["# Samples"]] or 0), n, r[ix["Source"]]))
+            if name in seen:  # one launch per kernel is enough
+                continue
+            seen.add(name)
             print("====", name[:110])
             print("SASS instructions %d, warp-instructions executed %d" % (len(lines), inst))
             S = sum(tot.values()) or 1
