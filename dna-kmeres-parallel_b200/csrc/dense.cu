@@ -300,19 +300,21 @@ dense_smem16c_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t*
     }
 }
 
+// grid (32768 / 256, SLICES): slice y adds the partial tables p = y, y + SLICES, ... (148 sequential loads per thread
+// made this kernel 27 us for 19 MB in round 2's first capture; 8 slices and one RED per word and slice instead)
 __global__ void smem16c_reduce_kernel(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ flags,
                                       int nparts, uint32_t* __restrict__ table) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= 32768) return;
     uint32_t lo = 0, hi = 0;
-    for (int p = 0; p < nparts; p++) {
+    for (int p = blockIdx.y; p < nparts; p += gridDim.y) {
         if (flags[p]) continue;  // that CTA's table wrapped: smem16_repair_kernel recounts its groups
-        const uint32_t v = partials[(uint64_t)p * 32768 + w];
+        const uint32_t v = kc_ld_cg(partials + (uint64_t)p * 32768 + w);
         lo += v & 0xFFFFu;
         hi += v >> 16;
     }
-    table[w] += lo;
-    table[w + 32768] += hi;
+    if (lo) atomicAdd(table + w, lo);
+    if (hi) atomicAdd(table + w + 32768, hi);
 }
 
 // one CTA per pass-1 CTA; does nothing unless that CTA's checksum failed
@@ -1217,7 +1219,7 @@ static int dense_smem16(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64
         KC_LAUNCH(dense_smem16c_kernel<DEPTH>, grid, 1024, smem, st, base, ngroups, partials, flags);
         KC_LAUNCH_CHECK(ctx, "dense_smem16c_kernel");
         if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[1], st));
-        KC_LAUNCH(smem16c_reduce_kernel, 32768 / 256, 256, 0, st, partials, flags, grid, d_table);
+        KC_LAUNCH(smem16c_reduce_kernel, dim3(32768 / 256, 8), 256, 0, st, partials, flags, grid, d_table);
         KC_LAUNCH_CHECK(ctx, "smem16c_reduce_kernel");
         KC_LAUNCH(smem16_repair_kernel<DEPTH>, grid, 256, 0, st, base, ngroups, grid, flags, d_table);
         KC_LAUNCH_CHECK(ctx, "smem16_repair_kernel");

@@ -218,11 +218,19 @@ uint64_t next_pow2(uint64_t x) {
 int sort_reduce_pairs(kc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n, int key_bits,
                       kc_sparse** out) {
     cudaStream_t st = ctx->stream;
-    kc_sparse* res = new kc_sparse();
+    *out = nullptr;  // published only on success: an error return never leaves a live handle behind
+    struct Owned {
+        kc_sparse* p;
+        ~Owned() { kc_sparse_free(p); }
+    } own{new kc_sparse()};
+    kc_sparse* res = own.p;
     res->ctx = ctx;
     res->device = ctx->device;
-    *out = res;
-    if (n == 0) return KC_OK;
+    if (n == 0) {
+        *out = res;
+        own.p = nullptr;
+        return KC_OK;
+    }
     DevBuf ks, cs, uk, uc, nr, tmp;
     if (ks.alloc(n * 8) || cs.alloc(n * 4) || uk.alloc(n * 8) || uc.alloc(n * 4) || nr.alloc(16)) {
         cudaGetLastError();
@@ -250,6 +258,8 @@ int sort_reduce_pairs(kc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_cou
     res->size = nruns;
     res->d_keys = (uint64_t*)uk.release();
     res->d_counts = (uint32_t*)uc.release();
+    *out = res;
+    own.p = nullptr;
     return KC_OK;
 }
 

@@ -501,17 +501,27 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
 }
 
 // ---------------------------------------------------------------------------
-// K3: exclusive scan of leaf_n (one CTA; leaves in code order)
+// K3: exclusive scan of leaf_n (leaves in code order), three small launches: per-block sums, scan of the block sums
+// by one CTA, per-block scan with its offset.  (One CTA walking all 2^20 leaves took 1.8 ms: profiles/r02_ncu_sp_*.)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(SP_THREADS, 1)
-sp_scan_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, unsigned long long* __restrict__ leaf_off,
-               SpCtl* ctl) {
+sp_scan_sums_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, unsigned long long* __restrict__ block_sums) {
+    __shared__ uint32_t s_warp[33];
+    const uint64_t i = (uint64_t)blockIdx.x * SP_THREADS + threadIdx.x;
+    uint32_t tot;
+    block_excl_scan(i < nleaves ? leaf_n[i] : 0u, s_warp, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sp_scan_blocks_kernel(unsigned long long* __restrict__ block_sums, uint32_t nblocks, SpCtl* ctl) {
+    // nblocks <= a few thousand: thread t owns a run of blocks, thread 0 combines the 1024 run totals
     __shared__ unsigned long long s_sum[SP_THREADS];
     const int tid = threadIdx.x;
-    const uint64_t per = (nleaves + SP_THREADS - 1) / SP_THREADS;
-    const uint64_t b = min((uint64_t)tid * per, nleaves), e = min(b + per, nleaves);
+    const uint32_t per = (nblocks + SP_THREADS - 1) / SP_THREADS;
+    const uint32_t b = min((uint32_t)tid * per, nblocks), e = min(b + per, nblocks);
     unsigned long long mine = 0;
-    for (uint64_t i = b; i < e; i++) mine += leaf_n[i];
+    for (uint32_t i = b; i < e; i++) mine += block_sums[i];
     s_sum[tid] = mine;
     __syncthreads();
     if (tid == 0) {
@@ -525,10 +535,21 @@ sp_scan_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, unsigned l
     }
     __syncthreads();
     unsigned long long run = s_sum[tid];
-    for (uint64_t i = b; i < e; i++) {
-        leaf_off[i] = run;
-        run += leaf_n[i];
+    for (uint32_t i = b; i < e; i++) {
+        const unsigned long long v = block_sums[i];
+        block_sums[i] = run;  // exclusive prefix of the block
+        run += v;
     }
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sp_scan_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, const unsigned long long* __restrict__ block_sums,
+               unsigned long long* __restrict__ leaf_off) {
+    __shared__ uint32_t s_warp[33];
+    const uint64_t i = (uint64_t)blockIdx.x * SP_THREADS + threadIdx.x;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(i < nleaves ? leaf_n[i] : 0u, s_warp, &tot);
+    if (i < nleaves) leaf_off[i] = block_sums[blockIdx.x] + ex;
 }
 
 // ---------------------------------------------------------------------------
@@ -620,7 +641,8 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void
     const size_t b_ctl = pad(sizeof(SpCtl));
     const size_t b_leaf_n = pad(nleaves * 4), b_leaf_base = pad(nleaves * 8), b_leaf_off = pad(nleaves * 8);
     const size_t b_scratch2 = pad((size_t)grid2 * Shape::P2 * cap2 * sizeof(R2T));
-    if (b_ctl + b_leaf_n + b_leaf_base + b_leaf_off + b_scratch2 > work_bytes)
+    const size_t b_sums = pad(((nleaves + SP_THREADS - 1) / SP_THREADS) * 8);
+    if (b_ctl + b_leaf_n + b_leaf_base + b_leaf_off + b_scratch2 + b_sums > work_bytes)
         return kc_set_error(ctx, KC_ERR_INVALID, "sparse radix: internal work area too small");
     SpCtl* ctl = (SpCtl*)work;
     uint32_t* leaf_n = (uint32_t*)(work + b_ctl);
@@ -657,8 +679,16 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void
                   out_cap, leaf_base, leaf_n, ctl, flush256_env());
         KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
     }
-    KC_LAUNCH(sp_scan_kernel, 1, SP_THREADS, 0, st, leaf_n, nleaves, leaf_off, ctl);
-    KC_LAUNCH_CHECK(ctx, "sp_scan_kernel");
+    {
+        const uint32_t nblocks = (uint32_t)((nleaves + SP_THREADS - 1) / SP_THREADS);
+        unsigned long long* block_sums = (unsigned long long*)((char*)scratch2 + b_scratch2);
+        KC_LAUNCH(sp_scan_sums_kernel, nblocks, SP_THREADS, 0, st, leaf_n, nleaves, block_sums);
+        KC_LAUNCH_CHECK(ctx, "sp_scan_sums_kernel");
+        KC_LAUNCH(sp_scan_blocks_kernel, 1, SP_THREADS, 0, st, block_sums, nblocks, ctl);
+        KC_LAUNCH_CHECK(ctx, "sp_scan_blocks_kernel");
+        KC_LAUNCH(sp_scan_kernel, nblocks, SP_THREADS, 0, st, leaf_n, nleaves, block_sums, leaf_off);
+        KC_LAUNCH_CHECK(ctx, "sp_scan_kernel");
+    }
     SpCtl h;
     KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
     KC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -700,7 +730,8 @@ size_t count_work_bytes(const kc_ctx* ctx, const kc_radix_plan* plan, uint32_t n
     const uint64_t cap2 = region_records((part_mean + part_mean / 8) / Shape::P2 + 1, 64 / rec2, 4, 16);
     const uint64_t nleaves = (uint64_t)nparts * Shape::P2;
     auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
-    return pad(sizeof(SpCtl)) + pad(nleaves * 4) + 2 * pad(nleaves * 8) + pad((size_t)grid2 * Shape::P2 * cap2 * rec2);
+    return pad(sizeof(SpCtl)) + pad(nleaves * 4) + 2 * pad(nleaves * 8) + pad((size_t)grid2 * Shape::P2 * cap2 * rec2) +
+           pad(((nleaves + SP_THREADS - 1) / SP_THREADS) * 8);
 }
 
 template <typename Shape>

@@ -18,6 +18,11 @@
  *     (a cudaStream_t passed as void*, NULL = legacy default stream) and
  *     return immediately;
  *   - one ctx is not thread-safe; distinct ctxs are.
+ *   - the *_async entry points take the caller's stream but share the ctx's scratch (partition slabs, per-CTA
+ *     partial tables): calls on ONE ctx must be stream-ordered, one in flight at a time — two async calls on
+ *     different streams of one ctx would overwrite each other's slabs.  Scratch grows on demand (free + malloc):
+ *     a CUDA graph captured around a call holds the scratch pointer of that moment, so capture after a warm-up
+ *     call of the largest size the graph will see (bench.py does), or use one ctx per graph.
  *   - there is NO CPU fallback: every counting call runs sm_100a kernels.
  *
  * K-mer semantics (bit-exact with the reference):
@@ -186,8 +191,9 @@ KC_API int kc_count_dense_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes
 #define KC_DENSE_AUTO 0      /* engine picks by k and size                    */
 #define KC_DENSE_DIRECT 1    /* smem-privatised (small k) / global-atomic bins */
 #define KC_DENSE_PARTITION 2 /* two-pass radix partition + smem sub-tables     */
-/* Variants written after round 1's GPU budget was spent (CPU-emulator verified, never picked by
- * KC_DENSE_AUTO until a B200 has measured them):                                              */
+/* KC_DENSE_AUTO picks by measurement on B200: k <= 7 shared-memory bins, k = 8
+ * KC_DENSE_SMEM16C, k = 12 KC_DENSE_PARTITION_WIDE2 from 2^26 windows, k = 9..11 KC_DENSE_PARTITION from 2^26
+ * windows, global REDs otherwise.  The explicit values below exist so that the choices can be compared:        */
 #define KC_DENSE_SMEM16C 3   /* k = 8: non-returning shared adds + per-CTA checksum + repair   */
 #define KC_DENSE_PARTITION_DEFER 4 /* partition path, full-bin records retried before REDs     */
 #define KC_DENSE_PARTITION_PAIR 5  /* k = 12: pass 2 counts two 13-mers + one 12-mer per record
@@ -199,9 +205,9 @@ KC_API int kc_count_dense_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes
                                       2 shared increments instead of 5                           */
 #define KC_DENSE_PARTITION_DEFER_PAIR 8  /* k = 12: the scatter of 4 with the count of 5 */
 #define KC_DENSE_PARTITION_DEFER_TRIO 9  /* k = 12: the scatter of 4 with the count of 6 */
-#define KC_DENSE_PARTITION_WIDE2 10  /* k = 12: seven windows per record, second-generation scatter: 16 records per
-                                        lane at static offsets, one shared atomic per record, warp-cooperative
-                                        64-byte bin flush                                         */
+#define KC_DENSE_PARTITION_WIDE2 10  /* k = 12: seven windows per record, second-generation scatter: super-steps of
+                                        7 x 512 bytes = 16 records per lane, bin generation = write cursor, flush by
+                                        the lane that fills the bin; the KC_DENSE_AUTO choice       */
 KC_API int kc_count_dense_range_async(kc_ctx* ctx, const char* d_data, uint64_t nbytes,
                                       uint64_t win_begin, uint64_t win_end, int k,
                                       uint32_t* d_table, int algo, void* stream);
