@@ -281,22 +281,6 @@ __device__ __forceinline__ uint4 smem_ld128(uint32_t saddr) {
 __device__ __forceinline__ void global_red_add(uint32_t* p, uint32_t v) {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// 256-bit global store (sm_100: STG.E.256), 32-byte aligned
-__device__ __forceinline__ void kc_stg256(void* p, uint4 a, uint4 b) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
-                 "r"(b.y), "r"(b.z), "r"(b.w)
-                 : "memory");
-}
-// Bulk copy shared -> global by the TMA unit (UBLKCP.G.S), issued by ONE thread; returns when the
-// unit has READ the shared bytes (they may be overwritten), not when they are visible in global
-// memory (kernel end / later launches order that).  16-byte aligned, size a multiple of 16.
-// The proxy fence makes the generic-proxy writes this thread has observed visible to the async proxy.
-__device__ __forceinline__ void kc_bulk_s2g(void* gdst, uint32_t saddr, uint32_t nbytes) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(nbytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
 // x >> 31 of a value known to be < 2^31, i.e. a zero the compiler cannot see through:
 // OR-ing it into a register copy pins the copy behind the producer of x.
 __device__ __forceinline__ uint32_t kc_opaque_zero(uint32_t x) {
@@ -349,18 +333,6 @@ static inline uint4 smem_ld128(uint32_t saddr) {
 static inline void global_red_add(uint32_t* p, uint32_t v) {
     emu::maybe_preempt();
     *p += v;
-}
-static inline void kc_stg256(void* p, uint4 a, uint4 b) {
-    emu::maybe_preempt();
-    if ((uintptr_t)p & 31) emu::fail("kc_stg256: pointer not 32-byte aligned");
-    ((uint4*)p)[0] = a;
-    ((uint4*)p)[1] = b;
-}
-static inline void kc_bulk_s2g(void* gdst, uint32_t saddr, uint32_t nbytes) {
-    emu::maybe_preempt();
-    if (((uintptr_t)gdst & 15) || (saddr & 15) || (nbytes & 15)) emu::fail("kc_bulk_s2g: 16-byte alignment");
-    memcpy(gdst, emu::smem_ptr(saddr, 16) , nbytes);
-    emu::smem_ptr(saddr + nbytes - 16, 16);  // bounds of the last piece
 }
 static inline uint32_t kc_opaque_zero(uint32_t x) { return x >> 31; }
 #endif

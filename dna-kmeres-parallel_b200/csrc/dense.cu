@@ -463,34 +463,17 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
     auto flush_bin = [&](uint32_t b) {
         constexpr int Q = C::CAP / 4;  // 128-bit pieces
         const uint32_t src = s_buf + b * (C::CAP * 4);
-        if (ABLATE == 4) {
-            // TMA variant (not the default until measured): the bin leaves through ONE bulk copy
-            // instead of Q shared loads + Q global stores of this lane (the per-lane flush is half
-            // of the kernel's LSU wavefronts, profiles/r01_ncu_instruction_mix.txt).  The bin is
-            // reopened only when the unit has read it.
-            const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
-            if (pos + C::CAP <= (b + 1) * region_cap) {
-                kc_bulk_s2g(my_slabs + pos, src, C::CAP * 4);
-                smem_st(s_state + b * 4, 0u);
-                return;
-            }
-            // region full: fall through to the register path below (its cursor bump is harmless:
-            // the region stays full)
-        }
+        // (Two flush variants were measured on B200 and removed: one TMA bulk copy per bin, 2.77 ms against 2.63 —
+        // the bin stays closed until the unit has read it; 256-bit stores, no gain.  BENCH_r01 config.probe.)
         uint4 v[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) v[q] = smem_ld128(src + 16 * q);
         smem_st(s_state + b * 4, 0u);  // every slot has been read: the bin is free again
         const uint32_t pos = smem_atom_add(s_cur + b * 4, (uint32_t)C::CAP);
         if (pos + C::CAP <= (b + 1) * region_cap) {
-            if (ABLATE == 5 && Q % 2 == 0) {  // 256-bit stores (STG.E.256): half the store instructions
+            uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
 #pragma unroll
-                for (int q = 0; q < Q; q += 2) kc_stg256(my_slabs + pos + 4 * q, v[q], v[q + 1]);
-            } else {
-                uint4* dst = reinterpret_cast<uint4*>(my_slabs + pos);  // pos, region_cap: multiples of 4 words
-#pragma unroll
-                for (int q = 0; q < Q; q++) dst[q] = v[q];
-            }
+            for (int q = 0; q < Q; q++) dst[q] = v[q];
         } else {  // region full (skewed input): rare, slow, exact (static indices: v stays in registers)
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -546,8 +529,6 @@ part_scatter_kernel(const uint4* __restrict__ base, uint64_t ngroups, uint32_t* 
                             const uint32_t rec = __funnelshift_r(p0, p1, sh);
                             if (okr != C::AMASK) {
                                 part_fallback<C>(rec, okr, table);  // rare: next to an N run
-                            } else if (ABLATE == 2) {
-                                if (rec == 0x12345678u && j0 == 77) table[rec] = okr;  // measurement only
                             } else if (ABLATE == 3) {
                                 // DEFER variant (not the default until measured): a record that meets a
                                 // full bin waits in a register for this lane's next record slot, where it
@@ -1136,8 +1117,8 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
     const size_t smem1 = (size_t)(2 * C::P + C::P * C::CAP) * sizeof(uint32_t);
     const size_t smem2 = (size_t)C::NBINS * sizeof(uint32_t);
     const uint4* base = g.abase + (G0 << 5);
-    static const int ablate_env = getenv("KC_PART_ABLATE") ? atoi(getenv("KC_PART_ABLATE")) : 0;  // measurement aid
-    const int ablate = defer ? 3 : ablate_env;
+    static const int ablate_env = getenv("KC_PART_ABLATE") ? atoi(getenv("KC_PART_ABLATE")) : 0;  // 3 = deferred retry (tests)
+    const int ablate = (defer || ablate_env == 3) ? 3 : 0;
     if (ctx->timing) KC_CUDA(ctx, cudaEventRecord(ctx->tev[0], st));
 #define KC_LAUNCH_SCATTER(ABL)                                                                              \
     do {                                                                                                    \
@@ -1145,16 +1126,8 @@ static int dense_partition(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uin
         KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));  \
         KC_LAUNCH(kern, grid1, S::THREADS, smem1, st, base, ngroups, d_table, slabs, counts, (uint32_t)cap);       \
     } while (0)
-    if (ablate == 1)
-        KC_LAUNCH_SCATTER(1);
-    else if (ablate == 2)
-        KC_LAUNCH_SCATTER(2);
-    else if (ablate == 3)
+    if (ablate == 3)
         KC_LAUNCH_SCATTER(3);
-    else if (ablate == 4)
-        KC_LAUNCH_SCATTER(4);
-    else if (ablate == 5)
-        KC_LAUNCH_SCATTER(5);
     else
         KC_LAUNCH_SCATTER(0);
 #undef KC_LAUNCH_SCATTER

@@ -75,7 +75,6 @@ struct Stager {
     uint64_t pstride;                // records between the regions of consecutive partitions
     uint32_t cap;                    // records per (CTA, partition) region; multiple of CAP
     uint32_t* failed;
-    bool flush256 = false;
 
     __device__ __forceinline__ void init(uint32_t* smem_words, RecT* region_, uint64_t pstride_, uint32_t cap_,
                                          uint32_t* failed_) {
@@ -103,13 +102,8 @@ struct Stager {
         const uint32_t pos = smem_atom_add(s_cur + p * 4, (uint32_t)CAP);
         if (pos + CAP <= cap) {
             uint4* dst = reinterpret_cast<uint4*>(region + (uint64_t)p * pstride + pos);  // 64-byte aligned
-            if (flush256) {  // measurement aid (KC_RADIX_FLUSH=1): two 256-bit stores instead of four 128-bit ones
-                kc_stg256(dst, v[0], v[1]);
-                kc_stg256(dst + 2, v[2], v[3]);
-            } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++) dst[q] = v[q];
-            }
+            for (int q = 0; q < 4; q++) dst[q] = v[q];  // (two 256-bit stores measured slower: profiles/r02_microbench3.txt)
         } else {
             atomicOr(failed, (uint32_t)SP_FAIL_REGION);  // region full (skewed input): the caller recounts with the hash path
         }
@@ -192,11 +186,10 @@ struct SpCtl {  // one 64-byte control block in device memory
 template <typename Shape, typename R1T, int HALO>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ counts1, uint32_t cap1, SpCtl* ctl,
-                  int flush256, int rbits, uint32_t round) {
+                  int rbits, uint32_t round) {
     KC_DYN_SMEM(uint32_t, smem);
     using St = Stager<R1T, Shape::P1>;
     St st;
-    st.flush256 = flush256 != 0;
     // slabs are partition-major, slabs1[p][cta][cap1]: the regions of a RANGE of partitions are one
     // contiguous block, which is what the multi-GPU path sends to the rank that owns the range
     st.init(smem, slabs1 + (uint64_t)blockIdx.x * cap1, (uint64_t)gridDim.x * cap1, cap1, &ctl->failed);
@@ -273,7 +266,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
                uint32_t grid1, uint32_t nsrc, uint32_t nparts, uint32_t part_first, R2T* __restrict__ scratch2,
                uint32_t cap2, uint64_t* __restrict__ tmp_keys,
                uint32_t* __restrict__ tmp_counts, uint64_t out_cap, unsigned long long* __restrict__ leaf_base,
-               uint32_t* __restrict__ leaf_n, SpCtl* ctl, int flush256) {
+               uint32_t* __restrict__ leaf_n, SpCtl* ctl) {
     KC_DYN_SMEM(uint32_t, smem);
     __shared__ uint32_t s_part, s_np;
     __shared__ unsigned long long s_base;
@@ -300,8 +293,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
         __syncthreads();  // previous partition fully done (s_part, staging area, s_sorted reusable)
         if (tid == 0) s_part = atomicAdd(&ctl->work, 1u);
         St st;
-        st.flush256 = flush256 != 0;
-        st.init(smem, my_scratch, (uint64_t)cap2, cap2, &ctl->failed);
+            st.init(smem, my_scratch, (uint64_t)cap2, cap2, &ctl->failed);
         // records of this partition (sum over the pass-1 CTAs' regions)
         __syncthreads();
         // Local partition q of `nparts`; its records lie in nsrc * grid1 regions: source rank s sent
@@ -583,11 +575,6 @@ struct DevMem {  // pool memory (kc_pool_alloc)
     }
 };
 
-int flush256_env() {
-    static const int v = getenv("KC_RADIX_FLUSH") ? atoi(getenv("KC_RADIX_FLUSH")) : 0;
-    return v;
-}
-
 // Records per private region for `mean` expected records: mean + 1/slack_div + sigmas * sqrt(mean)
 // + 4 chunks, a whole number of chunks.  Level 1 regions (one per pass-1 CTA and partition)
 // see near-Poisson counts; a LEAF holds whole families of repeated k-mers (coverage x copies
@@ -621,7 +608,7 @@ int run_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix
     auto kern = sp_scatter_kernel<Shape, R1T, HALO>;
     KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     KC_LAUNCH(kern, (int)plan->grid, SP_THREADS, smem1, st, g, (R1T*)d_slabs, d_counts, (uint32_t)plan->region_records, ctl,
-              flush256_env(), (int)plan->round_bits, round);
+              (int)plan->round_bits, round);
     KC_LAUNCH_CHECK(ctx, "sp_scatter_kernel");
     return KC_OK;
 }
@@ -676,7 +663,7 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void
         KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, cb, (uint64_t)round << cb, (const R1T*)d_slabs, d_counts, (uint32_t)plan->region_records,
                   plan->grid, nsrc, nparts, part_first, scratch2, (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p,
-                  out_cap, leaf_base, leaf_n, ctl, flush256_env());
+                  out_cap, leaf_base, leaf_n, ctl);
         KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
     }
     {

@@ -76,14 +76,6 @@ def test_partition_deferred_retry_variant(seed):
     run_case("dense", 9, 200_000, 2, "dirty", 50 + seed, 3, seed=0, sms=2, KC_PART_ABLATE=3)
 
 
-@pytest.mark.parametrize("ablate", [4, 5])
-def test_partition_flush_variants(ablate):
-    """KC_PART_ABLATE=4: the bin leaves through one TMA bulk copy (emulated as a memcpy); =5: 256-bit stores"""
-    run_case("dense", 12, 300_000, 2, "genome", 3, 0, seed=1, sms=1, shift=1, KC_PART_ABLATE=ablate)
-    run_case("dense", 12, 200_000, 2, "skew", 3, 5, seed=2, sms=2, KC_PART_ABLATE=ablate)
-    run_case("dense", 10, 200_000, 2, "dirty", 3, 5, KC_PART_ABLATE=ablate)
-
-
 def test_partition_paired_count_variant():
     """KC_DENSE_PARTITION_PAIR (algo 5, k = 12): pass 2 counts the 13-mers at offsets 0 and 2 and the
     12-mer at offset 4 of every record (3 increments instead of 5) and folds them into 12-mer bins at
