@@ -89,6 +89,14 @@ static int reserve(kc_ctx* ctx, void** p, size_t* have, size_t nbytes) {
 }
 int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes) { return reserve(ctx, &ctx->scratch, &ctx->scratch_bytes, nbytes); }
 int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes) { return reserve(ctx, &ctx->scratch2, &ctx->scratch2_bytes, nbytes); }
+void kc_scratch_release(kc_ctx* ctx) {
+    DeviceGuard dg(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
+    ctx->scratch = ctx->scratch2 = nullptr;
+    ctx->scratch_bytes = ctx->scratch2_bytes = 0;
+}
 
 extern "C" {
 

@@ -109,6 +109,7 @@ void kc_pool_free(void* p);
 size_t kc_pool_idle_bytes(int device);  // reserved by the pool but not in use: available to kc_pool_alloc
 int kc_scratch_reserve(kc_ctx* ctx, size_t nbytes);   // ctx->scratch  >= nbytes
 int kc_scratch2_reserve(kc_ctx* ctx, size_t nbytes);  // ctx->scratch2 >= nbytes
+void kc_scratch_release(kc_ctx* ctx);                 // free both (after stream sync); they grow again on demand
 
 #define KC_CUDA(ctx, call)                                                                   \
     do {                                                                                     \

@@ -268,9 +268,11 @@ __device__ __forceinline__ void w2_flush(const W2Stage& c, uint32_t pid, uint32_
         // flushed as zeros on a B200 while the sequentially consistent emulator saw nothing.
         KC_W2_PAUSE();
     }
+    // (One bulk copy of the TMA unit instead of the eight LSU instructions below was measured too: scatter 2.03 ms
+    // against 1.92 — the bin stays closed until the unit has read it.  profiles/r02_scatter7v2_history.txt.)
+    const uint32_t pos = gen * WCAP;
     const uint4 v0 = smem_ld128(binaddr), v1 = smem_ld128(binaddr + 16), v2 = smem_ld128(binaddr + 32), v3 = smem_ld128(binaddr + 48);
     smem_st(c.s_state + pid * 4, (gen + 1u) << 16);  // the next generation is open
-    const uint32_t pos = gen * WCAP;
     if (pos + WCAP <= c.region_cap) {
         uint4* dst = reinterpret_cast<uint4*>(c.my_slabs + (pid * c.region_cap + pos));  // 64-byte aligned; < 2^32 words per CTA (host)
         dst[0] = v0;

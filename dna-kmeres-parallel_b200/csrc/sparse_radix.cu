@@ -722,7 +722,7 @@ size_t count_work_bytes(const kc_ctx* ctx, const kc_radix_plan* plan, uint32_t n
 }
 
 template <typename Shape>
-int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t shape_id, kc_radix_plan* plan) {
+int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t shape_id, uint32_t min_round_bits, kc_radix_plan* plan) {
     if (2 * k - Shape::KB1 - Shape::KB2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix needs 2k > %d (k=%d)", Shape::KB1 + Shape::KB2, k);
     if (world < 1 || Shape::P1 % world) return kc_set_error(ctx, KC_ERR_INVALID, "sparse radix: world %u must divide %d partitions", world, Shape::P1);
     // ROUNDS.  A leaf (one of P1 x P2 code ranges) is sorted in shared memory and must fit it; the slabs of all
@@ -738,24 +738,32 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
     // memory this count can take again: the pool's idle blocks, the ctx's own scratch (the slabs of the last call
     // live there) and what the caller says its allocator has cached (the multi-GPU path keeps the slabs in torch tensors)
     free_b += kc_pool_idle_bytes(ctx->device) + ctx->scratch_bytes + ctx->scratch2_bytes + (size_t)ctx->caller_reusable_bytes;
-    int rbits = 0;
+    int rbits = (int)min_round_bits;
+    if (2 * k - rbits - Shape::KB1 - Shape::KB2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: %u round bits leave no code bits (k=%d)", min_round_bits, k);
     for (;; rbits++) {
         const int r1 = 2 * k - rbits - Shape::KB1, r2 = r1 - Shape::KB2;
         if (r2 < 1) {
             rbits = rbits ? rbits - 1 : 0;
             break;
         }
-        if (rb_env >= 0) {
+        if (rb_env >= 0 && min_round_bits == 0) {
             if (rbits >= rb_env) break;
             continue;
         }
         const uint64_t leaf_cap = (uint64_t)Shape::LEAF_CAP / (r2 <= 32 ? 1 : 2);  // records of 4 or 8 bytes
         const uint64_t leaf_mean = ((uint64_t)world * max_windows >> rbits) / ((uint64_t)Shape::P1 * Shape::P2);
         const uint64_t slab = (max_windows >> rbits) * (r1 <= 32 ? 4 : 8);
-        // mean <= 65 % of the capacity: a leaf holds ~coverage copies of every k-mer in it (compound Poisson); config 4
-        // at 30 x has mean 12.4 K, sigma 0.6 K against 20 480, and ran in one round without an overflow
-        const bool leaf_ok = leaf_mean * 20 <= leaf_cap * 13;
-        const bool mem_ok = free_b == 0 || (slab + slab / 4) * (world > 1 ? 2 : 1) <= free_b / 2;  // + the received copy
+        // window POSITIONS per leaf <= 72 % of the capacity.  The plan cannot know how many positions hold a valid
+        // window (reads: 130 of 151) nor how the records cluster (a leaf holds ~coverage copies of every k-mer in it:
+        // compound Poisson); config 4 at 30 x has 14.4 K positions, 12.4 K records, sigma 0.6 K per leaf against 20 480 and
+        // runs in one round.  A leaf that overflows anyway costs one retry with one more round bit (kc_sparse_radix,
+        // count_sparse_radix_sharded) before the hash table takes over.
+        const bool leaf_ok = leaf_mean * 25 <= leaf_cap * 18;
+        // slabs with their slack (+ the received copy when sharded) + the run list of a round + the result, the last two
+        // at an assumed one distinct k-mer per six windows (configs 4 / 5: 1 in 7.3 / 5.5).  An input that is less
+        // redundant than that runs out of memory or run-list room in some round and is retried with more rounds.
+        const uint64_t need = (slab + slab / 4) * (world > 1 ? 2 : 1) + ((max_windows >> rbits) / 6 + max_windows / 6) * 12;
+        const bool mem_ok = free_b == 0 || need <= free_b / 20 * 19;
         if ((leaf_ok && mem_ok) || rbits >= 8) break;
     }
     const int r1 = 2 * k - rbits - Shape::KB1;
@@ -816,12 +824,18 @@ bool plan_ok(kc_ctx* ctx, const kc_radix_plan* plan) {
 
 extern "C" {
 
-int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world, kc_radix_plan* plan) {
+int kc_sparse_radix_plan_rounds(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world, uint32_t min_round_bits,
+                                kc_radix_plan* plan) {
     if (!ctx || !plan) return KC_ERR_INVALID;
     if (k < 1 || k > KC_MAX_K) return kc_set_error(ctx, KC_ERR_INVALID, "sparse k must be 1..%d, got %d", KC_MAX_K, k);
+    if (min_round_bits > 8) return kc_set_error(ctx, KC_ERR_INVALID, "at most 8 round bits");
+    DeviceGuard dg(ctx->device);
     const uint32_t sh = shape_from_env();
-    return sh ? make_plan<ShapeSmall>(ctx, max_windows_per_rank, k, world, sh, plan)
-              : make_plan<ShapeShipped>(ctx, max_windows_per_rank, k, world, sh, plan);
+    return sh ? make_plan<ShapeSmall>(ctx, max_windows_per_rank, k, world, sh, min_round_bits, plan)
+              : make_plan<ShapeShipped>(ctx, max_windows_per_rank, k, world, sh, min_round_bits, plan);
+}
+int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world, kc_radix_plan* plan) {
+    return kc_sparse_radix_plan_rounds(ctx, max_windows_per_rank, k, world, 0, plan);
 }
 
 int kc_sparse_radix_scatter_round(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, uint32_t round,
@@ -932,35 +946,51 @@ int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_s
 int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_sparse** out, int* failed) {
     *failed = 0;
     *out = nullptr;
-    kc_radix_plan plan;
-    int rc = kc_sparse_radix_plan(ctx, nbytes - k + 1, k, 1, &plan);
-    if (rc) return rc;
     auto pad = [](size_t n) { return (n + 255) & ~(size_t)255; };
-    rc = kc_scratch_reserve(ctx, pad((size_t)plan.slab_bytes) + pad((size_t)plan.counts_bytes));
-    if (rc) return rc;
-    void* slabs = ctx->scratch;
-    uint32_t* counts = (uint32_t*)((char*)ctx->scratch + pad((size_t)plan.slab_bytes));
-    kc_trace(ctx, "radix: plan + scratch", true);
-    const uint32_t rounds = 1u << plan.round_bits;
-    std::vector<kc_sparse*> parts(rounds, nullptr);
-    for (uint32_t r = 0; r < rounds && rc == KC_OK; r++) {
-        rc = kc_sparse_radix_scatter_round(ctx, d_data, nbytes, &plan, r, slabs, counts);
-        kc_trace(ctx, "radix: scatter");
-        if (rc == KC_OK) rc = kc_sparse_radix_count_round(ctx, &plan, r, slabs, counts, 1, 0, plan.partitions, &parts[r]);
-        kc_trace(ctx, "radix: count (incl. frees)", true);
-    }
-    if (rc == KC_OK) {
-        if (rounds == 1) {
-            *out = parts[0];
-            parts[0] = nullptr;
-        } else {
-            rc = sparse_concat(ctx, parts.data(), rounds, out, true);
+    uint32_t min_bits = 0;
+    int retries = 0;
+    for (;;) {
+        kc_radix_plan plan;
+        int rc = kc_sparse_radix_plan_rounds(ctx, nbytes - k + 1, k, 1, min_bits, &plan);
+        if (rc == KC_ERR_UNSUPPORTED && min_bits) {  // no code bits left for another round
+            *failed = 1;
+            return KC_OK;
         }
+        if (rc) return rc;
+        rc = kc_scratch_reserve(ctx, pad((size_t)plan.slab_bytes) + pad((size_t)plan.counts_bytes));
+        if (rc) return rc;
+        void* slabs = ctx->scratch;
+        uint32_t* counts = (uint32_t*)((char*)ctx->scratch + pad((size_t)plan.slab_bytes));
+        kc_trace(ctx, "radix: plan + scratch", true);
+        const uint32_t rounds = 1u << plan.round_bits;
+        std::vector<kc_sparse*> parts(rounds, nullptr);
+        for (uint32_t r = 0; r < rounds && rc == KC_OK; r++) {
+            rc = kc_sparse_radix_scatter_round(ctx, d_data, nbytes, &plan, r, slabs, counts);
+            kc_trace(ctx, "radix: scatter");
+            if (rc == KC_OK) rc = kc_sparse_radix_count_round(ctx, &plan, r, slabs, counts, 1, 0, plan.partitions, &parts[r]);
+            kc_trace(ctx, "radix: count (incl. frees)", true);
+        }
+        if (rc == KC_OK) {
+            if (rounds == 1) {
+                *out = parts[0];
+                parts[0] = nullptr;
+            } else {
+                rc = sparse_concat(ctx, parts.data(), rounds, out, true);
+            }
+        }
+        for (kc_sparse* p : parts) kc_sparse_free(p);
+        if (rc != KC_ERR_TABLE_FULL && rc != KC_ERR_NOMEM) return rc;
+        // An overflow (the error text says which).  Denser-than-planned leaves or regions get ONE more round bit at a time
+        // while the plan has room; inputs that are skewed rather than dense (poly-A: one leaf takes everything) are
+        // hopeless for any number of rounds and go to the caller's fallback after two retries.
+        if (retries >= 2 || plan.round_bits >= 8) {
+            if (rc == KC_ERR_NOMEM) return rc;
+            *failed = 1;
+            return KC_OK;
+        }
+        retries++;
+        KC_STAT(11);
+        min_bits = plan.round_bits + 1;
+        kc_scratch_release(ctx);  // the next plan's slabs are smaller: give the memory back before they are allocated
     }
-    for (kc_sparse* p : parts) kc_sparse_free(p);
-    if (rc == KC_ERR_TABLE_FULL) {  // an overflow: the error text says which; the caller falls back
-        *failed = 1;
-        return KC_OK;
-    }
-    return rc;
 }

@@ -119,6 +119,7 @@ def lib():
         "kc_sparse_bucket_by_owner": (i32, [vp, vp, vp, u64, u32, vp, vp, vp]),
         "kc_sparse_merge": (i32, [vp, vp, vp, u64, C.POINTER(vp)]),
         "kc_ctx_set_reusable_bytes": (None, [vp, u64]),
+        "kc_sparse_radix_plan_rounds": (i32, [vp, u64, i32, u32, u32, vp]),
         "kc_sparse_radix_scatter_round": (i32, [vp, vp, u64, vp, u32, vp, vp]),
         "kc_sparse_radix_count_round": (i32, [vp, vp, u32, vp, vp, u32, u32, u32, C.POINTER(vp)]),
         "kc_sparse_concat": (i32, [vp, vp, u32, C.POINTER(vp)]),
@@ -490,14 +491,14 @@ class Context:
         return table
 
     # ---- stages of KC_SPARSE_RADIX (the multi-GPU path runs an all-to-all between them) ----
-    def radix_plan(self, max_windows, k, world):
+    def radix_plan(self, max_windows, k, world, min_round_bits=0):
         plan = RadixPlan()
         try:  # what torch's caching allocator holds free counts as available for the slab tensors
             torch = self._torch()
             lib().kc_ctx_set_reusable_bytes(self._h, max(0, torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)))
         except Exception:
             pass
-        self._check(lib().kc_sparse_radix_plan(self._h, max_windows, k, world, C.addressof(plan)))
+        self._check(lib().kc_sparse_radix_plan_rounds(self._h, max_windows, k, world, min_round_bits, C.addressof(plan)))
         return plan
 
     def radix_scatter(self, d_data, nbytes, plan, rnd=0, out=None):

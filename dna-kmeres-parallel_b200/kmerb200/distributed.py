@@ -139,33 +139,49 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
     dev = reads.device if hasattr(reads, "device") else "cpu"
     t = torch.tensor([max(nbytes - k + 1, 0)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    plan = stage(lambda: engine.radix_plan(int(t.item()), k, world), dev)
-    if plan is None:
-        return None
     # Large inputs run in 2^round_bits rounds (round r = the windows whose top code bits are r; the plan sizes them so
     # that a leaf fits shared memory and the slabs fit the device): every round has its own scatter, all-to-all and
-    # count and reuses the buffers; rank r's pieces are ascending code ranges, joined at the end.
-    rounds = 1 << getattr(plan, "round_bits", 0)
-    parts, bufs, recv = [], None, None
-    for rnd in range(rounds):
-        sc = stage(lambda: engine.radix_scatter(reads, nbytes, plan, rnd, bufs), dev)
-        if sc is None:
-            for p in parts:
-                p.close()
+    # count and reuses the buffers; rank r's pieces are ascending code ranges, joined at the end.  An overflow on any
+    # rank (leaves denser than planned) is retried twice with one more round bit before the caller's fallback.
+    min_bits, bufs, recv = 0, None, None
+    for attempt in range(3):
+        try:
+            plan = stage(lambda: engine.radix_plan(int(t.item()), k, world, min_bits), dev)
+        except Exception:
+            if attempt == 0:
+                raise
+            return None  # no code bits left for another round
+        if plan is None:
             return None
-        bufs = sc
-        if recv is None:
-            recv = stage(lambda: (torch.empty_like(bufs[0]), torch.empty_like(bufs[1])), dev)
-        dist.all_to_all_single(recv[0], bufs[0])  # equal splits: block o = partitions [o, o+1) * parts_per_rank
-        dist.all_to_all_single(recv[1], bufs[1])
-        res = stage(lambda: engine.radix_count(plan, recv[0], recv[1], world, rank * plan.parts_per_rank, plan.parts_per_rank, rnd), dev)
-        if res is None:
-            for p in parts:
+        if bufs is not None and (bufs[0].numel() != plan.slab_bytes or bufs[1].numel() * 4 != plan.counts_bytes):
+            bufs = recv = None  # the new plan has other buffer sizes
+        rounds = 1 << getattr(plan, "round_bits", 0)
+        parts, ok = [], True
+        for rnd in range(rounds):
+            sc = stage(lambda: engine.radix_scatter(reads, nbytes, plan, rnd, bufs), dev)
+            if sc is None:
+                ok = False
+                break
+            bufs = sc
+            if recv is None:
+                recv = stage(lambda: (torch.empty_like(bufs[0]), torch.empty_like(bufs[1])), dev)
+            dist.all_to_all_single(recv[0], bufs[0])  # equal splits: block o = partitions [o, o+1) * parts_per_rank
+            dist.all_to_all_single(recv[1], bufs[1])
+            res = stage(lambda: engine.radix_count(plan, recv[0], recv[1], world, rank * plan.parts_per_rank, plan.parts_per_rank, rnd), dev)
+            if res is None:
+                ok = False
+                break
+            parts.append(res)
+        if ok:
+            del bufs, recv
+            return parts[0] if rounds == 1 else stage(lambda: engine.sparse_concat(parts), dev)
+        for p in parts:
+            if hasattr(p, "close"):
                 p.close()
-            return None
-        parts.append(res)
-    del bufs, recv
-    return parts[0] if rounds == 1 else stage(lambda: engine.sparse_concat(parts), dev)
+        min_bits = getattr(plan, "round_bits", 0) + 1
+        if min_bits > 8:
+            break
+    return None
 
 
 def count_sparse_sharded_gpu(ctx, d_reads, nbytes, k, algo=0):

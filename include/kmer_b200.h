@@ -259,6 +259,10 @@ KC_API void kc_ctx_set_reusable_bytes(kc_ctx* ctx, uint64_t nbytes);
 /* same plan on every rank: pass the LARGEST per-rank window count */
 KC_API int kc_sparse_radix_plan(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world,
                                 kc_radix_plan* plan);
+/* the same with at least 2^min_round_bits rounds: what a caller asks for after KC_ERR_TABLE_FULL from a count whose
+ * leaves turned out denser than planned (kc_count_sparse and the sharded host logic retry twice this way)           */
+KC_API int kc_sparse_radix_plan_rounds(kc_ctx* ctx, uint64_t max_windows_per_rank, int k, uint32_t world,
+                                       uint32_t min_round_bits, kc_radix_plan* plan);
 /* d_slabs: plan->slab_bytes, d_counts: plan->counts_bytes, both [partition][cta]...; synchronous;
  * KC_ERR_TABLE_FULL when a region overflowed (skewed input)                                  */
 KC_API int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes,

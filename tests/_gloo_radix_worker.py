@@ -35,9 +35,10 @@ class EmuEngine:
             raise Full(msg)
         self.ctx.check(rc)
 
-    def radix_plan(self, max_windows, k, world):
+    def radix_plan(self, max_windows, k, world, min_round_bits=0):
         plan = H.RadixPlan()
-        self._check(self.ctx.L.kc_sparse_radix_plan(self.ctx.h, max_windows, k, world, C.byref(plan)))
+        self.ctx.L.kc_sparse_radix_plan_rounds.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+        self._check(self.ctx.L.kc_sparse_radix_plan_rounds(self.ctx.h, max_windows, k, world, min_round_bits, C.byref(plan)))
         return plan
 
     def radix_scatter(self, reads, nbytes, plan, rnd=0, out=None):
