@@ -147,6 +147,7 @@ int kc_ctx_create(int device, kc_ctx** out) {
 
 void kc_ctx_destroy(kc_ctx* ctx) {
     if (!ctx) return;
+
     DeviceGuard dg(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);

@@ -91,6 +91,7 @@ int kc_dense_direct_range(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint
                           uint32_t* d_table, cudaStream_t st);
 int kc_dense_partition_wide(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
                             uint32_t* d_table, cudaStream_t st);
+int kc_dense_host_plain(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table /* may be NULL */);
 int kc_dense_partition_wide2(kc_ctx* ctx, const char* d_data, uint64_t nbytes, uint64_t win_begin, uint64_t win_end,
                              uint32_t* d_table, cudaStream_t st);
 

@@ -1325,15 +1325,14 @@ extern "C" int kc_count_dense(kc_ctx* ctx, const char* d_data, uint64_t nbytes, 
     return KC_OK;
 }
 
-// End to end from host memory: chunked H2D into two device buffers on the copy
-// stream, counting on the compute stream, events for the hand-off.  Chunk c is
-// counted for the windows that END inside it (so only bytes already on the
-// device are touched); the device buffer holds the whole input.
-extern "C" int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k,
-                                   uint32_t* h_table) {
+// End to end from host memory: chunked H2D on the copy stream, counting on the compute stream, events for the
+// hand-off.  Chunk c is counted for the windows that END inside it (so only bytes already on the device are touched);
+// the device buffer holds the whole input.  h_table != NULL: the table is copied to the host; the device table stays in
+// ctx->scratch2 (its first 4 * 4^k bytes) either way, which is what the hybrid host path (packed.cu) adds up.
+int kc_dense_host_plain(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table) {
     if (!ctx) return KC_ERR_INVALID;
     if (k < 1 || k > KC_MAX_DENSE_K) return kc_set_error(ctx, KC_ERR_INVALID, "dense k must be 1..%d, got %d", KC_MAX_DENSE_K, k);
-    if (!h_table || (!h_data && nbytes)) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
+    if (!h_data && nbytes) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
     DeviceGuard dg(ctx->device);
     const size_t table_bytes = sizeof(uint32_t) << (2 * k);
     int rc = kc_scratch2_reserve(ctx, table_bytes + nbytes + 64);
@@ -1371,7 +1370,12 @@ extern "C" int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nby
     }
     cudaEventDestroy(ev);
     ctx->last_h2d_bytes = nbytes;
-    KC_CUDA(ctx, cudaMemcpyAsync(h_table, d_table, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_table) KC_CUDA(ctx, cudaMemcpyAsync(h_table, d_table, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     KC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KC_OK;
+}
+
+extern "C" int kc_count_dense_host(kc_ctx* ctx, const char* h_data, uint64_t nbytes, int k, uint32_t* h_table) {
+    if (ctx && !h_table) return kc_set_error(ctx, KC_ERR_INVALID, "null pointer");
+    return kc_dense_host_plain(ctx, h_data, nbytes, k, h_table);
 }

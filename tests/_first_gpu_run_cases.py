@@ -130,3 +130,4 @@ print("ROUNDS_OK")
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=200,
                            env=dict(os.environ, KC_SPARSE_RADIX_RBITS=rbits))
         assert r.returncode == 0 and "ROUNDS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
