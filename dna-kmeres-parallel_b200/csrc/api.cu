@@ -171,6 +171,15 @@ const char* kc_last_error(const kc_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 int kc_ctx_device(const kc_ctx* ctx) { return ctx ? ctx->device : -1; }
 int kc_ctx_sm_count(const kc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t kc_ctx_launch_count(const kc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void kc_ctx_release_memory(kc_ctx* ctx) {
+    if (!ctx) return;
+    kc_scratch_release(ctx);
+    DeviceGuard dg(ctx->device);
+    cudaMemPool_t pool;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess ||
+        cudaMemPoolTrimTo(pool, 0) != cudaSuccess)
+        cudaGetLastError();
+}
 void kc_ctx_set_reusable_bytes(kc_ctx* ctx, uint64_t nbytes) {
     if (ctx) ctx->caller_reusable_bytes = nbytes;
 }

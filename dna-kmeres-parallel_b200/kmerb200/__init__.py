@@ -119,6 +119,7 @@ def lib():
         "kc_sparse_bucket_by_owner": (i32, [vp, vp, vp, u64, u32, vp, vp, vp]),
         "kc_sparse_merge": (i32, [vp, vp, vp, u64, C.POINTER(vp)]),
         "kc_ctx_set_reusable_bytes": (None, [vp, u64]),
+        "kc_ctx_release_memory": (None, [vp]),
         "kc_sparse_radix_plan_rounds": (i32, [vp, u64, i32, u32, u32, vp]),
         "kc_sparse_radix_scatter_round": (i32, [vp, vp, u64, vp, u32, vp, vp]),
         "kc_sparse_radix_count_round": (i32, [vp, vp, u32, vp, vp, u32, u32, u32, C.POINTER(vp)]),
@@ -491,6 +492,10 @@ class Context:
         return table
 
     # ---- stages of KC_SPARSE_RADIX (the multi-GPU path runs an all-to-all between them) ----
+    def release_memory(self):
+        """give back the ctx's scratch areas and the idle blocks of the device memory pool"""
+        lib().kc_ctx_release_memory(self._h)
+
     def radix_plan(self, max_windows, k, world, min_round_bits=0):
         plan = RadixPlan()
         try:  # what torch's caching allocator holds free counts as available for the slab tensors

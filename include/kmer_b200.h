@@ -253,6 +253,9 @@ typedef struct kc_radix_plan {
     uint64_t slab_bytes;      /* partitions * grid * region_records * rec_bytes                  */
     uint64_t counts_bytes;    /* partitions * grid * 4                                           */
 } kc_radix_plan;
+/* Give back what the ctx keeps between calls: its scratch areas (partition slabs, staging buffers) and the idle blocks
+ * of the device's memory pool.  They grow again on demand; results (kc_sparse) and seqsets are not touched.          */
+KC_API void kc_ctx_release_memory(kc_ctx* ctx);
 /* Device memory the caller's own allocator has cached and will reuse for the buffers it passes in (a torch caller:
  * memory_reserved - memory_allocated): kc_sparse_radix_plan counts it as available when it sizes the rounds. */
 KC_API void kc_ctx_set_reusable_bytes(kc_ctx* ctx, uint64_t nbytes);

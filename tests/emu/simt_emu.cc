@@ -178,6 +178,12 @@ uint32_t warp_exchange(uint32_t mask, uint32_t v, int kind, int arg) {
         }
         case EMU_BALLOT:
             return W.ballot[p] & mask;
+        case 7: {  // EMU_MATCH_ANY
+            uint32_t m = 0;
+            for (int l = 0; l < 32; l++)
+                if ((mask & (1u << l)) && W.vals[p][l] == v) m |= 1u << l;
+            return m;
+        }
         case EMU_REDUCE_ADD: {
             uint32_t sum = 0;
             for (int l = 0; l < 32; l++)

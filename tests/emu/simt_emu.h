@@ -153,7 +153,7 @@ static inline uint32_t __brev(uint32_t x) {
     return r;
 }
 
-enum { EMU_SHFL_IDX = 0, EMU_SHFL_DOWN = 1, EMU_SHFL_UP = 2, EMU_SHFL_XOR = 3, EMU_BALLOT = 4, EMU_SYNCWARP = 5, EMU_REDUCE_ADD = 6 };
+enum { EMU_SHFL_IDX = 0, EMU_SHFL_DOWN = 1, EMU_SHFL_UP = 2, EMU_SHFL_XOR = 3, EMU_BALLOT = 4, EMU_SYNCWARP = 5, EMU_REDUCE_ADD = 6, EMU_MATCH_ANY = 7 };
 template <class T>
 static inline T emu_shfl(uint32_t mask, T v, int kind, int arg) {
     static_assert(sizeof(T) == 4 || sizeof(T) == 8, "shuffle of 32/64-bit values");
@@ -180,6 +180,15 @@ template <class T>
 static inline T __shfl_up_sync(uint32_t mask, T v, unsigned d) { return emu_shfl(mask, v, EMU_SHFL_UP, (int)d); }
 template <class T>
 static inline T __shfl_xor_sync(uint32_t mask, T v, int m) { return emu_shfl(mask, v, EMU_SHFL_XOR, m); }
+template <class T>
+static inline uint32_t __match_any_sync(uint32_t mask, T v) {  // lanes of `mask` holding the same value as this one
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "match of 32/64-bit values");
+    uint64_t u = 0;
+    memcpy(&u, &v, sizeof(T));
+    uint32_t m = emu::warp_exchange(mask, (uint32_t)u, EMU_MATCH_ANY, 0);
+    if (sizeof(T) == 8) m &= emu::warp_exchange(mask, (uint32_t)(u >> 32), EMU_MATCH_ANY, 0);
+    return m;
+}
 static inline uint32_t __ballot_sync(uint32_t mask, int pred) { return emu::warp_exchange(mask, pred ? 1u : 0u, EMU_BALLOT, 0); }
 static inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(uint32_t mask, int pred) { return (__ballot_sync(mask, pred) & mask) == mask; }

@@ -431,3 +431,54 @@ def test_sparse_unsorted_flag(ctx, kmerlib, oracle):
     keys, counts = ctx.count_sparse(to_dev(s), s.size, 21, kmerlib.SPARSE_HASH | kmerlib.SPARSE_UNSORTED).to_host()
     order = np.argsort(keys)
     assert (keys[order] == wk).all() and (counts[order] == wc).all()
+
+
+def test_config2_full_size(ctx, kmerlib, oracle):
+    """BASELINE configs[1] at its real size (100 Mbp, k = 8, the bench's seed): the library default (16-bit
+    shared-memory bins with the per-CTA checksum) against the CPU oracle, bin by bin"""
+    n, seed = 100_000_000, 0xB2000002
+    data = ctx.gen_genome(seed, n, 0, 0, 8, 0, n)
+    want, _ = oracle.count_dense(oracle.gen_genome(seed, n, 0, 0, 8, 0, n), 8, threads=8)
+    assert (dense_gpu(ctx, kmerlib, data, n, 8) == want).all()
+    assert ctx.dense_fingerprint(_table_of(ctx, kmerlib, data, n, 8), 8) == ctx.window_fingerprint(data, n, 8)
+
+
+def _table_of(ctx, kmerlib, d, n, k):
+    t = _torch().zeros(kmerlib.num_kmers(k), dtype=_torch().int32, device="cuda:0")
+    ctx.count_dense_range(d, n, 0, n, k, t)
+    _torch().cuda.synchronize()
+    return t
+
+
+def test_config4_full_scale_self_check(ctx, kmerlib):
+    """BASELINE configs[3] at FULL scale on one GPU (100 M reads x 150 bp, k = 21, the bench's generator): no CPU oracle
+    goes there, so the count is checked by the multiset identity of csrc/check.cu — the window fingerprint of the input
+    (one streaming scan, pinned to the oracle in test_fingerprint_self_checks) must equal the fingerprint of the result,
+    the sum of counts the number of valid windows, the keys must ascend strictly — and by the number of distinct k-mers,
+    which every algorithm and every GPU count (1, 2, 4, 8) of round 2 agreed on."""
+    nreads, k = 100_000_000, 21
+    reads = ctx.gen_reads(0xB2000004, 500_000_000, 150, 200, 0, nreads)
+    nb = nreads * 151
+    fin = ctx.window_fingerprint(reads, nb, k)
+    assert fin[1] == nreads * (150 - k + 1)
+    sp = ctx.count_sparse(reads, nb, k, kmerlib.SPARSE_AUTO)
+    assert ctx.sparse_fingerprint(sp) == fin + (0,)
+    assert len(sp) == 1_774_844_036
+    sp.close()
+
+
+def test_config5_quarter_scale_self_check(ctx, kmerlib):
+    """BASELINE configs[4] at 1/4 scale (50 M reads of 200 M, 1 Gbp genome, k = 31: 64-bit records on both partition
+    levels), radix and hash table: same self-check, same distinct count"""
+    nreads, k = 50_000_000, 31
+    ctx.release_memory()  # the slabs of the config-4 test above (60 GB) would leave the hash table too little room
+    _torch().cuda.empty_cache()
+    reads = ctx.gen_reads(0xB2000005, 1_000_000_000, 150, 200, 0, nreads)
+    nb = nreads * 151
+    fin = ctx.window_fingerprint(reads, nb, k)
+    assert fin[1] == nreads * (150 - k + 1)
+    for algo in (kmerlib.SPARSE_AUTO, kmerlib.SPARSE_HASH):
+        sp = ctx.count_sparse(reads, nb, k, algo)
+        assert ctx.sparse_fingerprint(sp) == fin + (0,), algo
+        assert len(sp) == 1_854_369_236
+        sp.close()
