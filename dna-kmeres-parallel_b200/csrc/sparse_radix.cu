@@ -229,32 +229,32 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
     st.finish(smem, counts1, gridDim.x, blockIdx.x);
 }
 
-// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive
-// prefix, *total = sum.  `s_warp` = 33 words of shared memory.  Two barriers.
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix, *total = sum.
+// ONE barrier: every warp scans the 32 warp totals itself (round 2's capture of sp_leaf_kernel had 29 % of its stall
+// samples at the second barrier of the old form, 31 warps waiting for warp 0).  `s_warp` = 2 x 32 words used
+// alternately: `calls` is the caller's running count of scans (the same in every thread), so a warp that is still
+// reading the totals of scan n cannot meet the writes of scan n + 2, whose writers have passed the barrier of n + 1.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total, uint32_t& calls) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* const tot = s_warp + 32 * (calls & 1u);
+    calls++;
     uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
     }
-    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 31) tot[warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t wv = s_warp[lane];
-        uint32_t winc = wv;
+    const uint32_t wv = tot[lane];
+    uint32_t winc = wv;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= d) winc += t;
-        }
-        s_warp[lane] = winc - wv;  // exclusive prefix of the warp totals
-        if (lane == 31) s_warp[32] = winc;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += t;
     }
-    __syncthreads();
-    *total = s_warp[32];
-    return s_warp[warp] + inc - v;
+    *total = __shfl_sync(0xffffffffu, winc, 31);
+    return __shfl_sync(0xffffffffu, winc - wv, warp) + inc - v;
 }
 
 // ---------------------------------------------------------------------------
@@ -270,7 +270,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
     KC_DYN_SMEM(uint32_t, smem);
     __shared__ uint32_t s_part, s_np;
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_warp[64];
     using St = Stager<R2T, Shape::P2>;
     constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
     constexpr int PER_THREAD = LEAF_CAP / SP_THREADS;
@@ -289,6 +289,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
     uint32_t* const s_hist = smem + STAGE_WORDS;                    // 1024 words
     R2T* const s_sorted = reinterpret_cast<R2T*>(smem + STAGE_WORDS + 1024);  // LEAF_CAP records
 
+    uint32_t scans = 0;  // block scans made so far (block_excl_scan alternates its two total arrays)
     for (;;) {
         __syncthreads();  // previous partition fully done (s_part, staging area, s_sorted reusable)
         if (tid == 0) s_part = atomicAdd(&ctl->work, 1u);
@@ -310,7 +311,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
             uint32_t mine = 0;
             for (uint32_t r = tid; r < nregions; r += SP_THREADS) mine += counts1[region_index(r)];
             uint32_t tot;
-            block_excl_scan(mine, s_warp, &tot);
+            block_excl_scan(mine, s_warp, &tot, scans);
             if (tid == 0) s_np = tot;
         }
         __syncthreads();
@@ -385,7 +386,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
             __syncthreads();
             uint32_t dummy;
             const uint32_t cnt = (uint32_t)tid < nb ? s_hist[tid] : 0u;
-            const uint32_t begin = block_excl_scan(cnt, s_warp, &dummy);
+            const uint32_t begin = block_excl_scan(cnt, s_warp, &dummy, scans);
             if ((uint32_t)tid < nb) s_hist[tid] = begin;  // becomes the scatter cursor
             __syncthreads();
 #pragma unroll
@@ -480,7 +481,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
                     runs += ((s_sorted[a] & keymask) != (s_sorted[a - 1] & keymask)) ? 1u : 0u;
             }
             uint32_t leaf_runs;
-            const uint32_t off = block_excl_scan(runs, s_warp, &leaf_runs);
+            const uint32_t off = block_excl_scan(runs, s_warp, &leaf_runs, scans);
             if (tid == 0) {
                 const unsigned long long base = atomicAdd(&ctl->out_cursor, (unsigned long long)leaf_runs);
                 s_base = base;
@@ -529,10 +530,10 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(SP_THREADS, 1)
 sp_scan_sums_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, unsigned long long* __restrict__ block_sums) {
-    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_warp[64];
     const uint64_t i = (uint64_t)blockIdx.x * SP_THREADS + threadIdx.x;
-    uint32_t tot;
-    block_excl_scan(i < nleaves ? leaf_n[i] : 0u, s_warp, &tot);
+    uint32_t tot, scans = 0;
+    block_excl_scan(i < nleaves ? leaf_n[i] : 0u, s_warp, &tot, scans);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
@@ -568,10 +569,10 @@ sp_scan_blocks_kernel(unsigned long long* __restrict__ block_sums, uint32_t nblo
 __global__ void __launch_bounds__(SP_THREADS, 1)
 sp_scan_kernel(const uint32_t* __restrict__ leaf_n, uint64_t nleaves, const unsigned long long* __restrict__ block_sums,
                unsigned long long* __restrict__ leaf_off) {
-    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_warp[64];
     const uint64_t i = (uint64_t)blockIdx.x * SP_THREADS + threadIdx.x;
-    uint32_t tot;
-    const uint32_t ex = block_excl_scan(i < nleaves ? leaf_n[i] : 0u, s_warp, &tot);
+    uint32_t tot, scans = 0;
+    const uint32_t ex = block_excl_scan(i < nleaves ? leaf_n[i] : 0u, s_warp, &tot, scans);
     if (i < nleaves) leaf_off[i] = block_sums[blockIdx.x] + ex;
 }
 
