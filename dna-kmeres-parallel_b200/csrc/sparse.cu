@@ -359,6 +359,7 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
         free_b += kc_pool_idle_bytes(ctx->device);
         uint64_t cap = next_pow2(want + want / 2 + 1024);
         while (cap * 16 > free_b * 6 / 10 && cap > 1024) cap >>= 1;  // keep room for the compacted copy
+        bool released = false;
         for (;;) {
             DevBuf ok, oc;
             uint64_t nd = 0;
@@ -378,6 +379,15 @@ int kc_count_sparse(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, int
                 }
                 rc = sort_reduce_pairs(ctx, ok.as<uint64_t>(), oc.as<uint32_t>(), nd, 2 * k, out);
                 return rc;
+            }
+            if (cap * 2 * 16 > free_b * 8 / 10 && !released) {
+                // the context's scratch (e.g. the radix path's slabs, tens of GB) is of no use here: hand it back and look again
+                released = true;
+                ok.reset();
+                oc.reset();
+                kc_scratch_release(ctx);
+                KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+                free_b += kc_pool_idle_bytes(ctx->device);
             }
             if (cap * 2 * 16 > free_b * 8 / 10)
                 return kc_set_error(ctx, KC_ERR_TABLE_FULL, "hash table with %llu slots overflowed and a larger one does not fit",

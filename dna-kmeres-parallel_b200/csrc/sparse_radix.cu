@@ -416,37 +416,11 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
             const R2T one = collapse ? ((R2T)1 << r2bits) : (R2T)0;
             const R2T cmax = collapse ? (R2T)(~keymask) : (R2T)0;  // count field all ones
             uint32_t nent = cnt;  // entries of this sub-bucket after the pass
-            // Sub-buckets of up to 32 records (nearly all of them) are collapsed by the WARP, one sub-bucket after the
-            // other: lane l takes record l, match.any groups the equal keys, the lowest lane of each group writes
-            // (key, copies) at the key's rank among the group leaders.  A thread collapsing its own sub-bucket record
-            // by record made every warp wait for its longest sub-bucket at every step (full-scale config 4: 60 % of
-            // the kernel's instructions in that loop, 32 % in its backward scan alone: profiles/r02_ncu_sp_*).
-            bool serial = cnt != 0 && collapse;
-            if (collapse && spare >= 6) {
-                const R2T none = ~(R2T)0;  // no valid key: keys have at least 6 clear bits on top
-#pragma unroll 1
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t bb = __shfl_sync(0xffffffffu, begin, j), bc = __shfl_sync(0xffffffffu, cnt, j);
-                    if (bc == 0 || bc > 32) continue;  // warp-uniform; longer ones are left to their owner thread below
-                    const bool have = (uint32_t)lane < bc;
-                    const R2T v = have ? (R2T)(s_sorted[bb + lane] & keymask) : none;
-                    const uint32_t m = __match_any_sync(0xffffffffu, v);
-                    const bool leader = have && (__ffs((int)m) - 1 == lane);
-                    const uint32_t lm = __ballot_sync(0xffffffffu, leader);
-                    uint32_t rank = 0;
-                    for (uint32_t t = lm; t; t &= t - 1u) {
-                        const R2T o = __shfl_sync(0xffffffffu, v, __ffs((int)t) - 1);
-                        rank += (o < v) ? 1u : 0u;
-                    }
-                    __syncwarp();  // every record of the sub-bucket is in a register before its front is overwritten
-                    if (leader) s_sorted[bb + rank] = v | ((R2T)(__popc(m) - 1) << r2bits);
-                    if (lane == j) {
-                        nent = (uint32_t)__popc(lm);
-                        serial = false;
-                    }
-                }
-                __syncwarp();
-            }
+            // (A warp-cooperative collapse — match.any over the up-to-32 records of a sub-bucket, the 32 sub-buckets of a warp
+            // one after the other — was built, verified and measured: leaf kernel 343 -> 395 ms at full-scale config 4.  Its
+            // 32 dependent shuffle / match / ballot chains per warp and leaf cost more than the divergence of the per-thread
+            // loop below, whose backward scan is 32 % of the kernel's instructions.  Removed.)
+            const bool serial = cnt != 0 && collapse;
             if (serial) {
                 uint32_t nd = 0;
                 for (uint32_t a = 0; a < cnt; a++) {
