@@ -169,7 +169,7 @@ template <int KB1_, int KB2_, int LEAF_CAP_>
 struct SpShape {
     static constexpr int KB1 = KB1_, KB2 = KB2_;
     static constexpr int P1 = 1 << KB1_, P2 = 1 << KB2_;
-    static constexpr int LEAF_CAP = LEAF_CAP_;  // records a leaf may hold (32-bit records; half for 64-bit)
+    static constexpr int LEAF_CAP = LEAF_CAP_;  // leaf size unit: a leaf may hold LEAF_CAP / 2 distinct 32-bit records (half for 64-bit)
 };
 
 struct SpCtl {  // one 64-byte control block in device memory
@@ -260,6 +260,24 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 // ---------------------------------------------------------------------------
 // K2: level-1 partition -> leaves -> sorted runs
 // ---------------------------------------------------------------------------
+// compare-and-swap on a leaf table slot (CUDA has the 64-bit overload for unsigned long long only)
+__device__ __forceinline__ uint32_t leaf_cas(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
+__device__ __forceinline__ uint64_t leaf_cas(uint64_t* p, uint64_t cmp, uint64_t val) {
+    return (uint64_t)atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
+}
+__device__ __forceinline__ uint32_t leaf_hash(uint32_t key) { return key * 0x9E3779B1u; }
+__device__ __forceinline__ uint32_t leaf_hash(uint64_t key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32); }
+
+// Shared-memory geometry of the dedupe-first leaf pass (phase B of sp_leaf_kernel): a leaf may hold any number of
+// records its scratch region takes, but at most D_MAX DISTINCT codes; the table has >= 1.5 slots per distinct code.
+template <typename Shape, typename R2T>
+struct LeafTable {
+    static constexpr int D_MAX = Shape::LEAF_CAP * 4 / (int)sizeof(R2T) / 2;
+    static constexpr int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+    static constexpr int SLOTS = pow2ceil(D_MAX * 3 / 2);
+    static constexpr size_t BYTES = 1024 * 4 + (size_t)SLOTS * (sizeof(R2T) + 4) + (size_t)D_MAX * (sizeof(R2T) + 4);
+};
+
 template <typename Shape, typename R1T, typename R2T>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefix /* round << cb */, const R1T* __restrict__ slabs1, const uint32_t* __restrict__ counts1, uint32_t cap1,
@@ -272,9 +290,6 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_warp[64];
     using St = Stager<R2T, Shape::P2>;
-    constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
-    constexpr int PER_THREAD = LEAF_CAP / SP_THREADS;
-    static_assert(LEAF_CAP % SP_THREADS == 0, "leaf records are held in registers, PER_THREAD per thread");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r1bits = cb - Shape::KB1;
     const int r2bits = r1bits - Shape::KB2;  // >= 1 (host checks)
@@ -283,18 +298,23 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
     const uint32_t nb = 1u << dbits;  // sub-buckets of a leaf, one per thread
     const uint64_t r2mask = (1ull << r2bits) - 1ull;
     R2T* const my_scratch = scratch2 + (uint64_t)blockIdx.x * Shape::P2 * cap2;
-    // shared memory: the staging block (its cur[] holds the leaf record counts after
-    // Stager::finish), then hist/cursor[1024], then sorted[LEAF_CAP]
-    constexpr size_t STAGE_WORDS = St::SMEM_BYTES / 4;
-    uint32_t* const s_hist = smem + STAGE_WORDS;                    // 1024 words
-    R2T* const s_sorted = reinterpret_cast<R2T*>(smem + STAGE_WORDS + 1024);  // LEAF_CAP records
+    // shared memory: the staging block (its cur[] holds the leaf record counts after Stager::finish)
+    // phase B lies over the staging BINS (free once Stager::finish has run; state[] and cur[] stay):
+    // hist/cursor[1024] | table keys[SLOTS] | table counts[SLOTS] | sorted keys[D_MAX] | sorted counts[D_MAX]
+    using LT = LeafTable<Shape, R2T>;
+    uint32_t* const s_hist = smem + 3 * Shape::P2;  // 1024 words
+    R2T* const t_keys = reinterpret_cast<R2T*>(s_hist + 1024);
+    uint32_t* const t_cnt = reinterpret_cast<uint32_t*>(t_keys + LT::SLOTS);
+    R2T* const o_keys = reinterpret_cast<R2T*>(t_cnt + LT::SLOTS);
+    uint32_t* const o_cnt = reinterpret_cast<uint32_t*>(o_keys + LT::D_MAX);
+    __shared__ uint32_t s_special, s_leaf_fail, s_ok;
 
     uint32_t scans = 0;  // block scans made so far (block_excl_scan alternates its two total arrays)
     for (;;) {
-        __syncthreads();  // previous partition fully done (s_part, staging area, s_sorted reusable)
+        __syncthreads();  // previous partition fully done (s_part, the staging area and what phase B laid over it)
         if (tid == 0) s_part = atomicAdd(&ctl->work, 1u);
         St st;
-            st.init(smem, my_scratch, (uint64_t)cap2, cap2, &ctl->failed);
+        st.init(smem, my_scratch, (uint64_t)cap2, cap2, &ctl->failed);
         // records of this partition (sum over the pass-1 CTAs' regions)
         __syncthreads();
         // Local partition q of `nparts`; its records lie in nsrc * grid1 regions: source rank s sent
@@ -336,7 +356,8 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
         };
         constexpr uint32_t RPV = 16 / sizeof(R1T);  // records per 128-bit load
         for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
-            if (*(volatile uint32_t*)&ctl->failed) break;  // the result is void already: do not grind on
+            // the result is void already: do not grind on (a short run list is not void: the host wants the full count of runs)
+            if (*(volatile uint32_t*)&ctl->failed & ~(uint32_t)SP_FAIL_RUNLIST) break;
             const uint64_t ri = region_index(reg);
             const uint32_t n = counts1[ri];
             const R1T* src = slabs1 + ri * cap1;  // 64-byte aligned
@@ -361,139 +382,144 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
         st.finish(smem, nullptr, 0, 0);
         __syncthreads();  // cur[p2] = records of leaf p2; scratch writes of this CTA are visible to it
 
-        // ---- phase B: sort + run-length encode every leaf -------------------------------
+        // ---- phase B: count the DISTINCT codes of a leaf first, sort those ---------------------------------
+        // A leaf of deep-coverage reads holds ~coverage copies of every code in it.  Round 2's first form sorted the
+        // RECORDS (counting sort on 10 bits, then a per-thread pass that collapsed each sub-bucket's duplicates): it paid
+        // for every copy and every leaf waited for the thread with the largest sub-bucket — 93 K cycles per 12.4 K-record
+        // leaf at config 4, 0.6 instructions issued per clock, leaf kernel 351 ms; a warp-cooperative collapse
+        // (match.any) was slower still (395 ms).  Here every record is one probe of a shared-memory hash table (read
+        // the slot; equal: count it; empty: claim it with a CAS) — the same work for every thread — and only the distinct
+        // codes (1/7 of the records at 30 x) are counting-sorted on their top bits and finished by a per-thread insertion
+        // sort of 1.7 entries on average.  No run-length pass: the entries are distinct, a leaf's run count is the
+        // table's population and a thread's output offset its cursor.  Measured: 351 -> 151 ms (config 4), 190 -> 133 ms
+        // (config 5, 50 M reads).  A leaf may now hold any number of records, but at most LeafTable::D_MAX distinct codes.
+        const R2T EMPTY = ~(R2T)0;  // a real code only when r2bits fills R2T: counted in s_special instead
+        for (uint32_t i = tid; i < (uint32_t)LT::SLOTS; i += SP_THREADS) {  // the bins of phase A lay here
+            t_keys[i] = EMPTY;
+            t_cnt[i] = 0;
+        }
+        s_hist[tid] = 0;
+        if (tid == 0) s_special = 0, s_leaf_fail = 0;
+        __syncthreads();
         for (uint32_t p2 = 0; p2 < (uint32_t)Shape::P2; p2++) {
             const uint32_t n = smem[2 * Shape::P2 + p2];
             if (n == 0) continue;  // CTA-uniform
-            if (n > (uint32_t)LEAF_CAP) {
-                if (tid == 0) atomicOr(&ctl->failed, (uint32_t)SP_FAIL_LEAF);
-                continue;
-            }
             const R2T* leaf = my_scratch + (uint64_t)p2 * cap2;
-            R2T rec[PER_THREAD] = {};
-            if ((uint32_t)tid < nb) s_hist[tid] = 0;
-#pragma unroll
-            for (int q = 0; q < PER_THREAD; q++) {
-                const uint32_t i = (uint32_t)tid + (uint32_t)q * SP_THREADS;
-                if (i < n) rec[q] = kc_ld_cg(leaf + i);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < PER_THREAD; q++) {
-                const uint32_t i = (uint32_t)tid + (uint32_t)q * SP_THREADS;
-                if (i < n) atomicAdd(&s_hist[(uint32_t)((uint64_t)rec[q] >> lowbits) & (nb - 1u)], 1u);
-            }
-            __syncthreads();
-            uint32_t dummy;
-            const uint32_t cnt = (uint32_t)tid < nb ? s_hist[tid] : 0u;
-            const uint32_t begin = block_excl_scan(cnt, s_warp, &dummy, scans);
-            if ((uint32_t)tid < nb) s_hist[tid] = begin;  // becomes the scatter cursor
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < PER_THREAD; q++) {
-                const uint32_t i = (uint32_t)tid + (uint32_t)q * SP_THREADS;
-                if (i < n) {
-                    const uint32_t pos = atomicAdd(&s_hist[(uint32_t)((uint64_t)rec[q] >> lowbits) & (nb - 1u)], 1u);
-                    s_sorted[pos] = rec[q];
+            // table size for this leaf: two slots per record, at most SLOTS (slots outside stay clean)
+            uint32_t slots = 64;
+            while (slots < 2 * n && slots < (uint32_t)LT::SLOTS) slots <<= 1;
+            const uint32_t smask = slots - 1u;
+            const int hshift = 32 - (31 - __clz(slots));
+            auto sub_of = [&](R2T key) { return (uint32_t)((uint64_t)key >> lowbits) & (nb - 1u); };
+            auto insert = [&](R2T key) {
+                if (key == EMPTY) {
+                    KC_STAT(12);
+                    if (atomicAdd(&s_special, 1u) == 0) atomicAdd(&s_hist[nb - 1u], 1u);
+                    return;
                 }
-            }
-            __syncthreads();
-            // thread t owns sub-bucket t = s_sorted[begin, begin+cnt).
-            // A leaf of deep-coverage reads holds ~coverage copies of every genomic k-mer, and all copies of a k-mer
-            // sit in ONE sub-bucket: plain insertion sort is quadratic in exactly the sub-buckets that are large
-            // (config 4, 30x: the slowest thread of a leaf ran ~1000-3000 shift steps while the average one ran 30;
-            // sp_leaf_kernel took 871 of the path's 973 ms).  So the sub-bucket is not sorted but COLLAPSED: the
-            // spare high bits of a record (r2bits < 8 sizeof(R2T)) hold "copies - 1", and each element is either
-            // merged into its key's entry or inserted into the sorted list of DISTINCT keys, whose length is what
-            // the shift cost now depends on (1-3 per sub-bucket at any coverage).  The list is built in place at the
-            // front of the sub-bucket (entry count <= elements consumed).  A saturated entry simply gets a sibling
-            // entry of the same key behind it; the run-length pass below merges equal neighbours.  Records that fill
-            // all bits of R2T (spare < 4) keep the plain insertion sort.
-            constexpr int RBITS = 8 * (int)sizeof(R2T);
-            const int spare = RBITS - r2bits;
-            const bool collapse = spare >= 4;
-            const R2T keymask = (R2T)r2mask;
-            const R2T one = collapse ? ((R2T)1 << r2bits) : (R2T)0;
-            const R2T cmax = collapse ? (R2T)(~keymask) : (R2T)0;  // count field all ones
-            uint32_t nent = cnt;  // entries of this sub-bucket after the pass
-            // (A warp-cooperative collapse — match.any over the up-to-32 records of a sub-bucket, the 32 sub-buckets of a warp
-            // one after the other — was built, verified and measured: leaf kernel 343 -> 395 ms at full-scale config 4.  Its
-            // 32 dependent shuffle / match / ballot chains per warp and leaf cost more than the divergence of the per-thread
-            // loop below, whose backward scan is 32 % of the kernel's instructions.  Removed.)
-            const bool serial = cnt != 0 && collapse;
-            if (serial) {
-                uint32_t nd = 0;
-                for (uint32_t a = 0; a < cnt; a++) {
-                    const R2T v = s_sorted[begin + a] & keymask;
-                    uint32_t b = nd;
-                    R2T e = 0;
-                    while (b > 0 && ((e = s_sorted[begin + b - 1]) & keymask) > v) b--;
-                    if (b > 0 && (e & keymask) == v && (e & cmax) != cmax) {
-                        s_sorted[begin + b - 1] = e + one;
-                    } else {
-                        for (uint32_t c = nd; c > b; c--) s_sorted[begin + c] = s_sorted[begin + c - 1];
-                        s_sorted[begin + b] = v;
-                        nd++;
+                uint32_t slot = (leaf_hash(key) >> hshift) & smask;
+                for (uint32_t probes = 0;; probes++) {
+                    R2T old = *(volatile R2T*)&t_keys[slot];
+                    if (old == EMPTY) old = leaf_cas(&t_keys[slot], EMPTY, key);
+                    if (old == EMPTY) {
+                        atomicAdd(&s_hist[sub_of(key)], 1u);  // a new distinct code
+                        break;
+                    }
+                    if (old == key) break;
+                    slot = (slot + 1u) & smask;
+                    if (probes >= 64u && (probes > smask || *(volatile uint32_t*)&s_leaf_fail)) {  // table full: the leaf fails
+                        s_leaf_fail = 1;
+                        return;
                     }
                 }
-                nent = nd;
-            } else if (cnt && !collapse) {
+                atomicAdd(&t_cnt[slot], 1u);
+            };
+            for (uint32_t i0 = 0; i0 < n; i0 += 4 * SP_THREADS) {  // four loads in flight per thread
+                R2T r[4];
+                bool have[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t i = i0 + (uint32_t)q * SP_THREADS + (uint32_t)tid;
+                    have[q] = i < n;
+                    r[q] = have[q] ? kc_ld_cg(leaf + i) : (R2T)0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (have[q]) insert(r[q]);
+            }
+            __syncthreads();
+            const uint32_t cnt = (uint32_t)tid < nb ? s_hist[tid] : 0u;
+            uint32_t nd;  // distinct codes of the leaf
+            const uint32_t begin = block_excl_scan(cnt, s_warp, &nd, scans);
+            if ((uint32_t)tid < nb) s_hist[tid] = begin;  // becomes the scatter cursor
+            if (tid == 0) {
+                uint32_t ok = 0;
+                if (nd > (uint32_t)LT::D_MAX || s_leaf_fail) {
+                    atomicOr(&ctl->failed, (uint32_t)SP_FAIL_LEAF);
+                } else {
+                    const unsigned long long base = atomicAdd(&ctl->out_cursor, (unsigned long long)nd);
+                    s_base = base;
+                    if (base + nd <= out_cap) {
+                        leaf_base[(uint64_t)q1 * Shape::P2 + p2] = base;
+                        leaf_n[(uint64_t)q1 * Shape::P2 + p2] = nd;
+                        ok = 1;
+                    } else {
+                        atomicOr(&ctl->failed, (uint32_t)SP_FAIL_RUNLIST);  // temporary list full; leaf_n stays 0
+                    }
+                }
+                s_ok = ok;
+            }
+            __syncthreads();
+            const bool ok = s_ok != 0;
+            // empty the table into the sorted area, sub-bucket by sub-bucket; the table is clean again afterwards
+            for (uint32_t slot = tid; slot < slots; slot += SP_THREADS) {
+                const R2T key = t_keys[slot];
+                if (key != EMPTY) {
+                    const uint32_t c = t_cnt[slot];
+                    t_keys[slot] = EMPTY;
+                    t_cnt[slot] = 0;
+                    if (ok) {
+                        const uint32_t pos = atomicAdd(&s_hist[sub_of(key)], 1u);
+                        o_keys[pos] = key;
+                        o_cnt[pos] = c;
+                    }
+                }
+            }
+            if (tid == 0 && s_special) {
+                if (ok) {
+                    const uint32_t pos = atomicAdd(&s_hist[nb - 1u], 1u);
+                    o_keys[pos] = EMPTY;
+                    o_cnt[pos] = s_special;
+                }
+                s_special = 0;
+            }
+            __syncthreads();
+            if (tid == 0) s_leaf_fail = 0;
+            if ((uint32_t)tid < nb) s_hist[tid] = 0;  // the next leaf's histogram
+            if (ok && cnt > 1) {  // thread t owns sub-bucket t = o_[begin, begin + cnt): distinct codes, a handful
                 for (uint32_t a = begin + 1; a < begin + cnt; a++) {
-                    const R2T v = s_sorted[a];
+                    const R2T v = o_keys[a];
+                    const uint32_t vc = o_cnt[a];
                     uint32_t b = a;
-                    while (b > begin && s_sorted[b - 1] > v) {
-                        s_sorted[b] = s_sorted[b - 1];
+                    while (b > begin && o_keys[b - 1] > v) {
+                        o_keys[b] = o_keys[b - 1];
+                        o_cnt[b] = o_cnt[b - 1];
                         b--;
                     }
-                    s_sorted[b] = v;
-                }
-            }
-            uint32_t runs = 0;
-            if (cnt) {
-                runs = 1;
-                for (uint32_t a = begin + 1; a < begin + nent; a++)
-                    runs += ((s_sorted[a] & keymask) != (s_sorted[a - 1] & keymask)) ? 1u : 0u;
-            }
-            uint32_t leaf_runs;
-            const uint32_t off = block_excl_scan(runs, s_warp, &leaf_runs, scans);
-            if (tid == 0) {
-                const unsigned long long base = atomicAdd(&ctl->out_cursor, (unsigned long long)leaf_runs);
-                s_base = base;
-                if (base + leaf_runs <= out_cap) {
-                    leaf_base[(uint64_t)q1 * Shape::P2 + p2] = base;
-                    leaf_n[(uint64_t)q1 * Shape::P2 + p2] = leaf_runs;
-                } else {
-                    atomicOr(&ctl->failed, (uint32_t)SP_FAIL_RUNLIST);  // temporary list full; leaf_n stays 0
+                    o_keys[b] = v;
+                    o_cnt[b] = vc;
                 }
             }
             __syncthreads();
-            const unsigned long long base = s_base;
-            if (cnt && base + leaf_runs <= out_cap) {
+            if (ok) {  // the leaf's runs, in code order, to the temporary list: coalesced
+                const unsigned long long base = s_base;
                 const uint64_t hi = prefix | ((uint64_t)p1 << r1bits) | ((uint64_t)p2 << r2bits);
-                uint64_t o = base + off;
-                R2T e0 = s_sorted[begin];
-                R2T cur = e0 & keymask;
-                uint32_t c = 1u + (uint32_t)((uint64_t)(e0 & cmax) >> (collapse ? r2bits : 0));
-                for (uint32_t a = begin + 1; a < begin + nent; a++) {
-                    const R2T ev = s_sorted[a];
-                    const R2T v = ev & keymask;
-                    const uint32_t cv = 1u + (uint32_t)((uint64_t)(ev & cmax) >> (collapse ? r2bits : 0));
-                    if (v != cur) {
-                        tmp_keys[o] = hi | (uint64_t)cur;
-                        tmp_counts[o] = c;
-                        o++;
-                        cur = v;
-                        c = cv;
-                    } else {
-                        c += cv;
-                    }
+                for (uint32_t i = tid; i < nd; i += SP_THREADS) {
+                    tmp_keys[base + i] = hi | (uint64_t)o_keys[i];
+                    tmp_counts[base + i] = o_cnt[i];
                 }
-                tmp_keys[o] = hi | (uint64_t)cur;
-                tmp_counts[o] = c;
             }
-            // the barriers of the next leaf (or of the next partition) order the reuse of
-            // s_hist / s_sorted behind these reads
-            __syncthreads();
+            // the next leaf writes o_[] and s_base only behind two more barriers
         }
     }
 }
@@ -619,9 +645,21 @@ int run_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix
     return KC_OK;
 }
 
+// Rounds on one GPU append their results (ascending code ranges) to ONE pair of arrays sized from the first round,
+// instead of leaving a piece each to be concatenated: no second copy of the result in memory, no copy pass, and the
+// same allocations in every call (the pool hands the same blocks out again).
+struct SpAppend {
+    uint64_t* keys = nullptr;
+    uint32_t* counts = nullptr;
+    uint64_t capacity = 0, used = 0;
+    uint32_t rounds = 0;    // > 1: the first round with k-mers allocates the arrays, sized from its own count
+    bool closed = false;    // a round did not fit: the later ones must stay behind it, as pieces
+    bool appended = false;  // set by run_count: the round's result went behind `used` (its kc_sparse has no arrays)
+};
+
 template <typename Shape, typename R1T, typename R2T>
 int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
-              uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, kc_sparse** out, int* failed) {
+              uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, SpAppend* into, kc_sparse** out, int* failed) {
     using St2 = Stager<R2T, Shape::P2>;
     cudaStream_t st = ctx->stream;
     const int cb = 2 * plan->k - (int)plan->round_bits;
@@ -643,36 +681,58 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void
     unsigned long long* leaf_off = (unsigned long long*)((char*)leaf_base + b_leaf_base);
     R2T* scratch2 = (R2T*)((char*)leaf_off + b_leaf_off);
 
-    // temporary run list: as many entries as fit in 45 % of what is free now (the final arrays
-    // need the same again), never more than one per window
+    // Temporary run list.  Its size must not depend on how much memory happens to be free (a different size every round
+    // makes the stream-ordered pool drop and re-create its blocks: 1.06 s for one allocation in round 2's config-5 runs),
+    // and one entry per window would be ~7 x what deep-coverage reads need: a quarter of this rank's share of the
+    // round's window positions, at most 45 % of what is free.  The leaf kernel keeps counting past the end of a list
+    // that turns out too short (SpCtl::out_cursor), so the second try below has the exact size.
     size_t free_b = 0, total_b = 0;
     KC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     free_b += kc_pool_idle_bytes(ctx->device);  // what earlier calls returned to the pool is ours to take again
-    uint64_t out_cap = (uint64_t)(free_b / 100 * 45) / 12;
+    // (45 %: the final arrays need the same again — unless the rounds append to arrays that exist already)
+    const uint64_t fit_cap = (uint64_t)(free_b / 100 * ((into && into->keys) ? 90 : 45)) / 12;
     const uint64_t round_windows = plan->max_windows >> plan->round_bits;
     const uint64_t most = (uint64_t)nsrc * (round_windows + round_windows / 8) / (plan->partitions / nparts) + (1u << 20);  // this rank's share of the round
-    if (out_cap > most) out_cap = most;
+    uint64_t out_cap = most / 4 + (1u << 20);
+    if (out_cap > fit_cap) out_cap = fit_cap;
+    static const char* cap_env = getenv("KC_SPARSE_RADIX_RUNLIST");  // tests: a first list this short
+    if (cap_env && (uint64_t)atoll(cap_env) < out_cap) out_cap = (uint64_t)atoll(cap_env);
     if (out_cap < 1024) return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: no device memory left for the run list");
     kc_trace(ctx, "count: enter", true);
     DevMem tkeys, tcounts;
-    if (tkeys.alloc(out_cap * 8) || tcounts.alloc(out_cap * 4)) {
-        cudaGetLastError();
-        return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: out of device memory for the run list");
+    SpCtl h;
+    for (int attempt = 0;; attempt++) {
+        if (tkeys.alloc(out_cap * 8) || tcounts.alloc(out_cap * 4)) {
+            cudaGetLastError();
+            return kc_set_error(ctx, KC_ERR_NOMEM, "sparse radix: out of device memory for the run list");
+        }
+        kc_trace(ctx, "count: run-list alloc");
+        KC_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(SpCtl), st));
+        KC_CUDA(ctx, cudaMemsetAsync(leaf_n, 0, nleaves * 4, st));
+        using LT = LeafTable<Shape, R2T>;
+        const size_t bins = (size_t)Shape::P2 * 2 * 64;  // phase B overlays the staging bins
+        const size_t smem2 = St2::SMEM_BYTES - bins + (bins > LT::BYTES ? bins : LT::BYTES);
+        {
+            auto kern = sp_leaf_kernel<Shape, R1T, R2T>;
+            KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, cb, (uint64_t)round << cb, (const R1T*)d_slabs, d_counts, (uint32_t)plan->region_records,
+                      plan->grid, nsrc, nparts, part_first, scratch2, (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p,
+                      out_cap, leaf_base, leaf_n, ctl);
+            KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
+        }
+        KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        KC_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h.failed == (uint32_t)SP_FAIL_RUNLIST && attempt == 0 && h.out_cursor <= fit_cap) {
+            // only the list was too short and the slabs are untouched: count again with the size the kernel reported
+            KC_STAT(13);
+            kc_pool_free(tkeys.release());
+            kc_pool_free(tcounts.release());
+            out_cap = h.out_cursor;
+            continue;
+        }
+        break;
     }
-    kc_trace(ctx, "count: run-list alloc");
-    KC_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(SpCtl), st));
-    KC_CUDA(ctx, cudaMemsetAsync(leaf_n, 0, nleaves * 4, st));
-    constexpr int LEAF_CAP = Shape::LEAF_CAP * 4 / (int)sizeof(R2T);
-    const size_t smem2 = St2::SMEM_BYTES + 1024 * 4 + (size_t)LEAF_CAP * sizeof(R2T);
-    {
-        auto kern = sp_leaf_kernel<Shape, R1T, R2T>;
-        KC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        KC_LAUNCH(kern, grid2, SP_THREADS, smem2, st, cb, (uint64_t)round << cb, (const R1T*)d_slabs, d_counts, (uint32_t)plan->region_records,
-                  plan->grid, nsrc, nparts, part_first, scratch2, (uint32_t)cap2, (uint64_t*)tkeys.p, (uint32_t*)tcounts.p,
-                  out_cap, leaf_base, leaf_n, ctl);
-        KC_LAUNCH_CHECK(ctx, "sp_leaf_kernel");
-    }
-    {
+    if (!h.failed) {
         const uint32_t nblocks = (uint32_t)((nleaves + SP_THREADS - 1) / SP_THREADS);
         unsigned long long* block_sums = (unsigned long long*)((char*)scratch2 + b_scratch2);
         KC_LAUNCH(sp_scan_sums_kernel, nblocks, SP_THREADS, 0, st, leaf_n, nleaves, block_sums);
@@ -681,10 +741,9 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void
         KC_LAUNCH_CHECK(ctx, "sp_scan_blocks_kernel");
         KC_LAUNCH(sp_scan_kernel, nblocks, SP_THREADS, 0, st, leaf_n, nleaves, block_sums, leaf_off);
         KC_LAUNCH_CHECK(ctx, "sp_scan_kernel");
+        KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        KC_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    SpCtl h;
-    KC_CUDA(ctx, cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
-    KC_CUDA(ctx, cudaStreamSynchronize(st));
     kc_trace(ctx, "count: leaf + scan kernels");
     if (h.failed) {
         *failed = (int)h.failed;
@@ -695,7 +754,34 @@ int run_count(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void
     res->device = ctx->device;
     res->size = h.total;
     *out = res;
+    if (into) into->appended = false;
     if (h.total == 0) return KC_OK;
+    if (into && !into->keys && !into->closed && into->rounds > 1) {
+        // the rounds split the codes by their top bits: size the whole result from this one (+ 12.5 %)
+        uint64_t cap = h.total * into->rounds;
+        cap += cap / 8 + 1024;
+        void *dk = nullptr, *dc = nullptr;
+        if (kc_pool_alloc(&dk, cap * 8) == cudaSuccess && kc_pool_alloc(&dc, cap * 4) == cudaSuccess) {
+            into->keys = (uint64_t*)dk;
+            into->counts = (uint32_t*)dc;
+            into->capacity = cap;
+            into->used = 0;
+        } else {  // no room for that: pieces, concatenated at the end
+            cudaGetLastError();
+            kc_pool_free(dk);
+            into->closed = true;
+        }
+    }
+    if (into && into->keys && !into->closed && into->used + h.total <= into->capacity) {
+        KC_LAUNCH(sp_gather_kernel, ctx->sm_count * 8, 256, 0, st, leaf_n, leaf_base, leaf_off, nleaves, (const uint64_t*)tkeys.p,
+                  (const uint32_t*)tcounts.p, into->keys + into->used, into->counts + into->used);
+        KC_LAUNCH_CHECK(ctx, "sp_gather_kernel");
+        KC_CUDA(ctx, cudaStreamSynchronize(st));
+        kc_trace(ctx, "count: gather kernel (appended)");
+        into->used += h.total;
+        into->appended = true;
+        return KC_OK;
+    }
     DevMem fk, fc;
     if (fk.alloc(h.total * 8) || fc.alloc(h.total * 4)) {
         cudaGetLastError();
@@ -734,7 +820,8 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
     // ROUNDS.  A leaf (one of P1 x P2 code ranges) is sorted in shared memory and must fit it; the slabs of all
     // windows must fit the device.  Large inputs are therefore counted in 2^round_bits rounds: round r keeps the
     // windows whose top round_bits code bits are r, and the partition tree works on the remaining bits.  Config 5
-    // (24 G windows, 64-bit leaf records): 22.9 K records per leaf against a capacity of 10 240 -> 4 rounds.
+    // (30 G window positions, 64-bit records): 192 GB of slabs -> 8 rounds on one GPU; 28.8 K positions per leaf against 14.7 K
+    // (leaf rule below) -> at least 2 rounds on any number of GPUs.
     static const int rb_env = getenv("KC_SPARSE_RADIX_RBITS") ? atoi(getenv("KC_SPARSE_RADIX_RBITS")) : -1;  // tests
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
@@ -746,6 +833,24 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
     free_b += kc_pool_idle_bytes(ctx->device) + ctx->scratch_bytes + ctx->scratch2_bytes + (size_t)ctx->caller_reusable_bytes;
     int rbits = (int)min_round_bits;
     if (2 * k - rbits - Shape::KB1 - Shape::KB2 < 1) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: %u round bits leave no code bits (k=%d)", min_round_bits, k);
+    auto fill = [&](int rb) {  // the plan for rb round bits
+        const int r1 = 2 * k - rb - Shape::KB1;
+        memset(plan, 0, sizeof *plan);
+        plan->k = k;
+        plan->world = world;
+        plan->partitions = Shape::P1;
+        plan->parts_per_rank = Shape::P1 / world;
+        plan->shape = shape_id;
+        plan->round_bits = (uint32_t)rb;
+        plan->rec_bytes = r1 <= 32 ? 4 : 8;
+        plan->max_windows = max_windows;
+        const uint64_t ngroups = (max_windows + k + 511 + 15) / 512 + 1;
+        const uint64_t want1 = (ngroups + 31) / 32;
+        plan->grid = (uint32_t)(want1 < 1 ? 1 : (want1 > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want1));
+        plan->region_records = region_records((max_windows >> rb) / ((uint64_t)Shape::P1 * plan->grid) + 1, 64 / (int)plan->rec_bytes, 8, 8);
+        plan->slab_bytes = (uint64_t)Shape::P1 * plan->grid * plan->region_records * plan->rec_bytes;
+        plan->counts_bytes = (uint64_t)Shape::P1 * plan->grid * 4;
+    };
     for (;; rbits++) {
         const int r1 = 2 * k - rbits - Shape::KB1, r2 = r1 - Shape::KB2;
         if (r2 < 1) {
@@ -756,39 +861,29 @@ int make_plan(kc_ctx* ctx, uint64_t max_windows, int k, uint32_t world, uint32_t
             if (rbits >= rb_env) break;
             continue;
         }
-        const uint64_t leaf_cap = (uint64_t)Shape::LEAF_CAP / (r2 <= 32 ? 1 : 2);  // records of 4 or 8 bytes
+        const uint64_t d_max = (uint64_t)Shape::LEAF_CAP / (r2 <= 32 ? 2 : 4);  // LeafTable::D_MAX for records of 4 or 8 bytes
         const uint64_t leaf_mean = ((uint64_t)world * max_windows >> rbits) / ((uint64_t)Shape::P1 * Shape::P2);
-        const uint64_t slab = (max_windows >> rbits) * (r1 <= 32 ? 4 : 8);
-        // window POSITIONS per leaf <= 72 % of the capacity.  The plan cannot know how many positions hold a valid
-        // window (reads: 130 of 151) nor how the records cluster (a leaf holds ~coverage copies of every k-mer in it:
-        // compound Poisson); config 4 at 30 x has 14.4 K positions, 12.4 K records, sigma 0.6 K per leaf against 20 480 and
-        // runs in one round.  A leaf that overflows anyway costs one retry with one more round bit (kc_sparse_radix,
-        // count_sparse_radix_sharded) before the hash table takes over.
-        const bool leaf_ok = leaf_mean * 25 <= leaf_cap * 18;
-        // slabs with their slack (+ the received copy when sharded) + the run list of a round + the result, the last two
-        // at an assumed one distinct k-mer per six windows (configs 4 / 5: 1 in 7.3 / 5.5).  An input that is less
-        // redundant than that runs out of memory or run-list room in some round and is retried with more rounds.
-        const uint64_t need = (slab + slab / 4) * (world > 1 ? 2 : 1) + ((max_windows >> rbits) / 6 + max_windows / 6) * 12;
+        // A leaf is limited by its DISTINCT codes (the leaf table), which the plan cannot know: it sees window
+        // POSITIONS (reads: 130 of 151 hold a valid window) and assumes every code has ~2.3 copies or more: positions
+        // per leaf <= 2.88 x D_MAX.  Config 4 at 30 x: 14.4 K positions, 12.4 K records, 1.7 K distinct against
+        // 10 240, one round.  Shallower inputs fill a leaf table; that costs one scatter and a cut-short leaf pass and
+        // is retried with one more round bit (kc_sparse_radix, count_sparse_radix_sharded) before the hash table takes over.
+        const bool leaf_ok = leaf_mean * 25 <= d_max * 72;
+        // Device memory: the slabs (+ the received copy when sharded), the work area with the leaf scratch, the run list
+        // of one round and the result with the slack the appended rounds give it, the last two at an assumed one distinct
+        // k-mer per six windows (configs 4 / 5: 1 in 7.3 / 5.5; run_count takes a quarter of the positions for the list
+        // when that fits).  An input that is less redundant than that runs out of memory or run-list room in some round
+        // and is counted again with the exact list size, or retried with more rounds.
+        fill(rbits);
+        const uint64_t rw = max_windows >> rbits;
+        const uint64_t result = max_windows / 6 * 12, run_list = ((rw + rw / 8) / 6 + (2u << 20)) * 12;
+        const uint64_t need = (plan->slab_bytes + plan->counts_bytes) * (world > 1 ? 2 : 1) + count_work_bytes<Shape>(ctx, plan, world, Shape::P1 / world) +
+                              result + result / 8 + run_list;
         const bool mem_ok = free_b == 0 || need <= free_b / 20 * 19;
         if ((leaf_ok && mem_ok) || rbits >= 8) break;
     }
-    const int r1 = 2 * k - rbits - Shape::KB1;
-    memset(plan, 0, sizeof *plan);
-    plan->k = k;
-    plan->world = world;
-    plan->partitions = Shape::P1;
-    plan->parts_per_rank = Shape::P1 / world;
-    plan->shape = shape_id;
-    plan->round_bits = (uint32_t)rbits;
-    plan->rec_bytes = r1 <= 32 ? 4 : 8;
-    plan->max_windows = max_windows;
-    const uint64_t ngroups = (max_windows + k + 511 + 15) / 512 + 1;
-    const uint64_t want1 = (ngroups + 31) / 32;
-    plan->grid = (uint32_t)(want1 < 1 ? 1 : (want1 > (uint64_t)ctx->sm_count ? (uint64_t)ctx->sm_count : want1));
-    plan->region_records = region_records((max_windows >> rbits) / ((uint64_t)Shape::P1 * plan->grid) + 1, 64 / (int)plan->rec_bytes, 8, 8);
+    fill(rbits);
     if (plan->region_records >= (1ull << 32)) return kc_set_error(ctx, KC_ERR_UNSUPPORTED, "sparse radix: region too large");
-    plan->slab_bytes = (uint64_t)Shape::P1 * plan->grid * plan->region_records * plan->rec_bytes;
-    plan->counts_bytes = (uint64_t)Shape::P1 * plan->grid * 4;
     return KC_OK;
 }
 
@@ -803,13 +898,13 @@ int scatter_dispatch(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_
 
 template <typename Shape>
 int count_dispatch(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
-                   uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, kc_sparse** out, int* failed) {
+                   uint32_t part_first, uint32_t nparts, char* work, size_t work_bytes, SpAppend* into, kc_sparse** out, int* failed) {
     const int r2 = 2 * plan->k - (int)plan->round_bits - Shape::KB1 - Shape::KB2;
     if (plan->rec_bytes == 4)
-        return run_count<Shape, uint32_t, uint32_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+        return run_count<Shape, uint32_t, uint32_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, into, out, failed);
     if (r2 <= 32)
-        return run_count<Shape, uint64_t, uint32_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
-    return run_count<Shape, uint64_t, uint64_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, out, failed);
+        return run_count<Shape, uint64_t, uint32_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, into, out, failed);
+    return run_count<Shape, uint64_t, uint64_t>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, work, work_bytes, into, out, failed);
 }
 
 using ShapeShipped = SpShape<10, 10, 20480>;
@@ -866,8 +961,8 @@ int kc_sparse_radix_scatter_round(kc_ctx* ctx, const char* d_data, uint64_t nbyt
     return KC_OK;
 }
 
-int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts,
-                                uint32_t nsrc, uint32_t part_first, uint32_t nparts, kc_sparse** out) {
+static int count_round_into(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts,
+                            uint32_t nsrc, uint32_t part_first, uint32_t nparts, SpAppend* into, kc_sparse** out) {
     if (!out) return KC_ERR_INVALID;
     *out = nullptr;
     if (!plan_ok(ctx, plan) || !d_slabs || !d_counts || nsrc < 1 || nparts < 1 || (uint64_t)part_first + nparts > plan->partitions ||
@@ -878,13 +973,18 @@ int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t
     int rc = kc_scratch2_reserve(ctx, wb);
     if (rc) return rc;
     int failed = 0;
-    rc = plan->shape ? count_dispatch<ShapeSmall>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed)
-                     : count_dispatch<ShapeShipped>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, out, &failed);
+    rc = plan->shape ? count_dispatch<ShapeSmall>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, into, out, &failed)
+                     : count_dispatch<ShapeShipped>(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, (char*)ctx->scratch2, wb, into, out, &failed);
     if (rc) return rc;
     if (failed)
         return kc_set_error(ctx, KC_ERR_TABLE_FULL, "sparse radix count overflowed (skewed input):%s%s%s%s", (failed & 1) ? " leaf region" : "",
                             (failed & 2) ? " staging bins" : "", (failed & 4) ? " leaf buffer" : "", (failed & 8) ? " run list" : "");
     return KC_OK;
+}
+
+int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs, const uint32_t* d_counts,
+                                uint32_t nsrc, uint32_t part_first, uint32_t nparts, kc_sparse** out) {
+    return count_round_into(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, nullptr, out);
 }
 
 // single-round forms (plans with round_bits = 0)
@@ -969,19 +1069,49 @@ int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_
         uint32_t* counts = (uint32_t*)((char*)ctx->scratch + pad((size_t)plan.slab_bytes));
         kc_trace(ctx, "radix: plan + scratch", true);
         const uint32_t rounds = 1u << plan.round_bits;
-        std::vector<kc_sparse*> parts(rounds, nullptr);
+        std::vector<kc_sparse*> parts(rounds + 1, nullptr);  // [0] = what the rounds appended, [1 + r] = round r's own piece
+        SpAppend acc;
+        acc.rounds = rounds;
         for (uint32_t r = 0; r < rounds && rc == KC_OK; r++) {
             rc = kc_sparse_radix_scatter_round(ctx, d_data, nbytes, &plan, r, slabs, counts);
             kc_trace(ctx, "radix: scatter");
-            if (rc == KC_OK) rc = kc_sparse_radix_count_round(ctx, &plan, r, slabs, counts, 1, 0, plan.partitions, &parts[r]);
+            if (rc == KC_OK) rc = count_round_into(ctx, &plan, r, slabs, counts, 1, 0, plan.partitions, rounds > 1 ? &acc : nullptr, &parts[1 + r]);
             kc_trace(ctx, "radix: count (incl. frees)", true);
+            if (rc != KC_OK || rounds == 1) continue;
+            if (acc.appended || (parts[1 + r] && parts[1 + r]->size == 0)) {  // the round's k-mers are in acc already (or it has none)
+                kc_sparse_free(parts[1 + r]);
+                parts[1 + r] = nullptr;
+            } else if (!acc.closed) {
+                KC_STAT(14);
+                acc.closed = true;  // a round that did not fit: the later ones must stay behind it, as pieces
+            }
+        }
+        if (acc.keys) {  // the appended rounds are the first piece
+            kc_sparse* head = new kc_sparse();
+            head->ctx = ctx;
+            head->device = ctx->device;
+            head->size = acc.used;
+            head->d_keys = acc.keys;
+            head->d_counts = acc.counts;
+            parts[0] = head;
         }
         if (rc == KC_OK) {
-            if (rounds == 1) {
-                *out = parts[0];
-                parts[0] = nullptr;
+            uint32_t npieces = 0, last = 0;
+            for (uint32_t i = 0; i <= rounds; i++)
+                if (parts[i]) npieces++, last = i;
+            if (npieces == 1) {
+                *out = parts[last];
+                parts[last] = nullptr;
+            } else if (npieces == 0) {
+                *out = new kc_sparse();
+                (*out)->ctx = ctx;
+                (*out)->device = ctx->device;
             } else {
-                rc = sparse_concat(ctx, parts.data(), rounds, out, true);
+                rc = sparse_concat(ctx, parts.data(), rounds + 1, out, true);
+                if (rc == KC_ERR_NOMEM) {  // the slabs have done their work: the pieces and their concatenation get the room
+                    kc_scratch_release(ctx);
+                    rc = sparse_concat(ctx, parts.data(), rounds + 1, out, true);
+                }
             }
         }
         for (kc_sparse* p : parts) kc_sparse_free(p);

@@ -174,7 +174,11 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
             parts.append(res)
         if ok:
             del bufs, recv
-            return parts[0] if rounds == 1 else stage(lambda: engine.sparse_concat(parts), dev)
+            if rounds == 1:
+                return parts[0]
+            if str(dev).startswith("cuda"):  # the pieces and their concatenation need the room the slab tensors took
+                torch.cuda.empty_cache()
+            return stage(lambda: engine.sparse_concat(parts), dev)
         for p in parts:
             if hasattr(p, "close"):
                 p.close()

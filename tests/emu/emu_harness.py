@@ -200,6 +200,15 @@ def make_input(kind, n, seed, k):
         pos = np.flatnonzero(rng.random(n) < 1.0 / period)
         a[pos] = np.frombuffer(b"N\n\0a", dtype=np.uint8)[rng.integers(0, 4, pos.size)]
         return a
+    if kind == "runsT":  # random ACGT with runs of T: windows whose code is all ones (the leaf table's EMPTY value)
+        rng = np.random.default_rng(seed)
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+        for pos in rng.integers(0, max(n - 2 * k, 1), 5):  # (few and short: long runs are skew, the regions' business)
+            a[pos:pos + k + int(rng.integers(0, 6))] = ord("T")
+        return a
+    if kind == "fewA":  # random ACGT with 21 % A: the round of the codes that END in A is smaller than the others
+        rng = np.random.default_rng(seed)
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, n, p=[0.21, 0.2633, 0.2633, 0.2634])].copy()
     if kind == "skew":  # 90 % of the windows fall into a few partitions
         rng = np.random.default_rng(seed)
         a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]

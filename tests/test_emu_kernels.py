@@ -158,6 +158,54 @@ def test_sparse_radix_small_shape(k):
         del os.environ["KC_SPARSE_RADIX_SHAPE"]
 
 
+def test_sparse_radix_leaf_table_all_ones_code():
+    """16 x 16 shape, k = 20: the leaf records keep all 32 bits of uint32, so the all-T window's record equals the leaf
+    table's EMPTY marker and is counted on the side (s_special); k = 21 / 31: EMPTY is not a record, same inputs"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        for k in (20, 21, 31):
+            run_case("sparse", k, 30_000, RADIX | NOFB, "runsT", k, 0, seed=0)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+def test_sparse_radix_leaf_with_too_many_distinct_codes_gets_more_rounds():
+    """16 x 16 shape, 64-bit leaf records: 512 distinct codes per leaf at most; 180 000 bases of shallow reads put ~540 in a
+    leaf, inside the plan's record rule — the leaf table fills, the count is void and kc_sparse_radix retries with one
+    more round bit (stat 11), which halves the leaves"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        out = run_case("sparse", 23, 180_000, RADIX | NOFB, "readsU", 3, 0, seed=0)
+        assert emu_stats(out)[11] == 1, out
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+def test_sparse_radix_rounds_on_one_gpu_append_to_one_result():
+    """four forced rounds (KC_SPARSE_RADIX_RBITS=2): round 0's result sizes the arrays the later rounds append to; with
+    'fewA' the last round does not fit behind the others and is concatenated as a piece of its own"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        for k in (21, 31):
+            run_case("sparse", k, 60_000, RADIX | NOFB, "readsU", k, 0, seed=0, KC_SPARSE_RADIX_RBITS=2)
+        out = run_case("sparse", 17, 60_000, RADIX | NOFB, "fewA", 3, 0, seed=0, KC_SPARSE_RADIX_RBITS=2)
+        assert emu_stats(out)[14] >= 1, out
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
+def test_sparse_radix_short_run_list_is_counted_again_with_the_exact_size():
+    """the temporary run list is sized from an estimate; when it is too short the leaf kernel still reports the number of
+    runs and the count is repeated once with exactly that many entries (stat 13), no new scatter, no hash fallback"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        out = run_case("sparse", 21, 60_000, RADIX | NOFB, "readsU", 5, 0, seed=0, KC_SPARSE_RADIX_RUNLIST=2000)
+        st = emu_stats(out)
+        assert st[13] == 1 and st[11] == 0, out
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_sparse_radix_staging_random_schedules(seed):
     os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
