@@ -62,7 +62,11 @@ enum { SP_FAIL_REGION = 1, SP_FAIL_STAGING = 2, SP_FAIL_LEAF = 4, SP_FAIL_RUNLIS
 // bin, which replaces that path's "count it directly with global REDs" fallback (a
 // sparse result has no table to RED into).  Failed attempts inflate only the reserved
 // field (24 bits: SP_MAX_TRIES x 1024 threads cannot carry into the written field), and the
-// reset wipes them.
+// reset wipes them.  (Round 2 also ran the form of dense_wide.cu here — the written count as a
+// red.shared without return value and the writer of the LAST slot waiting for it: scatter 82.6 vs
+// 81.9 ms, leaf kernel 152.3 vs 150.3 ms at config 4; the second round trip is not what these
+// kernels wait for — they are issue-bound at 4.4 warp instructions per window — so the form
+// without a wait loop stays.)
 // ---------------------------------------------------------------------------
 template <typename RecT, int P_>
 struct Stager {
