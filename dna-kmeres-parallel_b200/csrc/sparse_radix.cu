@@ -221,11 +221,29 @@ sp_scatter_kernel(ScanGeom g, R1T* __restrict__ slabs1, uint32_t* __restrict__ c
         // a loop over the set bits, not 16 unrolled copies: the staging code is long and 16
         // copies of it are 56 KB of SASS, more than the instruction cache holds
         uint32_t m = lw.ok & 0xFFFFu;
+        if (rbits >= 2) {
+            // ROUNDS: keep the windows whose top rbits code bits are `round` — for all 16 windows of the lane at once,
+            // before any code is built (a per-window test cost 15 instructions for each of the 7 in 8 windows that
+            // belong to other rounds: 138 -> 102 ms per round of config 5, which has 8 on one GPU; with two rounds
+            // the per-window test below is the cheaper one, 83 vs 89 ms).  The code of window j is the bit
+            // range [2j, 2j + 2k) of the lane's 2-bit stream p0|p1|p2, its top bits the range [2j + cb, 2j + 2k):
+            // S = stream >> cb holds them at stride 2, and plane b of all 16 windows is compared in one XOR.
+            const uint64_t lo64 = (uint64_t)lw.p0 | ((uint64_t)lw.p1 << 32);
+            const uint64_t S = (lo64 >> cb) | ((uint64_t)lw.p2 << (64 - cb));  // 22 - 8 <= cb <= 62: both shifts defined
+            uint32_t differs = 0;
+            for (int b = 0; b < rbits; b++) differs |= (uint32_t)(S >> b) ^ (0u - ((round >> b) & 1u));
+            uint32_t x = ~differs & 0x55555555u;  // bit 2j: window j is of this round
+            x = (x | (x >> 1)) & 0x33333333u;
+            x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+            x = (x | (x >> 4)) & 0x00FF00FFu;
+            x = (x | (x >> 8)) & 0x0000FFFFu;
+            m &= x;
+        }
         while (m) {
             const int j = __ffs((int)m) - 1;
             m &= m - 1u;
             const uint64_t code = lw.code64(j, kmask);
-            if (rbits && (uint32_t)(code >> cb) != round) continue;
+            if (rbits == 1 && (uint32_t)(code >> cb) != round) continue;
             st.stage((uint32_t)(code >> r1bits) & (Shape::P1 - 1), (R1T)(code & r1mask), pref + (uint32_t)j);
         }
     });
@@ -410,8 +428,8 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
             if (n == 0) continue;  // CTA-uniform
             const R2T* leaf = my_scratch + (uint64_t)p2 * cap2;
             // table size for this leaf: two slots per record, at most SLOTS (slots outside stay clean)
-            uint32_t slots = 64;
-            while (slots < 2 * n && slots < (uint32_t)LT::SLOTS) slots <<= 1;
+            uint32_t slots = n <= 32 ? 64u : (2u << (31 - __clz((int)(2 * n - 1))));  // smallest power of two >= 2 n
+            if (slots > (uint32_t)LT::SLOTS) slots = LT::SLOTS;
             const uint32_t smask = slots - 1u;
             const int hshift = 32 - (31 - __clz(slots));
             auto sub_of = [&](R2T key) { return (uint32_t)((uint64_t)key >> lowbits) & (nb - 1u); };

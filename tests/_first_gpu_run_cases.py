@@ -126,8 +126,11 @@ for k, nreads in ((21, %d), (31, %d), (13, %d)):
 print("ROUNDS_OK")
 """ % (ROOT, sz(150_000) if FULL else 700, sz(100_000) if FULL else 500, sz(100_000) if FULL else 500)
     import subprocess
-    for rbits in ("1", "3"):
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=200,
-                           env=dict(os.environ, KC_SPARSE_RADIX_RBITS=rbits))
-        assert r.returncode == 0 and "ROUNDS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    # KC_SPARSE_RADIX_RUNLIST: a first temporary run list this short, so that the count is repeated with the exact size
+    # the leaf kernel reported (run_count's second try), with one round and with appended rounds
+    for extra in (dict(KC_SPARSE_RADIX_RBITS="1"), dict(KC_SPARSE_RADIX_RBITS="3"), dict(KC_SPARSE_RADIX_RBITS="6"),
+                  dict(KC_SPARSE_RADIX_RBITS="0", KC_SPARSE_RADIX_RUNLIST="5000"),
+                  dict(KC_SPARSE_RADIX_RBITS="2", KC_SPARSE_RADIX_RUNLIST="5000")):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=200, env=dict(os.environ, **extra))
+        assert r.returncode == 0 and "ROUNDS_OK" in r.stdout, str(extra) + r.stdout[-1500:] + r.stderr[-3000:]
 

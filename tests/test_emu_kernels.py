@@ -194,6 +194,19 @@ def test_sparse_radix_rounds_on_one_gpu_append_to_one_result():
         del os.environ["KC_SPARSE_RADIX_SHAPE"]
 
 
+@pytest.mark.parametrize("rbits,k", [(1, 13), (3, 17), (3, 18), (5, 24), (4, 31), (8, 31)])
+def test_sparse_radix_round_filter(rbits, k):
+    """sp_scatter_kernel picks the windows of a round with one bit-plane compare per lane and group (all 16 windows at
+    once): every round count, both scanner halos, 'dirty' input with invalid bytes everywhere"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        n = 25_000 if rbits < 5 else 6_000  # (2^rbits rounds of 16 x 16 partitions each on the emulator)
+        run_case("sparse", k, n, RADIX | NOFB, "dirty", 10 * rbits + k, k % 7, seed=0, KC_SPARSE_RADIX_RBITS=rbits)
+        run_case("sparse", k, n, RADIX | NOFB, "readsU", rbits + k, 0, seed=0, KC_SPARSE_RADIX_RBITS=rbits)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
 def test_sparse_radix_short_run_list_is_counted_again_with_the_exact_size():
     """the temporary run list is sized from an estimate; when it is too short the leaf kernel still reports the number of
     runs and the count is repeated once with exactly that many entries (stat 13), no new scatter, no hash fallback"""

@@ -23,6 +23,23 @@ def entry(path):
     return e
 
 
+def code_state(name):
+    """which leaf pass / planning the run had (the file tags are the GPU calls of round 2, in order)"""
+    import re
+    m = re.match(r"r02_(c|m|n)(\d+)(b?)_", name)
+    if not m:
+        return None
+    kind, num, b = m.group(1), int(m.group(2)), m.group(3)
+    if kind == "c" and num == 23:
+        return "A/B of call 23: distinct-first leaf pass" if "dedupe" in name else "A/B of call 23: record-sort leaf pass"
+    if (kind == "c" and num >= 24) or b:
+        s = "distinct-first leaf pass"
+        if kind == "c" and num in (24, 25):
+            s += " (plan / append logic of that call still being fixed: config 5 lines show allocation stalls or a retried plan)"
+        return s
+    return "record-sort leaf pass (round 2's first form)"
+
+
 def main():
     out = []
     for p in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "r02_*.log"))):
@@ -33,6 +50,8 @@ def main():
             if "_sp_" not in p and "config4" not in p and "config5" not in p:
                 e = None
         # runs under ncu are never bench values; lines without the self-check predate csrc/check.cu (early round 2)
+        if e:
+            e["code"] = code_state(e["file"])
         if e and "_ncu_" not in e["file"] and (e.get("self_check") or e.get("ms_per_step") is None) \
                 and ("config4" in e["file"] or "config5" in e["file"]):
             out.append(e)
