@@ -19,9 +19,9 @@ KC_OK = 0
 KC_ERR_INVALID, KC_ERR_CUDA, KC_ERR_IO, KC_ERR_NOMEM, KC_ERR_TABLE_FULL, KC_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 DENSE_AUTO, DENSE_DIRECT, DENSE_PARTITION = 0, 1, 2
 DENSE_SMEM16C, DENSE_PARTITION_DEFER, DENSE_PARTITION_PAIR, DENSE_PARTITION_TRIO = 3, 4, 5, 6
-DENSE_PARTITION_WIDE = 7  # first B200 run pending; never chosen by DENSE_AUTO
+DENSE_PARTITION_WIDE = 7  # seven windows per record, first-generation scatter (2.72 + 0.82 ms); not chosen by DENSE_AUTO
 DENSE_PARTITION_DEFER_PAIR, DENSE_PARTITION_DEFER_TRIO = 8, 9  # the scatter of 4 with the count of 5 / 6
-DENSE_PARTITION_WIDE2 = 10  # seven windows per record, second-generation scatter (cooperative flush)
+DENSE_PARTITION_WIDE2 = 10  # seven windows per record, second-generation scatter: DENSE_AUTO's choice at k = 12 (1.91 + 0.82 ms)
 SPARSE_HASH, SPARSE_SORT, SPARSE_RADIX = 0, 1, 2
 SPARSE_AUTO = 3  # the engine picks (radix wherever it exists, by measurement on B200)
 SPARSE_UNSORTED = 0x100
