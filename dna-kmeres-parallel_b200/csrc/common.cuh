@@ -500,6 +500,10 @@ __device__ __forceinline__ void kc_warp_scan(const ScanGeom& g, uint64_t gb, uin
         }
         lw.ok = ok;
         body(lw, a0);
+        // A body with data-dependent loops (staging, probing) leaves the lanes of a warp on separate paths, and nothing
+        // brought them together before the next shuffle: ncu showed the decode below running with 5 of 32 threads per
+        // instruction, 6.4 times as often as there are groups (sp_scatter_kernel, round 2).  Converge here.
+        __syncwarp();
         cur = nxt;
         nxt = kc_finish_block(g, (grp + 2) * 32 + lane, raw);
     }

@@ -379,24 +379,27 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
         constexpr uint32_t RPV = 16 / sizeof(R1T);  // records per 128-bit load
         for (uint32_t reg = warp; reg < nregions; reg += SP_THREADS / 32) {
             // the result is void already: do not grind on (a short run list is not void: the host wants the full count of runs)
-            if (*(volatile uint32_t*)&ctl->failed & ~(uint32_t)SP_FAIL_RUNLIST) break;
+            // (decided by the whole warp: the loop below holds __syncwarp)
+            if (__any_sync(0xffffffffu, (*(volatile uint32_t*)&ctl->failed & ~(uint32_t)SP_FAIL_RUNLIST) != 0)) break;
             const uint64_t ri = region_index(reg);
             const uint32_t n = counts1[ri];
             const R1T* src = slabs1 + ri * cap1;  // 64-byte aligned
             const uint4* src4 = reinterpret_cast<const uint4*>(src);
             const uint32_t nv = n / RPV;
-            for (uint32_t i = lane; i < nv; i += 64) {  // two 128-bit loads in flight per lane
-                const bool two = i + 32 < nv;
-                const uint4 v0 = kc_ldg_stream(src4 + i);
+            for (uint32_t i0 = 0; i0 < nv; i0 += 64) {  // two 128-bit loads in flight per lane; warp-uniform trip count
+                const uint32_t i = i0 + (uint32_t)lane;
+                const bool one = i < nv, two = i + 32 < nv;
+                const uint4 v0 = one ? kc_ldg_stream(src4 + i) : make_uint4(0, 0, 0, 0);
                 const uint4 v1 = two ? kc_ldg_stream(src4 + i + 32) : make_uint4(0, 0, 0, 0);
                 const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                const int words = two ? 8 : 4;
+                const int words = two ? 8 : (one ? 4 : 0);
 #pragma unroll 1
                 for (int e = 0; e < words; e += (int)sizeof(R1T) / 4) {
                     uint64_t r1 = pick(w, e);
                     if (sizeof(R1T) == 8) r1 |= (uint64_t)pick(w, e + 1) << 32;
                     stage1(r1, (uint32_t)warp + (uint32_t)e);
                 }
+                __syncwarp();  // the staging paths of the lanes end here (see kc_warp_scan): the next loads are issued by the whole warp
             }
             for (uint32_t t = nv * RPV + lane; t < n; t += 32) stage1((uint64_t)src[t], (uint32_t)warp);
         }
@@ -468,6 +471,7 @@ sp_leaf_kernel(int cb /* code bits of this round = 2k - rbits */, uint64_t prefi
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     if (have[q]) insert(r[q]);
+                __syncwarp();  // probe loops differ per lane: the next four loads are issued by the whole warp
             }
             __syncthreads();
             const uint32_t cnt = (uint32_t)tid < nb ? s_hist[tid] : 0u;
