@@ -78,6 +78,7 @@ struct kc_sparse {
     kc_ctx* ctx = nullptr;
     int device = -1;   // recorded at creation: kc_sparse_free does not dereference ctx (it may be gone)
     uint64_t size = 0;
+    uint64_t capacity = 0;  // entries the arrays hold; 0 = exactly `size` (a result that rounds append to has more)
     uint64_t* d_keys = nullptr;
     uint32_t* d_counts = nullptr;
 };

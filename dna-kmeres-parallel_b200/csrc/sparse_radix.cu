@@ -1013,6 +1013,75 @@ int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t
     return count_round_into(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, nullptr, out);
 }
 
+// The rounds of a plan, one call per round in ascending order, into ONE result: *acc is NULL before the first round
+// and holds everything counted so far after each call.  The first round with k-mers sizes the arrays for all rounds
+// (its count x rounds + 12.5 %: the rounds split the codes by their top bits); a later round that does not fit makes
+// them grow (one copy).  Nothing is concatenated at the end and the allocations of a call repeat in the next one.
+int kc_sparse_radix_count_round_append(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round, const void* d_slabs,
+                                       const uint32_t* d_counts, uint32_t nsrc, uint32_t part_first, uint32_t nparts,
+                                       kc_sparse** acc) {
+    if (!acc || !plan) return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_count_round_append: bad argument");
+    const uint32_t rounds = 1u << plan->round_bits;
+    SpAppend a;
+    a.rounds = rounds;
+    if (*acc) {
+        if ((*acc)->ctx != ctx) return kc_set_error(ctx, KC_ERR_INVALID, "kc_sparse_radix_count_round_append: result of another context");
+        a.keys = (*acc)->d_keys;
+        a.counts = (*acc)->d_counts;
+        a.used = (*acc)->size;
+        a.capacity = (*acc)->capacity ? (*acc)->capacity : (*acc)->size;
+        a.closed = a.keys == nullptr;  // an empty result so far: the round's own arrays are adopted below
+    }
+    kc_sparse* piece = nullptr;
+    int rc = count_round_into(ctx, plan, round, d_slabs, d_counts, nsrc, part_first, nparts, &a, &piece);
+    if (rc) return rc;
+    DeviceGuard dg(ctx->device);
+    if (!*acc) {
+        *acc = new kc_sparse();
+        (*acc)->ctx = ctx;
+        (*acc)->device = ctx->device;
+    }
+    kc_sparse* r = *acc;
+    if (a.appended) {  // run_count wrote behind a.used (and allocated the arrays if this was the first round with k-mers)
+        r->d_keys = a.keys;
+        r->d_counts = a.counts;
+        r->capacity = a.capacity;
+        r->size = a.used;
+    } else if (piece && piece->size) {
+        if (!r->d_keys) {  // nothing so far: the piece's arrays become the result's
+            r->d_keys = piece->d_keys;
+            r->d_counts = piece->d_counts;
+            r->size = r->capacity = piece->size;
+            piece->d_keys = nullptr;
+            piece->d_counts = nullptr;
+        } else {  // did not fit behind the others: grow to what the remaining rounds are likely to need as well
+            KC_STAT(14);
+            uint64_t cap = r->size + piece->size + (uint64_t)(rounds - 1 - (round < rounds ? round : rounds - 1)) * (piece->size + piece->size / 8);
+            void *dk = nullptr, *dc = nullptr;
+            if (kc_pool_alloc(&dk, cap * 8) != cudaSuccess || kc_pool_alloc(&dc, cap * 4) != cudaSuccess) {
+                cudaGetLastError();
+                kc_pool_free(dk);
+                kc_sparse_free(piece);
+                return kc_set_error(ctx, KC_ERR_NOMEM, "kc_sparse_radix_count_round_append: out of device memory for %llu k-mers", (unsigned long long)cap);
+            }
+            cudaStream_t st = ctx->stream;
+            KC_CUDA(ctx, cudaMemcpyAsync(dk, r->d_keys, r->size * 8, cudaMemcpyDeviceToDevice, st));
+            KC_CUDA(ctx, cudaMemcpyAsync(dc, r->d_counts, r->size * 4, cudaMemcpyDeviceToDevice, st));
+            KC_CUDA(ctx, cudaMemcpyAsync((uint64_t*)dk + r->size, piece->d_keys, piece->size * 8, cudaMemcpyDeviceToDevice, st));
+            KC_CUDA(ctx, cudaMemcpyAsync((uint32_t*)dc + r->size, piece->d_counts, piece->size * 4, cudaMemcpyDeviceToDevice, st));
+            KC_CUDA(ctx, cudaStreamSynchronize(st));
+            kc_pool_free(r->d_keys);
+            kc_pool_free(r->d_counts);
+            r->d_keys = (uint64_t*)dk;
+            r->d_counts = (uint32_t*)dc;
+            r->size += piece->size;
+            r->capacity = cap;
+        }
+    }
+    kc_sparse_free(piece);
+    return KC_OK;
+}
+
 // single-round forms (plans with round_bits = 0)
 int kc_sparse_radix_scatter(kc_ctx* ctx, const char* d_data, uint64_t nbytes, const kc_radix_plan* plan, void* d_slabs,
                             uint32_t* d_counts) {
@@ -1117,6 +1186,7 @@ int kc_sparse_radix(kc_ctx* ctx, const char* d_data, uint64_t nbytes, int k, kc_
             head->ctx = ctx;
             head->device = ctx->device;
             head->size = acc.used;
+            head->capacity = acc.capacity;
             head->d_keys = acc.keys;
             head->d_counts = acc.counts;
             parts[0] = head;

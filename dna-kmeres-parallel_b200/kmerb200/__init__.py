@@ -123,6 +123,7 @@ def lib():
         "kc_sparse_radix_plan_rounds": (i32, [vp, u64, i32, u32, u32, vp]),
         "kc_sparse_radix_scatter_round": (i32, [vp, vp, u64, vp, u32, vp, vp]),
         "kc_sparse_radix_count_round": (i32, [vp, vp, u32, vp, vp, u32, u32, u32, C.POINTER(vp)]),
+        "kc_sparse_radix_count_round_append": (i32, [vp, vp, u32, vp, vp, u32, u32, u32, C.POINTER(vp)]),
         "kc_sparse_concat": (i32, [vp, vp, u32, C.POINTER(vp)]),
         "kc_mix64": (u64, [u64]),
         "kc_window_fingerprint": (i32, [vp, vp, u64, i32, C.POINTER(u64), C.POINTER(u64)]),
@@ -528,6 +529,18 @@ class Context:
         self._check(lib().kc_sparse_radix_count_round(self._h, C.addressof(plan), rnd, _ptr(slabs), _ptr(counts), nsrc, part_first,
                                                       nparts, C.byref(h)))
         return Sparse(self, h)
+
+    def radix_count_append(self, plan, slabs, counts, nsrc, part_first, nparts, rnd, acc=None):
+        """count round `rnd` (rounds in ascending order) behind what `acc` holds; returns the one growing result"""
+        self._torch().cuda.current_stream().synchronize()
+        h = C.c_void_p(acc._h.value if acc is not None else None)
+        try:
+            self._check(lib().kc_sparse_radix_count_round_append(self._h, C.addressof(plan), rnd, _ptr(slabs), _ptr(counts), nsrc,
+                                                                 part_first, nparts, C.byref(h)))
+        finally:
+            if acc is not None:
+                acc._h = h
+        return acc if acc is not None else Sparse(self, h)
 
     def sparse_concat(self, parts):
         """one result from ascending pieces (the rounds of a radix plan); the pieces are closed"""

@@ -141,7 +141,7 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     # Large inputs run in 2^round_bits rounds (round r = the windows whose top code bits are r; the plan sizes them so
     # that a leaf fits shared memory and the slabs fit the device): every round has its own scatter, all-to-all and
-    # count and reuses the buffers; rank r's pieces are ascending code ranges, joined at the end.  An overflow on any
+    # count and reuses the buffers; rank r's rounds are ascending code ranges, appended to one result.  An overflow on any
     # rank (leaves denser than planned) is retried twice with one more round bit before the caller's fallback.
     min_bits, bufs, recv = 0, None, None
     for attempt in range(3):
@@ -156,7 +156,7 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
         if bufs is not None and (bufs[0].numel() != plan.slab_bytes or bufs[1].numel() * 4 != plan.counts_bytes):
             bufs = recv = None  # the new plan has other buffer sizes
         rounds = 1 << getattr(plan, "round_bits", 0)
-        parts, ok = [], True
+        acc, ok = None, True  # one result that the rounds append to (kc_sparse_radix_count_round_append): no pieces, no concat
         for rnd in range(rounds):
             sc = stage(lambda: engine.radix_scatter(reads, nbytes, plan, rnd, bufs), dev)
             if sc is None:
@@ -167,21 +167,19 @@ def count_sparse_radix_sharded(engine, reads, nbytes, k, table_full=()):
                 recv = stage(lambda: (torch.empty_like(bufs[0]), torch.empty_like(bufs[1])), dev)
             dist.all_to_all_single(recv[0], bufs[0])  # equal splits: block o = partitions [o, o+1) * parts_per_rank
             dist.all_to_all_single(recv[1], bufs[1])
-            res = stage(lambda: engine.radix_count(plan, recv[0], recv[1], world, rank * plan.parts_per_rank, plan.parts_per_rank, rnd), dev)
+            res = stage(lambda: engine.radix_count_append(plan, recv[0], recv[1], world, rank * plan.parts_per_rank, plan.parts_per_rank,
+                                                          rnd, acc), dev)
             if res is None:
                 ok = False
                 break
-            parts.append(res)
+            acc = res
         if ok:
-            del bufs, recv
-            if rounds == 1:
-                return parts[0]
-            if str(dev).startswith("cuda"):  # the pieces and their concatenation need the room the slab tensors took
-                torch.cuda.empty_cache()
-            return stage(lambda: engine.sparse_concat(parts), dev)
-        for p in parts:
-            if hasattr(p, "close"):
-                p.close()
+            return engine.finish(acc) if hasattr(engine, "finish") else acc
+        if acc is not None:
+            if hasattr(acc, "close"):
+                acc.close()
+            elif hasattr(engine, "finish"):
+                engine.finish(acc)
         min_bits = getattr(plan, "round_bits", 0) + 1
         if min_bits > 8:
             break

@@ -285,6 +285,15 @@ KC_API int kc_sparse_radix_scatter_round(kc_ctx* ctx, const char* d_data, uint64
 KC_API int kc_sparse_radix_count_round(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round,
                                        const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
                                        uint32_t part_first, uint32_t nparts, kc_sparse** out);
+/* The count stage of round `round` APPENDED to one result: call it for the rounds in ascending order with *acc = NULL
+ * before the first; after every call *acc holds all k-mers counted so far (ascending), after the last one it is the
+ * rank's whole result.  The arrays are sized from the first round (count x rounds + 12.5 %) and grow when a later
+ * round does not fit, so nothing is concatenated and no second copy of the result exists (kc_sparse_radix_count_round
+ * + kc_sparse_concat: pieces and whole side by side).  On an error *acc stays valid (without the failed round);
+ * free it with kc_sparse_free. */
+KC_API int kc_sparse_radix_count_round_append(kc_ctx* ctx, const kc_radix_plan* plan, uint32_t round,
+                                              const void* d_slabs, const uint32_t* d_counts, uint32_t nsrc,
+                                              uint32_t part_first, uint32_t nparts, kc_sparse** acc);
 KC_API int kc_sparse_concat(kc_ctx* ctx, kc_sparse* const* parts, uint32_t nparts, kc_sparse** out);
 KC_API void kc_sparse_free(kc_sparse* s);
 KC_API uint64_t kc_sparse_size(const kc_sparse* s);

@@ -67,6 +67,26 @@ class EmuEngine:
         self.ctx.L.kc_sparse_free(sp)
         return keys, cnts
 
+    def radix_count_append(self, plan, slabs, counts, nsrc, part_first, nparts, rnd, acc=None):
+        """kc_sparse_radix_count_round_append: `acc` = the kc_sparse handle that grows round by round"""
+        b1, d_s = self.ctx.upload(slabs.numpy())
+        b2, d_c = self.ctx.upload(counts.numpy())
+        h = acc if acc is not None else C.c_void_p()
+        try:
+            self._check(self.ctx.L.kc_sparse_radix_count_round_append(self.ctx.h, C.byref(plan), rnd, d_s, d_c, nsrc, part_first, nparts,
+                                                                      C.byref(h)))
+        finally:
+            self.ctx.free(b1)
+            self.ctx.free(b2)
+        return h
+
+    def finish(self, acc):  # handle -> (keys, counts) on the host
+        n = int(self.ctx.L.kc_sparse_size(acc))
+        keys, cnts = np.empty(n, np.uint64), np.empty(n, np.uint32)
+        self.ctx.check(self.ctx.L.kc_sparse_copy_to_host(self.ctx.h, acc, keys.ctypes.data, cnts.ctypes.data))
+        self.ctx.L.kc_sparse_free(acc)
+        return keys, cnts
+
     def sparse_concat(self, parts):  # the rounds' pieces of this rank, ascending
         return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
 

@@ -91,6 +91,8 @@ def lib():
         L.kc_sparse_radix_scatter_round.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.kc_sparse_radix_count_round.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                   C.c_void_p]
+        L.kc_sparse_radix_count_round_append.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.c_void_p]
         L.kc_sparse_radix_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                             C.POINTER(C.c_void_p)]
         L.kc_gen_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
@@ -576,7 +578,36 @@ def case_fingerprint(args):
     print("ok fingerprint", *args)
 
 
-CASES = {"fingerprint": case_fingerprint, "dense_host_packed": case_dense_host_packed, "ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
+def case_radix_append(args):
+    """kc_sparse_radix_count_round_append on one rank: the rounds of a plan (KC_SPARSE_RADIX_RBITS forces several) are
+    appended to ONE result; with 'fewA' the first round is the smallest, so a later one does not fit the arrays that
+    were sized from it and they grow (stat 14)."""
+    k, n, kind, seed = int(args[0]), int(args[1]), args[2], int(args[3])
+    O = _oracle()
+    data = make_input(kind, n, seed, k) if kind != "readsU" else O.gen_reads(seed, 4 * n, 100, 50, 0, n // 101)
+    ctx = EmuContext()
+    L = ctx.L
+    plan = RadixPlan()
+    ctx.check(L.kc_sparse_radix_plan(ctx.h, max(data.size - k + 1, 0), k, 1, C.byref(plan)))
+    base, p = ctx.upload(data, 3)
+    d_s, d_c = ctx.alloc(plan.slab_bytes), ctx.alloc(plan.counts_bytes)
+    acc = C.c_void_p()
+    for rnd in range(1 << plan.round_bits):
+        ctx.check(L.kc_sparse_radix_scatter_round(ctx.h, p, data.size, C.byref(plan), rnd, d_s, d_c))
+        ctx.check(L.kc_sparse_radix_count_round_append(ctx.h, C.byref(plan), rnd, d_s, d_c, 1, 0, plan.partitions, C.byref(acc)))
+    cnt = int(L.kc_sparse_size(acc))
+    keys, counts = np.empty(cnt, np.uint64), np.empty(cnt, np.uint32)
+    ctx.check(L.kc_sparse_copy_to_host(ctx.h, acc, keys.ctypes.data, counts.ctypes.data))
+    L.kc_sparse_free(acc)
+    for q in (base, d_s, d_c):
+        ctx.free(q)
+    wk, wc, _ = O.count_sparse(data, k)
+    assert keys.size == wk.size and (keys == wk).all() and (counts == wc).all(), "appended rounds differ from the oracle (k=%d)" % k
+    ctx.close()
+    print("ok radix_append", *args, "rounds", 1 << plan.round_bits, "distinct", cnt)
+
+
+CASES = {"radix_append": case_radix_append, "fingerprint": case_fingerprint, "dense_host_packed": case_dense_host_packed, "ingest": case_ingest, "packed": case_packed, "dense_host": case_dense_host, "radix_sharded": case_radix_sharded, "dense": case_dense, "sparse": case_sparse, "perseq": case_perseq, "gen": case_gen}
 
 if __name__ == "__main__":
     CASES[sys.argv[1]](sys.argv[2:])

@@ -207,6 +207,19 @@ def test_sparse_radix_round_filter(rbits, k):
         del os.environ["KC_SPARSE_RADIX_SHAPE"]
 
 
+def test_sparse_radix_count_round_append():
+    """the multi-GPU form of the appended rounds (kc_sparse_radix_count_round_append, one call per round): arrays sized
+    from the first round, grown when a later round does not fit ('fewA': stat 14), a single round adopted as it is"""
+    os.environ["KC_SPARSE_RADIX_SHAPE"] = "small"
+    try:
+        run_case("radix_append", 21, 40_000, "readsU", 4, seed=0, KC_SPARSE_RADIX_RBITS=3)
+        out = run_case("radix_append", 17, 60_000, "fewA", 3, seed=0, KC_SPARSE_RADIX_RBITS=2)
+        assert emu_stats(out)[14] >= 1, out
+        run_case("radix_append", 31, 20_000, "dirty", 5, seed=0)
+    finally:
+        del os.environ["KC_SPARSE_RADIX_SHAPE"]
+
+
 def test_sparse_radix_short_run_list_is_counted_again_with_the_exact_size():
     """the temporary run list is sized from an estimate; when it is too short the leaf kernel still reports the number of
     runs and the count is repeated once with exactly that many entries (stat 13), no new scatter, no hash fallback"""

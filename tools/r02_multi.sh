@@ -20,7 +20,7 @@ PY
 SPECS=${SPECS:-config4:0:auto config4:0:hash config5:0:auto config5:0:hash}
 for spec in $SPECS; do
   IFS=: read W RD A <<< "$spec"
-  timeout 240 $R --master-port 29752 bench.py --gpus $N --workload $W --reads $RD --sparse-algo $A --steps 2 --warmup 1 > $O/r02_m${N}${TAG:-}_${W}_${RD}_$A.log 2> $O/r02_m${N}${TAG:-}_${W}_${RD}_$A.err
+  timeout 240 $R --master-port 29752 bench.py --gpus $N --workload $W --reads $RD --sparse-algo $A --steps ${STEPS:-2} --warmup ${WARM:-1} > $O/r02_m${N}${TAG:-}_${W}_${RD}_$A.log 2> $O/r02_m${N}${TAG:-}_${W}_${RD}_$A.err
   echo "$W reads=$RD $A rc=$?"; python - <<PY
 import json
 try:
