@@ -26,12 +26,17 @@ def entry(path):
 def code_state(name):
     """which leaf pass / planning the run had (the file tags are the GPU calls of round 2, in order)"""
     import re
-    m = re.match(r"r02_(c|m|n)(\d+)(b?)_", name)
+    m = re.match(r"r02_(c|m|n)(\d+)([b-z]?)_", name)
     if not m:
         return None
-    kind, num, b = m.group(1), int(m.group(2)), m.group(3)
+    kind, num, b = m.group(1), int(m.group(2)), m.group(3) == "b"
     if kind == "c" and num == 23:
         return "A/B of call 23: distinct-first leaf pass" if "dedupe" in name else "A/B of call 23: record-sort leaf pass"
+    if kind in ("m", "n") and re.match(r"r02_[mn]\d+[c-z]_", name):
+        return "distinct-first leaf pass, warp converged after divergent bodies" + (
+            ", rounds appended through kc_sparse_radix_count_round_append" if re.match(r"r02_[mn]\d+[e-z]_", name) else "")
+    if kind == "c" and num >= 32:
+        return "distinct-first leaf pass, warp converged after divergent bodies, rounds appended on one GPU"
     if (kind == "c" and num >= 24) or b:
         s = "distinct-first leaf pass"
         if kind == "c" and num in (24, 25):
