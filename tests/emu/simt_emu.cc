@@ -272,7 +272,14 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     S.grid = grid;
     S.block = block;
     S.smem_bytes = smem;
-    S.dyn_smem = (char*)aligned_alloc(128, (smem + 255) & ~(size_t)127);
+    // dynamic shared memory ENDS at a guard page (16-byte granular, like the device allocations below): a kernel that
+    // reads or writes past the size its host code asked for dies here with SIGSEGV instead of passing by luck
+    const size_t smem_page = 4096, smem_body = (smem + 15) & ~(size_t)15;
+    const size_t smem_map = ((smem_body + smem_page - 1) & ~(smem_page - 1)) + smem_page;
+    char* smem_base = (char*)mmap(nullptr, smem_map, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (smem_base == (char*)MAP_FAILED) fail("mmap of %zu bytes of shared memory failed", smem_map);
+    mprotect(smem_base + smem_map - smem_page, smem_page, PROT_NONE);
+    S.dyn_smem = smem_base + smem_map - smem_page - smem_body;
     if ((int)S.fibers.size() < tpb) S.fibers.resize(tpb);
     S.warps.assign((tpb + 31) / 32, Warp());
     S.body = &body;
@@ -317,7 +324,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
             }
     S.in_kernel = false;
     S.cur = -1;
-    free(S.dyn_smem);
+    munmap(smem_base, smem_map);
     S.dyn_smem = nullptr;
     S.smem_bytes = 0;
 }

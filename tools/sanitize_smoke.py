@@ -1,4 +1,5 @@
-"""Small run of every kernel family, meant for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`."""
+"""Small run of every kernel family, meant for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`
+(closed on the round-2 pool: there the script only runs plain; tests/emu under AddressSanitizer covers the bounds on the CPU)."""
 import os
 import sys
 
@@ -17,6 +18,18 @@ host = O.gen_genome(7, n, 3, 300, 12, 0, n)
 buf = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
 buf[3:3 + n] = torch.from_numpy(host)
 ptr = buf.data_ptr() + 3  # unaligned on purpose
+# the radix path (scatter, leaf pass with its shared-memory hash table, scan, gather); KC_SPARSE_RADIX_RBITS=2 in the
+# environment adds the round filter and the appended rounds.  SANITIZE_ONLY=radix runs just this part.
+reads = O.gen_reads(11, 40_000, 100, 50, 0, 3000)
+d_reads = torch.from_numpy(reads).cuda()
+for k in (13, 21, 31):
+    keys, counts = ctx.count_sparse(d_reads, reads.size, k, kmerb200.SPARSE_RADIX | kmerb200.SPARSE_NO_FALLBACK).to_host()
+    wk, wc, _ = O.count_sparse(reads, k)
+    assert keys.size == wk.size and (keys == wk).all() and (counts == wc).all(), k
+if os.environ.get("SANITIZE_ONLY") == "radix":
+    print("sanitize_smoke (radix only) ok, launches", ctx.launch_count)
+    ctx.close()
+    sys.exit(0)
 for k, algo in ((3, 0), (7, 0), (8, 0), (10, 2), (12, 2), (12, 1), (13, 0)):
     t = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
     ctx.count_dense_range(ptr, n, 0, n, k, t, algo=algo)
