@@ -780,7 +780,7 @@ def main():
             assert int(h_table.to(torch.int64).sum().item()) == checksum, "e2e table differs from resident-input table"
         # The plain host path is bound by PCIe at 1 byte per base.  kc_count_dense_host_packed packs on the host cores
         # first (0.375 B/base or less over PCIe); whether that wins depends on the cores this process may use, so it
-        # is measured: first in its own process (its kernels' first B200 run is pending), then —
+        # is measured: first in its own process (a failure there must not take the bench line down), then —
         # only if that process reproduced the resident-input table — here, and the faster of the two is reported.
         if world == 1 and not args.no_probe and not os.environ.get("KC_BENCH_NO_PROBE"):
             pk = probe_e2e_packed(args, local)
