@@ -202,7 +202,8 @@ def test_sparse_radix_round_filter(rbits, k):
     try:
         n = 25_000 if rbits < 5 else 6_000  # (2^rbits rounds of 16 x 16 partitions each on the emulator)
         run_case("sparse", k, n, RADIX | NOFB, "dirty", 10 * rbits + k, k % 7, seed=0, KC_SPARSE_RADIX_RBITS=rbits)
-        run_case("sparse", k, n, RADIX | NOFB, "readsU", rbits + k, 0, seed=0, KC_SPARSE_RADIX_RBITS=rbits)
+        if rbits < 8:  # (256 rounds once are enough)
+            run_case("sparse", k, n, RADIX | NOFB, "readsU", rbits + k, 0, seed=0, KC_SPARSE_RADIX_RBITS=rbits)
     finally:
         del os.environ["KC_SPARSE_RADIX_SHAPE"]
 
